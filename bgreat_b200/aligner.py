@@ -1,0 +1,162 @@
+"""Host-side mirror of the reference's `class Aligner` (reference aligner.h:58-179) over the C ABI.
+
+Same vocabulary as the reference: an Aligner is built for (k, errorsMax, tryNumber), indexes unitigs
+(indexUnitigs, aligner.cpp:537) and aligns reads (alignReadGreedy / alignReadExhaustive, aligner.h:127,135)
+-- here a batch at a time on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+class MappingResult:
+    """Per-read results of one batch: flags (uint8), path offsets/lengths and the path pool."""
+
+    def __init__(self, flags_len, path_off, pool):
+        self.flags = (flags_len & 0xFF).astype(np.uint8)
+        self.path_len = (flags_len >> 8).astype(np.uint32)
+        self.path_off = path_off
+        self.pool = pool
+
+    def __len__(self):
+        return len(self.flags)
+
+    def path(self, i):
+        o, n = int(self.path_off[i]), int(self.path_len[i])
+        return [int(x) for x in self.pool[o:o + n]]
+
+    def overlap_found(self, i):
+        return bool(self.flags[i] & A.F_OVERLAP_FOUND)
+
+    def rc(self, i):
+        return bool(self.flags[i] & A.F_RC)
+
+    def mapped(self, i):
+        return bool(self.flags[i] & A.F_MAPPED)
+
+    def as_tuples(self):
+        """[(overlap_found, rc, path)] -- the shape the reference's per-read API returns."""
+        return [(self.overlap_found(i), self.rc(i), self.path(i)) for i in range(len(self))]
+
+
+def _concat(seqs):
+    b = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(b) + 1, dtype=np.uint64)
+    if b:
+        off[1:] = np.cumsum([len(x) for x in b], dtype=np.uint64)
+    return np.frombuffer(b"".join(b) + b"\0", dtype=np.uint8), off
+
+
+class Aligner:
+    """Aligner(k, errors=2, effort=2, device=0): reference ctor arguments kValue, errorsAllowed, effort
+    (aligner.h:80). Modes: greedy (default, `bgreat`), exhaustive (`bgreat -b`)."""
+
+    def __init__(self, k, errors=2, effort=2, device=0, n_slots=2):
+        self.L = A.lib()
+        self.k, self.errors, self.effort = k, errors, effort
+        self.ctx = C.c_void_p()
+        rc = self.L.bgr_ctx_create(device, n_slots, C.byref(self.ctx))
+        if rc:
+            raise A.BgrError(rc, self.L.bgr_last_error(None).decode())
+        self.n_slots = n_slots
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.bgr_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise A.BgrError(rc, self.L.bgr_last_error(self.ctx).decode())
+
+    # ---- index (indexUnitigs, aligner.cpp:537)
+    def index_unitigs(self, unitigs):
+        """unitigs: sequences in file order (ids 1..n)."""
+        buf, off = _concat(unitigs)
+        self._ck(self.L.bgr_index_build(self.ctx, buf.ctypes.data, off.ctypes.data, len(unitigs), self.k))
+
+    def index_unitigs_packed(self, buf, off):
+        """buf: uint8 array of concatenated sequences, off: uint64 array of n+1 offsets."""
+        self._ck(self.L.bgr_index_build(self.ctx, buf.ctypes.data, off.ctypes.data, len(off) - 1, self.k))
+
+    def index_file(self, path):
+        self._ck(self.L.bgr_index_build_file(self.ctx, path.encode(), self.k))
+
+    def index_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bgr_index_stats(self.ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(unitigs=a.value, keys=b.value, device_bytes=c.value)
+
+    def index_blob_size(self):
+        n = C.c_uint64()
+        self._ck(self.L.bgr_index_blob_size(self.ctx, C.byref(n)))
+        return n.value
+
+    def export_index_device(self, dev_ptr, nbytes):
+        self._ck(self.L.bgr_index_export_device(self.ctx, dev_ptr, nbytes))
+
+    def import_index_device(self, dev_ptr, nbytes):
+        self._ck(self.L.bgr_index_import_device(self.ctx, dev_ptr, nbytes))
+
+    def export_index_host(self):
+        n = self.index_blob_size()
+        out = np.empty(n, dtype=np.uint8)
+        self._ck(self.L.bgr_index_export_host(self.ctx, out.ctypes.data, n))
+        return out
+
+    def import_index_host(self, blob):
+        self._ck(self.L.bgr_index_import_host(self.ctx, blob.ctypes.data, blob.nbytes))
+
+    def get_begin(self, code):
+        """getBegin (aligner.cpp:209): signed ids of the unitigs beginning with the (k-1)-mer code."""
+        return self._query(code, 0)
+
+    def get_end(self, code):
+        """getEnd (aligner.cpp:147)."""
+        return self._query(code, 1)
+
+    def _query(self, code, want_end):
+        ids = (C.c_int32 * 4)()
+        n = self.L.bgr_index_query(self.ctx, code, want_end, ids)
+        if n < 0:
+            raise A.BgrError(-n, self.L.bgr_last_error(self.ctx).decode())
+        return list(ids[:n])
+
+    # ---- mapping
+    def params(self, mode):
+        return A.Params(mode, self.errors, self.effort, 0)
+
+    def align_batch(self, reads, mode=A.MODE_GREEDY):
+        """reads: list of str/bytes. -> MappingResult (through bgr_map_batch, host buffers)."""
+        buf, off = _concat(reads)
+        return self.align_packed(buf, off, mode)
+
+    def align_packed(self, buf, off, mode=A.MODE_GREEDY):
+        n = len(off) - 1
+        res = np.zeros((max(n, 1), 2), dtype=np.uint32)
+        cap = max(1024, int(off[-1]) + 2 * n + 16)  # a path never has more ints than the read has bases + 2
+        pool = np.zeros(cap, dtype=np.int32)
+        used = C.c_uint64()
+        p = self.params(mode)
+        self._ck(self.L.bgr_map_batch(self.ctx, buf.ctypes.data, off.ctypes.data, n, C.byref(p), res.ctypes.data,
+                                      pool.ctypes.data, cap, C.byref(used)))
+        return MappingResult(res[:n, 0], res[:n, 1], pool[:used.value])
+
+    def counters(self):
+        out = (C.c_uint64 * A.BGR_C_COUNT)()
+        self._ck(self.L.bgr_counters(self.ctx, out))
+        return dict(zip(A.COUNTER_NAMES, [int(x) for x in out]))
+
+    def reset_counters(self):
+        self._ck(self.L.bgr_counters_reset(self.ctx))
+
+    def launch_count(self):
+        return int(self.L.bgr_launch_count(self.ctx))

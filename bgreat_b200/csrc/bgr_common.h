@@ -1,0 +1,121 @@
+// Shared host/device definitions: 2-bit encoding, the border-index layout and its hash.
+//
+// Data layout (everything lives in ONE flat blob so that it can be exported / broadcast /
+// imported with a single copy, see bgr_index_export_device):
+//
+//   BlobHeader
+//   keys    : u64[n_buckets * 4]      bucketed open addressing, one bucket = 4 keys = one 32-byte
+//                                     DRAM sector; EMPTY_KEY marks a free slot; a key lives in the
+//                                     first bucket at or after hash(key) that had room
+//   payload : Payload[n_buckets * 4]  per key slot: left[4] + right[4] unitig slots (32 bytes),
+//                                     the reference's two unitigIndices tables merged
+//                                     (reference aligner.h:49-55, aligner.cpp:463-533)
+//   meta    : UnitigMeta[n_unitigs+1] first base of the unitig in `pool`, and its length; ids are
+//                                     1-based like the reference's (aligner.cpp:408)
+//   pool    : u64[pool_words]         all unitigs, 2 bits per base, first base in the most
+//                                     significant bits (same digit order as str2num, utils.cpp:117)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BGR_HD __host__ __device__ __forceinline__
+#else
+#define BGR_HD inline
+#endif
+
+namespace bgr {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef int64_t i64;
+typedef int32_t i32;
+
+static const u64 EMPTY_KEY = ~0ull;
+static const u32 SLOT_ID_MASK = 0x3FFFFFFFu;  // unitig ids < 2^30
+// Orientation flags of a slot, decided at build time by the reference's "forward test"
+// (aligner.cpp:174,235): bit 30 answers the query made with the canonical key itself, bit 31 the
+// query made with its reverse complement.
+//   left  table: bit30 = unitig begins with key        (getBegin(key))
+//                bit31 = rc(unitig end) == key          (getEnd(rc(key)))
+//   right table: bit30 = unitig ends with key           (getEnd(key))
+//                bit31 = rc(unitig begin) == key        (getBegin(rc(key)))
+static const u32 SLOT_FWD_CANON = 1u << 30;
+static const u32 SLOT_FWD_RC = 1u << 31;
+
+struct Payload {
+    u32 left[4];
+    u32 right[4];
+};
+
+struct UnitigMeta {
+    u64 start;  // base offset in pool
+    u32 len;    // bases
+    u32 pad;
+};
+
+struct BlobHeader {
+    u64 magic;
+    u32 version;
+    u32 k;
+    u64 n_unitigs;
+    u64 n_keys;
+    u64 n_buckets;
+    u64 pool_words;
+    u64 off_keys, off_payload, off_meta, off_pool;  // byte offsets from the blob start
+    u64 total_bytes;
+};
+static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
+
+// 2-bit code of a base character, A0 C1 G2 T3 (utils.cpp:117-129). Returns 4 for anything else.
+BGR_HD u32 base_code(unsigned char c) {
+    switch (c) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+    }
+    return 4;
+}
+
+// reverse complement of all 32 bases of a word (complement = 3 - code = ~code)
+BGR_HD u64 rc64(u64 x) {
+    x = ~x;
+#if defined(__CUDA_ARCH__)
+    x = __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = __builtin_bswap64(x);
+#endif
+    // the bit reversal also swapped the two bits of every base: swap them back
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+// reverse the order of the 32 two-bit groups (no complement); used for N masks
+BGR_HD u64 rev2(u64 x) { return rc64(~x); }
+
+// rcb(x, n) of the reference (utils.cpp:182-192): reverse complement of an n-base code
+BGR_HD u64 rcb(u64 x, u32 n) { return rc64(x) >> (64 - 2 * n); }
+
+// hash of a canonical (k-1)-mer -> bucket
+BGR_HD u64 key_hash(u64 key) {
+    key ^= key >> 29;
+    key *= 0x9E3779B97F4A7C15ull;
+    key ^= key >> 32;
+    return key * 0xD6E8FEB86659FD93ull;
+}
+BGR_HD u64 bucket_of(u64 key, u64 n_buckets) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(key_hash(key), n_buckets);
+#else
+    return (u64)(((unsigned __int128)key_hash(key) * n_buckets) >> 64);
+#endif
+}
+
+// word offset of read r's packed words inside a batch whose reads are concatenated characters:
+// read r occupies chars [o, o') and gets ceil(len/32)+2 words (one zero pad word in front, one
+// behind); floor(o/32) + 3r is a closed form that leaves at least that much room.
+BGR_HD u64 read_word_base(u64 char_off, u64 r) { return (char_off >> 5) + 3 * r; }
+
+}  // namespace bgr

@@ -1,0 +1,338 @@
+// Host side of the mapping path: reader semantics, unitig loading, index blob construction.
+#include "bgr_host.h"
+
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+
+#include "../../include/bgreat_b200.h"
+
+namespace bgr {
+
+// ------------------------------------------------------------------------------ LineStream
+
+void LineStream::getline(std::string& s) {
+    if (!good()) {  // sentry fails: failbit, string untouched
+        fail_ = true;
+        return;
+    }
+    s.clear();
+    const char* p;
+    size_t len;
+    if (getline_view(p, len)) s.assign(p, len);
+}
+
+bool LineStream::getline_view(const char*& p, size_t& len) {
+    if (!good()) {
+        fail_ = true;
+        return false;
+    }
+    p = d_ + pos_;
+    if (pos_ >= n_) {  // nothing extracted at all: eofbit and failbit, string erased
+        eof_ = true;
+        fail_ = true;
+        len = 0;
+        return true;
+    }
+    const char* nl = (const char*)memchr(p, '\n', n_ - pos_);
+    if (nl) {
+        len = (size_t)(nl - p);
+        pos_ += len + 1;
+    } else {  // ran into the end of input: eofbit only
+        len = n_ - pos_;
+        pos_ = n_;
+        eof_ = true;
+    }
+    return true;
+}
+
+int LineStream::peek() {
+    if (!good()) return -1;
+    if (pos_ >= n_) {
+        eof_ = true;
+        return -1;
+    }
+    return (unsigned char)d_[pos_];
+}
+
+// ------------------------------------------------------------------------------ MappedFile
+
+bool MappedFile::open(const char* path) {
+    close();
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+        // not a regular file (pipe, /dev/stdin ...): slurp it
+        std::string* buf = new std::string();
+        char tmp[1 << 16];
+        ssize_t r;
+        while ((r = ::read(fd, tmp, sizeof tmp)) > 0) buf->append(tmp, (size_t)r);
+        ::close(fd);
+        fd = -2;
+        data = buf->data();
+        size = buf->size();
+        ok = true;
+        // ownership of buf is kept until close(); stash the pointer behind data via a side table
+        // (simple: leak-free because close() reconstructs it from data)
+        slurped_ = buf;
+        return true;
+    }
+    size = (size_t)st.st_size;
+    if (size == 0) {
+        data = "";
+        ok = true;
+        return true;
+    }
+    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) {
+        ::close(fd);
+        fd = -1;
+        return false;
+    }
+    madvise(m, size, MADV_SEQUENTIAL);
+    data = (const char*)m;
+    ok = true;
+    return true;
+}
+
+void MappedFile::close() {
+    if (slurped_) {
+        delete (std::string*)slurped_;
+        slurped_ = nullptr;
+    } else if (ok && size > 0 && data) {
+        munmap((void*)data, size);
+    }
+    if (fd >= 0) ::close(fd);
+    fd = -1;
+    data = nullptr;
+    size = 0;
+    ok = false;
+}
+
+// ------------------------------------------------------------------------------ unitigs
+
+bool load_unitig_file(const char* path, uint32_t k, std::string& seqs, std::vector<uint64_t>& off) {
+    seqs.clear();
+    off.assign(1, 0);
+    MappedFile f;
+    bool opened = f.open(path);
+    LineStream s(f.data, f.size, opened);
+    // Both getlines of a record write the same string in the reference, so a failed second
+    // getline leaves the HEADER text in it: keep one string to reproduce that.
+    std::string line;
+    while (!s.eof()) {
+        s.getline(line);
+        s.getline(line);
+        if (line.size() < k) break;
+        seqs += line;
+        off.push_back(seqs.size());
+    }
+    return opened;
+}
+
+static inline u64 pool_bases(const u64* pool, u64 p, u32 n) {
+    // n (1..32) bases starting at base p, right-aligned (str2num value)
+    u64 w = p >> 5;
+    u32 s = (u32)(p & 31) * 2;
+    u64 hi = pool[w], lo = pool[w + 1];
+    u64 x = (hi << s) | ((lo >> 1) >> (63 - s));
+    return x >> (64 - 2 * n);
+}
+
+namespace {
+struct KeyRef {
+    u64 key;
+    u32 id;       // unitig id
+    u32 side_flg;  // bit0: 1 = right table; bits 30/31: orientation flags for the slot
+};
+}  // namespace
+
+int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t k, std::vector<uint64_t>& blob,
+                     std::string& err) {
+    if (k < 2 || k > 32) {
+        err = "k must be in [2,32] (kmer is a 64-bit word in the reference, utils.h:27)";
+        return BGR_ERR_ARG;
+    }
+    // accepted unitigs: up to the first one shorter than k (aligner.cpp:418)
+    u64 nu = 0, total_bases = 0;
+    for (; nu < n; ++nu) {
+        u64 len = off[nu + 1] - off[nu];
+        if (len < k) break;
+        if (len > 0xFFFFFFFFull) {
+            err = "unitig longer than 2^32-1 bases";
+            return BGR_ERR_LIMIT;
+        }
+        total_bases += len;
+    }
+    if (nu >= SLOT_ID_MASK) {
+        err = "more than 2^30-1 unitigs";
+        return BGR_ERR_LIMIT;
+    }
+    const u64 pool_words = (total_bases + 31) / 32 + 2;  // + lookahead padding
+
+    // ---- pack + per-unitig border codes
+    std::vector<u64> pool(pool_words, 0);
+    std::vector<UnitigMeta> meta(nu + 1);
+    meta[0].start = 0;
+    meta[0].len = 0;
+    meta[0].pad = 0;
+    u64 base = 0;
+    for (u64 i = 0; i < nu; ++i) {
+        const char* s = seqs + off[i];
+        u32 len = (u32)(off[i + 1] - off[i]);
+        meta[i + 1].start = base;
+        meta[i + 1].len = len;
+        meta[i + 1].pad = 0;
+        for (u32 j = 0; j < len; ++j) {
+            u32 c = base_code((unsigned char)s[j]);
+            if (c > 3) {
+                err = "unitig " + std::to_string(i + 1) + " contains a character outside ACGT";
+                return BGR_ERR_FORMAT;
+            }
+            u64 p = base + j;
+            pool[p >> 5] |= (u64)c << (62 - 2 * (p & 31));
+        }
+        base += len;
+    }
+
+    // ---- key occurrences in file order (aligner.cpp:466-533)
+    std::vector<KeyRef> refs;
+    refs.reserve(2 * nu);
+    for (u64 i = 1; i <= nu; ++i) {
+        u64 beg = pool_bases(pool.data(), meta[i].start, k - 1);
+        u64 end = pool_bases(pool.data(), meta[i].start + meta[i].len - (k - 1), k - 1);
+        u64 rcbeg = rcb(beg, k - 1), rcend = rcb(end, k - 1);
+        KeyRef a, b;
+        a.id = b.id = (u32)i;
+        if (beg <= rcbeg) {  // left[beg]
+            a.key = beg;
+            a.side_flg = 0u | SLOT_FWD_CANON /* begins with key */ | (rcend == beg ? SLOT_FWD_RC : 0u);
+        } else {  // right[rcbeg]
+            a.key = rcbeg;
+            a.side_flg = 1u | SLOT_FWD_RC /* rc(begin) == key */ | (end == rcbeg ? SLOT_FWD_CANON : 0u);
+        }
+        if (end <= rcend) {  // right[end]
+            b.key = end;
+            b.side_flg = 1u | SLOT_FWD_CANON /* ends with key */ | (rcbeg == end ? SLOT_FWD_RC : 0u);
+        } else {  // left[rcend]
+            b.key = rcend;
+            b.side_flg = 0u | SLOT_FWD_RC /* rc(end) == key */ | (beg == rcend ? SLOT_FWD_CANON : 0u);
+        }
+        refs.push_back(a);
+        refs.push_back(b);
+    }
+
+    // ---- distinct keys
+    std::vector<u64> keys(refs.size());
+    for (size_t i = 0; i < refs.size(); ++i) keys[i] = refs[i].key;
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const u64 n_keys = keys.size();
+    const u64 n_buckets = std::max<u64>(4, (n_keys + 1) / 2);  // <= 50% load: 2 of 4 slots on average
+
+    // ---- blob
+    BlobHeader h;
+    memset(&h, 0, sizeof h);
+    h.magic = BLOB_MAGIC;
+    h.version = 1;
+    h.k = k;
+    h.n_unitigs = nu;
+    h.n_keys = n_keys;
+    h.n_buckets = n_buckets;
+    h.pool_words = pool_words;
+    auto align_up = [](u64 x) { return (x + 255) & ~255ull; };
+    h.off_keys = align_up(sizeof(BlobHeader));
+    h.off_payload = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
+    h.off_meta = align_up(h.off_payload + n_buckets * 4 * sizeof(Payload));
+    h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
+    h.total_bytes = align_up(h.off_pool + pool_words * sizeof(u64));
+    blob.assign(h.total_bytes / 8, 0);
+    char* B = (char*)blob.data();
+    memcpy(B, &h, sizeof h);
+    u64* tkeys = (u64*)(B + h.off_keys);
+    Payload* tpay = (Payload*)(B + h.off_payload);
+    memcpy(B + h.off_meta, meta.data(), (nu + 1) * sizeof(UnitigMeta));
+    memcpy(B + h.off_pool, pool.data(), pool_words * sizeof(u64));
+    for (u64 i = 0; i < n_buckets * 4; ++i) tkeys[i] = EMPTY_KEY;
+
+    auto find_or_insert = [&](u64 key, bool insert) -> u64 {
+        u64 b = bucket_of(key, n_buckets);
+        for (;;) {
+            u64* bk = tkeys + b * 4;
+            for (int j = 0; j < 4; ++j) {
+                if (bk[j] == key) return b * 4 + j;
+                if (bk[j] == EMPTY_KEY) {
+                    if (!insert) return ~0ull;
+                    bk[j] = key;
+                    return b * 4 + j;
+                }
+            }
+            if (++b == n_buckets) b = 0;
+        }
+    };
+    for (u64 i = 0; i < n_keys; ++i) find_or_insert(keys[i], true);
+
+    // ---- slot fill in file order: first free of 4, the 5th and later overwrite slot 4
+    // (aligner.cpp:481-489)
+    for (size_t i = 0; i < refs.size(); ++i) {
+        u64 slot = find_or_insert(refs[i].key, false);
+        u32* s = (refs[i].side_flg & 1u) ? tpay[slot].right : tpay[slot].left;
+        u32 v = refs[i].id | (refs[i].side_flg & (SLOT_FWD_CANON | SLOT_FWD_RC));
+        if (s[0] == 0) s[0] = v;
+        else if (s[1] == 0) s[1] = v;
+        else if (s[2] == 0) s[2] = v;
+        else s[3] = v;
+    }
+    return BGR_OK;
+}
+
+// ------------------------------------------------------------------------------ reads
+
+static inline bool acgtn_only(const std::string& r) {
+    for (char c : r)
+        if (c != 'A' && c != 'C' && c != 'T' && c != 'G' && c != 'N') return false;
+    return true;
+}
+
+void ReadParser::next_chunk(uint32_t n, ReadBatch& out) {
+    // The three strings are locals of getReads: fresh on every call (this is what makes the FASTQ
+    // phantom read depend on where the 10000-read chunk boundaries fall).
+    std::string read, header, inter;
+    if (fastq_) {
+        for (uint32_t i = 0; i < n; ++i) {
+            s_.getline(header);
+            s_.getline(read);
+            if (read.size() > 2 && acgtn_only(read)) out.push(header.data(), header.size(), read.data(), read.size());
+            s_.getline(header);
+            s_.getline(header);
+            if (s_.eof()) return;
+        }
+    } else {
+        for (uint32_t i = 0; i < n; ++i) {
+            s_.getline(header);
+            s_.getline(read);
+            for (;;) {
+                int c = s_.peek();
+                if (c == '>') {
+                    if (read.size() > 2 && acgtn_only(read) && read.size() > k_)
+                        out.push(header.data(), header.size(), read.data(), read.size());
+                    break;
+                } else if (!s_.eof()) {
+                    s_.getline(inter);
+                    read += inter;
+                } else {
+                    if (read.size() > 2 && acgtn_only(read) && read.size() > k_)
+                        out.push(header.data(), header.size(), read.data(), read.size());
+                    return;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace bgr

@@ -1,0 +1,916 @@
+// sm_100a kernels of the read-to-graph mapping path.
+//
+//   k_pack_scan     warp per read: ASCII -> 2-bit words (+ N mask), then the seed scan: every
+//                   (k-1)-mer window of the read is canonicalised and probed in the border index
+//                   with one 256-bit load per probe (one 32-byte sector). Replaces getNOverlap /
+//                   getListOverlap + the BooPHF lookups (reference aligner.cpp:318-378,
+//                   BooPHF.h:783). Output: a hit bitmask per read.
+//   k_extend_greedy thread per read: alignReadGreedy and its four walkers (reference
+//                   alignerGreedy.cpp:35-57,167-364) on packed words, mismatches by XOR + popc.
+//   k_extend_exhaustive  thread per read: alignReadExhaustive / alignReadExhaustivePath
+//                   (alignerExhaustive.cpp:35-259, alignerPaths.cpp:66-88,127-175,289-460) as an
+//                   iterative branch-and-bound depth-first search.
+//
+// The per-read bodies are __host__ __device__ so that tests/emu can single-step the very same
+// code on the CPU (there is no GPU in the build container). The product never runs them on the
+// host: libbgreat_b200.so only ever launches the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bgreat_b200.h"
+#include "bgr_common.h"
+
+namespace bgr {
+
+#if defined(__CUDA_ARCH__)
+#define BGR_POPCLL(x) __popcll(x)
+#define BGR_FFS(x) __ffs(x)
+#define BGR_CLZ(x) __clz(x)
+#else
+#define BGR_POPCLL(x) __builtin_popcountll(x)
+#define BGR_FFS(x) __builtin_ffs(x)
+#define BGR_CLZ(x) __builtin_clz(x)
+#endif
+
+struct DevIndex {
+    const u64* keys;
+    const Payload* payload;
+    const UnitigMeta* meta;
+    const u64* pool;
+    u64 n_buckets;
+    u32 k;
+    u32 pad;
+};
+
+struct DevCounters {
+    unsigned long long pool_cursor;
+    unsigned long long c[BGR_C_COUNT];
+    u32 scratch_overflow;  // some path / search stack did not fit the per-read scratch
+    u32 pool_overflow;     // the path pool was too small (pool_cursor = ints needed)
+    u32 pad[2];
+};
+
+struct BatchArgs {
+    const char* seq;  // concatenated read characters
+    const u64* off;   // n+1 character offsets
+    u32 n;
+    u64* F;     // 2-bit words, per read: [pad][ceil(len/32) data words][pad], see read_word_base
+    u64* NM;    // N mask in the same layout (0b11 per non-ACGT base); written only for reads with N
+    u32* H1;    // hit mask of the forward scan, bit i of word (i/32): window i is a border
+    u32* H2;    // hit mask for the scan of the reverse-complemented read (only for reads with N)
+    u32* info;  // per read: bit0 has N, bit1 any H1 hit, bit2 any H2 hit
+    bgr_result* res;
+    i32* scratch;  // n * scratch_ints, interleaved (entry j of read r at scratch[j*n + r])
+    u32 scratch_ints;
+    i32* pool;
+    u64 pool_cap;
+    DevCounters* cnt;
+    u32 errors, effort, mode;
+};
+
+static const u32 INFO_HAS_N = 1u, INFO_HIT1 = 2u, INFO_HIT2 = 4u;
+
+// ------------------------------------------------------------------------------ helpers
+
+struct __align__(32) u64x4 {
+    u64 a, b, c, d;
+};
+
+// one 32-byte sector = one bucket of 4 keys, read-only path
+BGR_HD u64x4 ld_bucket(const u64* p) {
+    u64x4 r;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+#else
+    r.a = p[0];
+    r.b = p[1];
+    r.c = p[2];
+    r.d = p[3];
+#endif
+    return r;
+}
+
+// 32 bases starting at base p (left-aligned). W[p/32 + 1] must be readable.
+BGR_HD u64 ld_bases(const u64* W, i64 p) {
+    i64 w = p >> 5;
+    u32 s = (u32)(p & 31) * 2;
+    u64 hi = W[w], lo = W[w + 1];
+    return (hi << s) | ((lo >> 1) >> (63 - s));
+}
+
+// slot index of `key`, or -1. A key lives in the first bucket at/after its home bucket that had a
+// free slot when it was inserted; slots of a bucket fill in order, so "last slot empty" ends the probe.
+BGR_HD i64 index_find(const DevIndex& ix, u64 key) {
+    u64 b = bucket_of(key, ix.n_buckets);
+    for (;;) {
+        u64x4 v = ld_bucket(ix.keys + b * 4);
+        if (v.a == key) return (i64)(b * 4);
+        if (v.b == key) return (i64)(b * 4 + 1);
+        if (v.c == key) return (i64)(b * 4 + 2);
+        if (v.d == key) return (i64)(b * 4 + 3);
+        if (v.d == EMPTY_KEY) return -1;
+        if (++b == ix.n_buckets) b = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------ pack + seed scan
+
+static const int PS_WARPS = 8;    // warps per block
+static const int PS_SWORDS = 20;  // shared words per warp and array: reads up to 576 bases stay on chip
+
+// 4 characters (one 32-bit word, first character in the low byte) -> 8 bits of 2-bit codes (first
+// character most significant) and 8 bits of N mask (0b11 per character that is not A/C/G/T; in the
+// reference every such character behaves like N: str2num -> 3, nuc2int/nuc2intrc -> 0,
+// revCompChar -> 'A', and it never equals a unitig character).
+BGR_HD void pack4(u32 x, u32& code8, u32& nm8) {
+    // A=0x41 C=0x43 G=0x47 T=0x54: ((c>>1)^(c>>2))&3 = 0,1,2,3
+    u32 t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+    // expected character for that code: 0x41 + {0,2,6,0x13}
+    u32 b0 = t & 0x01010101u, b1 = (t >> 1) & 0x01010101u;
+    u32 expect = 0x41414141u + 2u * b0 + 6u * b1 + 11u * (b0 & b1);
+    u32 d = x ^ expect;
+    // 0x80 in every byte of d that is non-zero
+    u32 nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    u32 n3 = (nz >> 7) * 3u;  // 0 or 3 per byte
+    t &= ~n3;                 // non-ACGT encodes as 0 (the rolling encoders' default, utils.cpp:132-151)
+    // gather the four 2-bit fields: byte0 -> bits 7:6 ... byte3 -> bits 1:0
+    code8 = (t * 0x40100401u) >> 24;
+    nm8 = (n3 * 0x40100401u) >> 24;
+}
+
+// byte of the packed arrays that holds characters [c0, c0+4) of a read (c0 % 4 == 0): word 0 is the
+// front pad, bases are big-endian inside a word
+BGR_HD u32 packed_byte(u32 c0) { return 8 * (1 + (c0 >> 5)) + 7 - ((c0 >> 2) & 7); }
+
+// Seed-scan test for window i (bases [i, i+k-1)) of a read: is its canonical (k-1)-mer a unitig
+// border? D / ND: data words of the read (D[-1] is the front pad).
+//   greedy modes: getNOverlap's rolling encoders (aligner.cpp:345-378). The forward code takes N as
+//     3 in the first window (str2num) and as 0 when rolled in later (nuc2int), i.e. N reads 3 only at
+//     absolute positions < k-1; the rolling RC stream takes N as 3 everywhere (nuc2intrc default 0 =
+//     complement of 3). hit1 is that test; hit2 is the test for the same window of the
+//     reverse-complemented read (N->A, utils.cpp:52-73), needed only when the read has N.
+//   exhaustive modes: getListOverlap stores the same forward code; getBegin/getEnd canonicalise it
+//     with a true rcb (aligner.cpp:149,211), so hit1 tests min(num, rcb(num)).
+BGR_HD void scan_window(const DevIndex& ix, const u64* D, const u64* ND, bool anyN, bool exhaustive, u32 i,
+                        bool& hit1, bool& hit2) {
+    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
+    u64 x0 = ld_bases(D, i) >> sh;
+    u64 num = x0, x2 = x0;
+    if (anyN) {
+        u64 nm = ld_bases(ND, i) >> sh;
+        x2 = x0 | nm;
+        u64 first = (i < km1) ? (nm & ~((1ull << (2 * i)) - 1)) : 0ull;
+        num = x0 | first;
+    }
+    u64 rc = rcb(exhaustive ? num : x2, km1);
+    u64 rep = num < rc ? num : rc;
+    hit1 = index_find(ix, rep) >= 0;
+    hit2 = false;
+    if (anyN && !exhaustive) {
+        u64 rep2 = x2 < rc ? x2 : rc;
+        hit2 = (rep2 == rep) ? hit1 : (index_find(ix, rep2) >= 0);
+    }
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(PS_WARPS * 32) k_pack_scan(DevIndex ix, BatchArgs a) {
+    __shared__ u64 sF[PS_WARPS][PS_SWORDS];
+    __shared__ u64 sN[PS_WARPS][PS_SWORDS];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 nwarps = gridDim.x * PS_WARPS;
+    const u32 km1 = ix.k - 1;
+    const bool exhaustive = a.mode != BGR_MODE_GREEDY;
+    unsigned long long windows = 0;
+
+    for (u32 r = blockIdx.x * PS_WARPS + warp; r < a.n; r += nwarps) {
+        const u64 o = a.off[r];
+        const u32 len = (u32)(a.off[r + 1] - o);
+        const u64 wb = read_word_base(o, r);
+        const u32 nw = (len + 31) >> 5;
+        const bool on_chip = nw + 2 <= (u32)PS_SWORDS;
+        u64* gF = a.F + wb;
+        u64* gN = a.NM + wb;
+        u64* F = on_chip ? sF[warp] : gF;
+        u64* N = on_chip ? sN[warp] : gN;
+        __syncwarp();  // the previous read's shared words are no longer in use
+        if (lane == 0) {  // pad words, front and back
+            F[0] = 0;
+            N[0] = 0;
+            F[nw + 1] = 0;
+            N[nw + 1] = 0;
+        }
+        // ---- pack: 128 characters per pass, 4 per lane
+        const unsigned char* src = (const unsigned char*)a.seq + o;
+        bool anyN = false;
+        for (u32 base = 0; base < nw * 32; base += 128) {
+            u32 c0 = base + 4 * lane;
+            if (c0 < nw * 32) {
+                u32 x = 0x41414141u;
+                if (c0 < len) {
+                    // unaligned 4-byte load out of two aligned words
+                    uintptr_t ad = (uintptr_t)(src + c0);
+                    const u32* wp = (const u32*)(ad & ~(uintptr_t)3);
+                    u32 bs = (u32)(ad & 3) * 8;
+                    u32 w0 = __ldg(wp), w1 = bs ? __ldg(wp + 1) : 0u;
+                    x = __funnelshift_r(w0, w1, bs);
+                    u32 left = len - c0;  // characters of this word that belong to the read
+                    if (left < 4) {
+                        u32 keep = (1u << (8 * left)) - 1;
+                        x = (x & keep) | (0x41414141u & ~keep);
+                    }
+                }
+                u32 code8, nm8;
+                pack4(x, code8, nm8);
+                u32 byte = packed_byte(c0);
+                ((unsigned char*)F)[byte] = (unsigned char)code8;
+                ((unsigned char*)N)[byte] = (unsigned char)nm8;
+                anyN |= nm8 != 0;
+            }
+        }
+        anyN = __any_sync(0xFFFFFFFFu, anyN);
+        __syncwarp();
+        if (on_chip) {
+            for (u32 j = lane; j < nw + 2; j += 32) {
+                gF[j] = F[j];
+                if (anyN) gN[j] = N[j];
+            }
+        } else {
+            __threadfence_block();
+            __syncwarp();
+        }
+        // ---- seed scan
+        const u64* D = F + 1;
+        const u64* ND = N + 1;
+        const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
+        u32 any1 = 0, any2 = 0;
+        for (u32 base = 0; base < nwin; base += 32) {
+            u32 i = base + lane;
+            bool hit1 = false, hit2 = false;
+            if (i < nwin) scan_window(ix, D, ND, anyN, exhaustive, i, hit1, hit2);
+            u32 m1 = __ballot_sync(0xFFFFFFFFu, hit1);
+            any1 |= m1;
+            if (lane == 0) a.H1[wb + (base >> 5)] = m1;
+            if (anyN) {
+                u32 m2 = __ballot_sync(0xFFFFFFFFu, hit2);
+                any2 |= m2;
+                if (lane == 0) a.H2[wb + (base >> 5)] = m2;
+            }
+        }
+        if (lane == 0) {
+            a.info[r] = (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
+            windows += nwin;
+        }
+    }
+    if (lane == 0 && windows) atomicAdd(&a.cnt->c[BGR_C_WINDOWS], windows);
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------ extension: shared pieces
+
+// One pass over a read: pass 0 is the read as given (N mismatches everything: missmatchNumber
+// compares characters, utils.cpp:154); pass 1 is reverseComplements(read) (utils.cpp:66), in which
+// every N has become 'A'. Both are views of the same stored words:
+//   pass 0 sequence  = F0 (N->0) with mask NM
+//   pass 1 sequence  = reverse complement of F2 = F0|NM (N->3), no mask
+struct ReadView {
+    const u64* D;   // data words (D[-1] and D[nw] are zero pads)
+    const u64* ND;  // N mask words
+    i32 len;
+    bool hasN;
+    bool pass;
+};
+
+struct Oriented {
+    u64 start;  // first base of the FORWARD unitig in the pool
+    i64 len;
+    i32 sid;  // signed id: negative = reverse complemented
+    bool rc;
+};
+
+struct Cands {
+    u32 raw[4];
+    int n;
+    u32 fwd_bit;
+};
+
+// getBegin / getEnd (aligner.cpp:147-267)
+BGR_HD Cands index_query(const DevIndex& ix, u64 bin, bool want_end) {
+    Cands c;
+    c.n = 0;
+    c.fwd_bit = 0;
+    u64 rc = rcb(bin, ix.k - 1);
+    bool canon = bin <= rc;
+    i64 slot = index_find(ix, canon ? bin : rc);
+    if (slot < 0) return c;
+    // getEnd: canonical -> right table, else left; getBegin: canonical -> left, else right
+    bool right = (want_end == canon);
+    const u32* p = right ? ix.payload[slot].right : ix.payload[slot].left;
+#if defined(__CUDA_ARCH__)
+    uint4 v = __ldg((const uint4*)p);
+    c.raw[0] = v.x;
+    c.raw[1] = v.y;
+    c.raw[2] = v.z;
+    c.raw[3] = v.w;
+#else
+    for (int j = 0; j < 4; ++j) c.raw[j] = p[j];
+#endif
+    c.fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+    // slots are scanned in order up to the first empty one (aligner.cpp:172-203)
+    while (c.n < 4 && (c.raw[c.n] & SLOT_ID_MASK) != 0) ++c.n;
+    return c;
+}
+
+BGR_HD Oriented orient(const DevIndex& ix, const Cands& c, int i) {
+    Oriented u;
+    u32 id = c.raw[i] & SLOT_ID_MASK;
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 m = __ldg((const ulonglong2*)&ix.meta[id]);
+    u.start = m.x;
+    u.len = (i64)(u32)m.y;
+#else
+    u.start = ix.meta[id].start;
+    u.len = ix.meta[id].len;
+#endif
+    u.rc = (c.raw[i] & c.fwd_bit) == 0;
+    u.sid = u.rc ? -(i32)id : (i32)id;
+    return u;
+}
+
+// str2num of the first / last k-1 bases of the oriented unitig
+BGR_HD u64 first_code(const DevIndex& ix, const Oriented& u) {
+    u32 km1 = ix.k - 1;
+    if (!u.rc) return ld_bases(ix.pool, (i64)u.start) >> (64 - 2 * km1);
+    return rcb(ld_bases(ix.pool, (i64)u.start + u.len - km1) >> (64 - 2 * km1), km1);
+}
+BGR_HD u64 last_code(const DevIndex& ix, const Oriented& u) {
+    u32 km1 = ix.k - 1;
+    if (!u.rc) return ld_bases(ix.pool, (i64)u.start + u.len - km1) >> (64 - 2 * km1);
+    return rcb(ld_bases(ix.pool, (i64)u.start) >> (64 - 2 * km1), km1);
+}
+
+// missmatchNumber (utils.cpp:154-168) between n bases of the oriented unitig starting at upos and n
+// bases of the pass's read starting at rpos; the value is capped at cap+1 like the reference's
+// early exit. XOR + popc on 2-bit words, N mask ORed in.
+BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+    // forward pool coordinates of the unitig segment, stored coordinates of the read segment
+    const i64 ua = (i64)u.start + (u.rc ? u.len - upos - n : upos);
+    const i32 sa = v.pass ? v.len - rpos - n : rpos;
+    const bool flip = u.rc != v.pass;    // the read segment is reverse-complemented before comparing
+    const bool orN = v.pass && v.hasN;   // pass 1 sequence is F0|NM
+    const bool useM = !v.pass && v.hasN;  // pass 0 carries the N mask
+    u32 miss = 0;
+    for (i32 done = 0; done < n; done += 32) {
+        const i32 m = (n - done < 32) ? n - done : 32;
+        u64 xu = ld_bases(ix.pool, ua + done);
+        u64 xr, nm = 0;
+        if (!flip) {
+            xr = ld_bases(v.D, sa + done);
+            if (orN) xr |= ld_bases(v.ND, sa + done);
+            if (useM) nm = ld_bases(v.ND, sa + done);
+        } else {
+            const i32 a = sa + n - done - m;
+            u64 y = ld_bases(v.D, a);
+            if (orN) y |= ld_bases(v.ND, a);
+            xr = rc64(y) << (64 - 2 * m);
+            if (useM) nm = rev2(ld_bases(v.ND, a)) << (64 - 2 * m);
+        }
+        u64 d = xu ^ xr;
+        d = (d | (d >> 1) | nm) & 0x5555555555555555ull;
+        if (m < 32) d &= ~(~0ull >> (2 * m));
+        miss += (u32)BGR_POPCLL(d);
+        if (miss > cap) return cap + 1;
+    }
+    return miss;
+}
+
+// forward code of window i of the pass's read, as the seed scans store it
+// (getNOverlap / getListOverlap push `num`, aligner.cpp:326,354)
+BGR_HD u64 seed_code(const DevIndex& ix, const ReadView& v, i32 i) {
+    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
+    if (!v.pass) {
+        u64 x = ld_bases(v.D, i) >> sh;
+        if (v.hasN && (u32)i < km1) {
+            u64 nm = ld_bases(v.ND, i) >> sh;
+            x |= nm & ~((1ull << (2 * i)) - 1);
+        }
+        return x;
+    }
+    i32 j = v.len - (i32)km1 - i;  // same window in stored coordinates
+    u64 x = ld_bases(v.D, j);
+    if (v.hasN) x |= ld_bases(v.ND, j);
+    return rcb(x >> sh, km1);
+}
+
+// per-read scratch: entry j of this read is base[j*stride]
+struct Scratch {
+    i32* base;
+    u32 stride, cap;
+    bool overflow;
+    BGR_HD void set(u32 j, i32 x) {
+        if (j < cap) base[(size_t)j * stride] = x;
+        else overflow = true;
+    }
+    BGR_HD i32 get(u32 j) const { return j < cap ? base[(size_t)j * stride] : 0; }
+};
+
+// Iterator over the seed windows of one pass in the order the reference visits them. Pass 0 walks
+// the set bits of the hit mask upwards. The windows of the reverse-complemented read are the same
+// (k-1)-mers mirrored, so pass 1 walks the stored bits downwards (of H2 when the read has N: its RC
+// copy has none and is scanned with the plain encoders). Positions are returned in pass coordinates.
+struct SeedIter {
+    const u32* H;
+    i32 nwin, lim, cur;
+    bool down;
+    BGR_HD void init(const u32* h, i32 nwin_, bool down_, i32 lim_) {
+        H = h;
+        nwin = nwin_;
+        down = down_;
+        cur = 0;
+        lim = lim_ < nwin_ ? lim_ : nwin_;
+    }
+    BGR_HD i32 next() {
+        while (cur < lim) {
+            i32 j = down ? nwin - 1 - cur : cur;
+            if (!down) {
+                u32 w = H[j >> 5] >> (j & 31);
+                if (w == 0) {
+                    cur += 32 - (j & 31);
+                    continue;
+                }
+                cur += BGR_FFS(w) - 1;
+            } else {
+                u32 w = H[j >> 5] << (31 - (j & 31));
+                if (w == 0) {
+                    cur += (j & 31) + 1;
+                    continue;
+                }
+                cur += BGR_CLZ(w);
+            }
+            if (cur >= lim) return -1;
+            return cur++;
+        }
+        return -1;
+    }
+};
+
+// ------------------------------------------------------------------------------ greedy extension
+
+// checkBeginGreedy == mapOnLeftEndGreedy (alignerGreedy.cpp:268-319,167-218), tail recursion
+// unrolled into a loop. Pushes to sc[n...]; returns false when the walk fails.
+BGR_HD bool greedy_left(const DevIndex& ix, const ReadView& v, u64 code, i32 pos, u32 budget, Scratch& sc, u32& n,
+                        u32& total) {
+    const i64 km1 = ix.k - 1;
+    u32 acc = 0;
+    for (;;) {
+        if (pos == 0) {
+            sc.set(n++, 0);
+            total = acc;
+            return true;
+        }
+        Cands c = index_query(ix, code, true);
+        u32 best = budget + 1;
+        i32 best_sid = 0, offset = 0;
+        bool ended = false, stepped = false;
+        u64 next_code = 0;
+        i64 next_L = 0;
+        for (int i = 0; i < c.n; ++i) {
+            Oriented u = orient(ix, c, i);
+            const i64 L = u.len - km1;  // bases left of the overlap
+            if (L >= pos) {
+                u32 miss = mismatches(ix, v, u, L - pos, 0, pos, budget);
+                if (miss == 0) {  // accepted at once (quirk 9)
+                    sc.set(n++, u.sid);
+                    sc.set(n++, (i32)(L - pos));
+                    total = acc;
+                    return true;
+                } else if (miss < best) {
+                    best = miss;
+                    best_sid = u.sid;
+                    ended = true;
+                    offset = (i32)(L - pos);
+                }
+            } else {
+                u32 miss = mismatches(ix, v, u, 0, pos - (i32)L, (i32)L, budget);
+                if (miss == 0) {
+                    sc.set(n++, u.sid);
+                    code = first_code(ix, u);
+                    pos -= (i32)L;
+                    stepped = true;  // continue the walk with the budget untouched
+                    break;
+                } else if (miss < best) {
+                    ended = false;
+                    best = miss;
+                    best_sid = u.sid;
+                    next_L = L;
+                    next_code = first_code(ix, u);
+                }
+            }
+        }
+        if (stepped) continue;
+        if (best > budget) return false;
+        sc.set(n++, best_sid);
+        if (ended) {
+            sc.set(n++, offset);
+            total = acc + best;
+            return true;
+        }
+        acc += best;
+        budget -= best;
+        code = next_code;
+        pos -= (i32)next_L;
+    }
+}
+
+// checkEndGreedy (first step, alignerGreedy.cpp:322-364) then mapOnRightEndGreedy (:221-265).
+// In the first step comparisons start after the anchor overlap; in later steps the remaining read
+// starts AT the overlap and the whole unitig is compared, so mismatches inside an overlap count
+// again (quirk 8).
+BGR_HD bool greedy_right(const DevIndex& ix, const ReadView& v, u64 code, i32 pos, u32 budget, Scratch& sc, u32& n,
+                         u32& total) {
+    const i64 km1 = ix.k - 1;
+    u32 acc = 0;
+    bool first = true;
+    for (;;) {
+        // first: readLeft = read[pos+k-1:], later: readLeft = read[pos:]
+        const i32 rstart = first ? pos + (i32)km1 : pos;
+        const i32 rl = v.len - rstart;
+        if (first ? (rl == 0) : (rl < (i32)ix.k)) {
+            total = acc;
+            return true;
+        }
+        Cands c = index_query(ix, code, false);
+        u32 best = budget + 1;
+        i32 best_sid = 0;
+        bool ended = false, stepped = false;
+        u64 next_code = 0;
+        i64 next_L = 0;
+        for (int i = 0; i < c.n; ++i) {
+            Oriented u = orient(ix, c, i);
+            const i64 L = u.len - km1;
+            const bool ends_here = L >= rl;
+            u32 miss;
+            if (first) {
+                // unitig[k-1 : k-1+n) against readLeft[0:n)
+                i32 n2 = ends_here ? rl : (i32)L;
+                miss = mismatches(ix, v, u, km1, rstart, n2, budget);
+            } else {
+                // unitig[0:n) against read[pos : pos+n): n = |readLeft| if it ends here, else
+                // min(|unitig|, |readLeft|) (substr is cut at the end of the read)
+                i32 n2 = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
+                miss = mismatches(ix, v, u, 0, rstart, n2, budget);
+            }
+            if (ends_here) {
+                if (miss == 0) {
+                    sc.set(n++, u.sid);
+                    total = acc;
+                    return true;
+                } else if (miss < best) {
+                    best = miss;
+                    best_sid = u.sid;
+                    ended = true;
+                }
+            } else {
+                if (miss == 0) {
+                    sc.set(n++, u.sid);
+                    code = last_code(ix, u);
+                    pos += (i32)L;
+                    stepped = true;
+                    break;
+                } else if (miss < best) {
+                    ended = false;
+                    best = miss;
+                    best_sid = u.sid;
+                    next_L = L;
+                    next_code = last_code(ix, u);
+                }
+            }
+        }
+        first = false;
+        if (stepped) continue;
+        if (best > budget) return false;
+        sc.set(n++, best_sid);
+        if (ended) {
+            total = acc + best;
+            return true;
+        }
+        acc += best;
+        budget -= best;
+        code = next_code;
+        pos += (i32)next_L;
+    }
+}
+
+struct ReadSetup {
+    ReadView v;
+    u64 wb;
+    u32 info;
+    i32 nwin;
+};
+
+BGR_HD ReadSetup setup_read(const DevIndex& ix, const BatchArgs& a, u32 r) {
+    ReadSetup s;
+    const u64 o = a.off[r];
+    const u32 len = (u32)(a.off[r + 1] - o);
+    s.wb = read_word_base(o, r);
+    s.info = a.info[r];
+    s.v.D = a.F + s.wb + 1;
+    s.v.ND = a.NM + s.wb + 1;
+    s.v.len = (i32)len;
+    s.v.hasN = (s.info & INFO_HAS_N) != 0;
+    s.v.pass = false;
+    const u32 km1 = ix.k - 1;
+    s.nwin = (len >= km1) ? (i32)(len - km1 + 1) : 0;
+    return s;
+}
+
+// alignReadGreedy (alignerGreedy.cpp:35-57) for read r. The path is left in scratch as
+// [0, nl) = pathBegin in push order (to be reversed) followed by [nl, n) = pathEnd.
+BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    u32 flags = 0;
+    n = nl = 0;
+    // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
+    const i32 lim = a.effort ? s.nwin : 1;
+    const u32 max_seeds = a.effort ? a.effort : 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        v.pass = pass != 0;
+        const bool useH2 = v.pass && v.hasN;
+        const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
+        SeedIter it;
+        it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, v.pass, lim);
+        u32 tried = 0;
+        while (tried < max_seeds) {
+            i32 pos = it.next();
+            if (pos < 0) break;
+            ++tried;
+            u64 code = seed_code(ix, v, pos);
+            n = 0;
+            u32 eb = 0, ee = 0;
+            if (!greedy_left(ix, v, code, pos, a.errors, sc, n, eb)) continue;
+            nl = n;
+            if (!greedy_right(ix, v, code, pos, a.errors - eb, sc, n, ee)) continue;
+            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (pass ? BGR_F_RC : 0u);
+            return flags;
+        }
+        if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
+            flags |= BGR_F_CNT_NOOVERLAP;
+            n = 0;
+            return flags;
+        }
+        // every seed failed: rc=true, retry on the reverse complement (alignerGreedy.cpp:54), or give up
+        flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
+    }
+    flags |= BGR_F_CNT_NOTALIGNED;
+    n = 0;
+    return flags;
+}
+
+// ------------------------------------------------------------------------------ exhaustive extension
+//
+// The reference's recursion (alignerExhaustive.cpp:61-259) returns, at every level, the FIRST
+// candidate in slot order whose subtree reaches the minimal total mismatch count: equivalently the
+// first complete walk in depth-first order that attains the global minimum, provided it is within the
+// budget. That is what the iterative branch-and-bound search below keeps (strict < on update;
+// subtrees whose partial sum cannot beat the incumbent are skipped, which the reference also does
+// level by level with `miss < miniMiss`). alignReadExhaustivePath (alignerPaths.cpp:66-88) calls the
+// *Path helpers with empty vectors, so their "unitig already in path" filters never fire and the
+// results are the same.
+//
+// Scratch layout (ints): [0, 2*D+2) final path | cur ids [D] | best ids [D] | frames 5*[D].
+struct DfsLayout {
+    u32 D, out0, cur0, best0, fr0;
+    BGR_HD void init(u32 scratch_ints) {
+        D = scratch_ints > 11 ? (scratch_ints - 2) / 9 : 1;
+        out0 = 0;
+        cur0 = 2 * D + 2;
+        best0 = cur0 + D;
+        fr0 = best0 + D;
+    }
+};
+
+// Search one side. Returns true and (best_total, best_n ids at best0.., term) when a walk within
+// `budget` exists. term: left side = start offset or -1 (ended exactly on a unitig start: nothing
+// emitted); right side = end marker (|readLeft|+k-1, or 0 when the read ends on a unitig boundary).
+BGR_HD bool exhaustive_side(const DevIndex& ix, const ReadView& v, bool right, u64 code0, i32 pos0, u32 budget,
+                            Scratch& sc, const DfsLayout& lay, u32& best_total, u32& best_n, i32& term) {
+    const i64 km1 = ix.k - 1;
+    best_total = budget + 1;
+    best_n = 0;
+    term = -1;
+    i32 depth = 0;
+    // frame: code (2 ints), pos, acc, next candidate
+    auto fr_set = [&](u32 d, u64 code, i32 pos, u32 acc, u32 next) {
+        u32 b = lay.fr0 + 5 * d;
+        sc.set(b, (i32)(u32)code);
+        sc.set(b + 1, (i32)(u32)(code >> 32));
+        sc.set(b + 2, pos);
+        sc.set(b + 3, (i32)acc);
+        sc.set(b + 4, (i32)next);
+    };
+    fr_set(0, code0, pos0, 0, 0);
+    while (depth >= 0) {
+        const u32 fb = lay.fr0 + 5 * (u32)depth;
+        const u64 code = (u64)(u32)sc.get(fb) | ((u64)(u32)sc.get(fb + 1) << 32);
+        const i32 pos = sc.get(fb + 2);
+        const u32 acc = (u32)sc.get(fb + 3);
+        const u32 next = (u32)sc.get(fb + 4);
+        // how much of the read is left on this side
+        const i32 rl = right ? v.len - (pos + (i32)km1) : pos;
+        if (rl == 0) {
+            // the read is used up exactly at a unitig boundary (mapOnLeftEndExhaustive:112 returns 0
+            // pushing nothing; mapOnRightEndExhaustive:64 pushes 0)
+            if (acc < best_total) {
+                best_total = acc;
+                best_n = (u32)depth;
+                term = right ? 0 : -1;
+                for (u32 j = 0; j < best_n; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+            }
+            --depth;
+            continue;
+        }
+        Cands c = index_query(ix, code, !right);
+        bool descended = false;
+        for (u32 i = next; i < (u32)c.n; ++i) {
+            if (acc >= best_total) break;  // nothing below can be strictly better
+            Oriented u = orient(ix, c, (int)i);
+            const i64 L = u.len - km1;
+            const u32 cap = best_total - 1 - acc;  // a candidate is useful only if acc+miss < best_total
+            if (L >= rl) {
+                u32 miss = right ? mismatches(ix, v, u, km1, pos + (i32)km1, rl, cap)
+                                 : mismatches(ix, v, u, L - rl, 0, rl, cap);
+                if (miss <= cap) {
+                    best_total = acc + miss;
+                    best_n = (u32)depth + 1;
+                    term = right ? rl + (i32)km1 : (i32)(L - rl);
+                    for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+                    sc.set(lay.best0 + (u32)depth, u.sid);
+                }
+            } else {
+                u32 miss = right ? mismatches(ix, v, u, km1, pos + (i32)km1, (i32)L, cap)
+                                 : mismatches(ix, v, u, 0, rl - (i32)L, (i32)L, cap);
+                if (miss <= cap) {
+                    if ((u32)depth + 1 >= lay.D) {
+                        sc.overflow = true;
+                        continue;
+                    }
+                    sc.set(lay.cur0 + (u32)depth, u.sid);
+                    sc.set(fb + 4, (i32)(i + 1));
+                    u64 nc = right ? last_code(ix, u) : first_code(ix, u);
+                    fr_set((u32)depth + 1, nc, right ? pos + (i32)L : pos - (i32)L, acc + miss, 0);
+                    ++depth;
+                    descended = true;
+                    break;
+                }
+            }
+        }
+        if (!descended) --depth;
+    }
+    return best_total <= budget;
+}
+
+// alignReadExhaustive (alignerExhaustive.cpp:35-58) for read r; the final path is left in scratch
+// [0, n) in output order.
+BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& overlaps) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    const u32 km1 = ix.k - 1;
+    DfsLayout lay;
+    lay.init(a.scratch_ints);
+    n = 0;
+    overlaps = (u32)s.nwin;  // overlaps += listOverlap.size(): every window is listed
+    u32 flags = BGR_F_OVERLAP_FOUND;
+    if (s.nwin == 0) return flags | BGR_F_CNT_NOTALIGNED;  // shorter than k-1: see DESIGN.md
+    if ((u32)v.len == km1) {
+        // single window, nothing on either side: checkBegin pushes 0, checkEnd pushes 0
+        sc.set(0, 0);
+        sc.set(1, 0);
+        n = 2;
+        return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+    }
+    // Every window is tried in order, but only windows whose (k-1)-mer is a border can succeed: a
+    // window at pos>0 needs getEnd non-empty, window 0 needs getBegin non-empty (the read is longer
+    // than the window here).
+    SeedIter it;
+    it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, s.nwin);
+    for (;;) {
+        i32 pos = it.next();
+        if (pos < 0) break;
+        u64 code = seed_code(ix, v, pos);
+        u32 eb = 0, nb = 0, ee = 0, ne = 0;
+        i32 tb = 0, te = 0;
+        u32 w = 0;
+        if (pos == 0) {
+            sc.set(w++, 0);  // checkBeginExhaustive:159
+        } else {
+            if (!exhaustive_side(ix, v, false, code, pos, a.errors, sc, lay, eb, nb, tb)) continue;
+            // left part in output order: [offset] then the ids from the far end to the anchor
+            if (tb >= 0) sc.set(w++, tb);
+            for (u32 j = 0; j < nb; ++j) sc.set(w++, sc.get(lay.best0 + nb - 1 - j));
+        }
+        if (!exhaustive_side(ix, v, true, code, pos, a.errors - eb, sc, lay, ee, ne, te)) continue;
+        for (u32 j = 0; j < ne; ++j) sc.set(w++, sc.get(lay.best0 + j));
+        sc.set(w++, te);
+        n = w;
+        return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+    }
+    n = 0;
+    return flags | BGR_F_CNT_NOTALIGNED;
+}
+
+#if defined(__CUDACC__)
+// Write-out shared by the extension kernels: a warp-wide prefix sum over the path lengths allocates
+// pool space with a single atomic per warp.
+__device__ __forceinline__ void emit_result(const BatchArgs& a, u32 r, bool valid, u32 flags, const Scratch& sc,
+                                            u32 n, u32 nl) {
+    const u32 lane = threadIdx.x & 31;
+    u32 plen = (valid && (flags & BGR_F_MAPPED)) ? n : 0;
+    if (valid && sc.overflow) {  // did not fit the scratch: the host re-runs the batch with a larger one
+        atomicExch(&a.cnt->scratch_overflow, 1u);
+        plen = 0;
+    }
+    u32 incl = plen;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += t;
+    }
+    u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(&a.cnt->pool_cursor, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    if (!valid) return;
+    unsigned long long off = base + (incl - plen);
+    if (plen) {
+        if (off + plen <= a.pool_cap) {
+            i32* dst = a.pool + off;
+            // [0, nl) is reversed on the way out (alignerGreedy.cpp:48)
+            for (u32 j = 0; j < plen; ++j) dst[j] = (j < nl) ? sc.get(nl - 1 - j) : sc.get(j);
+        } else {
+            atomicExch(&a.cnt->pool_overflow, 1u);
+        }
+    }
+    bgr_result res;
+    res.flags_len = (flags & 0xFFu) | (plen << 8);
+    res.path_off = (u32)off;
+    a.res[r] = res;
+}
+
+__device__ __forceinline__ void count_classes(const BatchArgs& a, bool valid, u32 flags, u32 overlaps) {
+    const u32 lane = threadIdx.x & 31;
+    u32 m_reads = __ballot_sync(0xFFFFFFFFu, valid);
+    u32 m_al = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_ALIGNED));
+    u32 m_na = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_NOTALIGNED));
+    u32 m_no = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_NOOVERLAP));
+    u32 ov = valid ? overlaps : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ov += __shfl_xor_sync(0xFFFFFFFFu, ov, d);
+    if (lane == 0) {
+        if (m_reads) atomicAdd(&a.cnt->c[BGR_C_READS], (unsigned long long)__popc(m_reads));
+        if (m_al) atomicAdd(&a.cnt->c[BGR_C_ALIGNED], (unsigned long long)__popc(m_al));
+        if (m_na) atomicAdd(&a.cnt->c[BGR_C_NOTALIGNED], (unsigned long long)__popc(m_na));
+        if (m_no) atomicAdd(&a.cnt->c[BGR_C_NOOVERLAP], (unsigned long long)__popc(m_no));
+        if (ov) atomicAdd(&a.cnt->c[BGR_C_OVERLAPS], (unsigned long long)ov);
+    }
+}
+
+static const int EXT_THREADS = 128;
+
+__global__ void __launch_bounds__(EXT_THREADS) k_extend_greedy(DevIndex ix, BatchArgs a) {
+    const u32 r = blockIdx.x * EXT_THREADS + threadIdx.x;
+    const bool valid = r < a.n;
+    Scratch sc;
+    sc.base = a.scratch + (valid ? r : 0);
+    sc.stride = a.n;
+    sc.cap = a.scratch_ints;
+    sc.overflow = false;
+    u32 flags = 0, n = 0, nl = 0;
+    if (valid) flags = greedy_read(ix, a, r, sc, n, nl);
+    count_classes(a, valid, flags, 0);
+    emit_result(a, r, valid, flags, sc, n, nl);
+}
+
+__global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, BatchArgs a) {
+    const u32 r = blockIdx.x * EXT_THREADS + threadIdx.x;
+    const bool valid = r < a.n;
+    Scratch sc;
+    sc.base = a.scratch + (valid ? r : 0);
+    sc.stride = a.n;
+    sc.cap = a.scratch_ints;
+    sc.overflow = false;
+    u32 flags = 0, n = 0, overlaps = 0;
+    if (valid) flags = exhaustive_read(ix, a, r, sc, n, overlaps);
+    count_classes(a, valid, flags, overlaps);
+    emit_result(a, r, valid, flags, sc, n, 0);
+}
+
+// getBegin / getEnd for one code, for tests (bgr_index_query)
+__global__ void k_index_query(DevIndex ix, u64 code, int want_end, i32* out) {
+    Cands c = index_query(ix, code, want_end != 0);
+    out[0] = c.n;
+    for (int i = 0; i < c.n; ++i) out[1 + i] = orient(ix, c, i).sid;
+}
+#endif  // __CUDACC__
+
+}  // namespace bgr

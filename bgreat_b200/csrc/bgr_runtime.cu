@@ -1,0 +1,515 @@
+// C ABI implementation (include/bgreat_b200.h): context, index residency, batch slots, launches.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bgreat_b200.h"
+#include "bgr_host.h"
+#include "bgr_kernels.cuh"
+
+using namespace bgr;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // device buffers and their capacities
+    char* d_seq = nullptr;
+    size_t cap_seq = 0;
+    u64* d_off = nullptr;
+    bgr_result* d_res = nullptr;
+    u32* d_info = nullptr;
+    size_t cap_reads = 0;
+    u64 *d_F = nullptr, *d_NM = nullptr;
+    u32 *d_H1 = nullptr, *d_H2 = nullptr;
+    size_t cap_words = 0;
+    i32* d_scratch = nullptr;
+    size_t cap_scratch = 0;  // ints
+    i32* d_pool = nullptr;
+    size_t cap_pool = 0;  // ints
+    DevCounters* d_cnt = nullptr;
+    DevCounters* h_cnt = nullptr;  // pinned
+    // current batch
+    u32 n = 0;
+    u64 chars = 0, words = 0;
+    bgr_params params{};
+    u32 scratch_ints = 0;
+    bool uploaded = false, ran = false, timed = false;
+    bgr_result* h_res = nullptr;
+    i32* h_pool = nullptr;
+    u64 h_pool_cap = 0;
+    bool want_download = false;
+};
+
+}  // namespace
+
+struct bgr_ctx {
+    int device = 0;
+    int n_slots = 1;
+    int sm_count = 148;
+    Slot slots[8];
+    void* d_blob = nullptr;
+    BlobHeader hdr{};
+    DevIndex ix{};
+    bool has_index = false;
+    unsigned long long totals[BGR_C_COUNT] = {0};
+    uint64_t launches = 0;
+    u32 scratch_greedy = 32, scratch_exhaustive = 128;  // ints per read, grown on overflow
+    std::string err;
+};
+
+namespace {
+
+int fail(bgr_ctx* c, int code, const std::string& msg) {
+    g_err = msg;
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, BGR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+template <typename T>
+int grow(bgr_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack_num = 5, size_t slack_den = 4) {
+    if (need <= cap && p) return BGR_OK;
+    if (p) CK(cudaFree(p));
+    p = nullptr;
+    size_t ncap = std::max<size_t>(need * slack_num / slack_den, 256);
+    CK(cudaMalloc((void**)&p, ncap * sizeof(T)));
+    cap = ncap;
+    return BGR_OK;
+}
+
+int set_index_from_device_blob(bgr_ctx* ctx) {
+    CK(cudaMemcpy(&ctx->hdr, ctx->d_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost));
+    const BlobHeader& h = ctx->hdr;
+    if (h.magic != BLOB_MAGIC || h.version != 1) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
+    char* B = (char*)ctx->d_blob;
+    ctx->ix.keys = (const u64*)(B + h.off_keys);
+    ctx->ix.payload = (const Payload*)(B + h.off_payload);
+    ctx->ix.meta = (const UnitigMeta*)(B + h.off_meta);
+    ctx->ix.pool = (const u64*)(B + h.off_pool);
+    ctx->ix.n_buckets = h.n_buckets;
+    ctx->ix.k = h.k;
+    ctx->ix.pad = 0;
+    ctx->has_index = true;
+    return BGR_OK;
+}
+
+int drop_index(bgr_ctx* ctx) {
+    if (ctx->d_blob) CK(cudaFree(ctx->d_blob));
+    ctx->d_blob = nullptr;
+    ctx->has_index = false;
+    return BGR_OK;
+}
+
+int install_host_blob(bgr_ctx* ctx, const void* blob, u64 bytes) {
+    if (bytes < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index blob too small");
+    BlobHeader h;
+    memcpy(&h, blob, sizeof h);
+    if (h.magic != BLOB_MAGIC || h.version != 1 || h.total_bytes != bytes)
+        return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version/size");
+    CK(cudaSetDevice(ctx->device));
+    int rc = drop_index(ctx);
+    if (rc) return rc;
+    CK(cudaMalloc(&ctx->d_blob, bytes));
+    CK(cudaMemcpy(ctx->d_blob, blob, bytes, cudaMemcpyHostToDevice));
+    return set_index_from_device_blob(ctx);
+}
+
+int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
+    const u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
+    switch (s.params.mode) {
+        case BGR_MODE_GREEDY: k_extend_greedy<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+        case BGR_MODE_EXHAUSTIVE:
+        case BGR_MODE_EXHAUSTIVE_PATH: k_extend_exhaustive<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+        default: return fail(ctx, BGR_ERR_ARG, "mode not supported");
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return BGR_OK;
+}
+
+BatchArgs make_args(Slot& s) {
+    BatchArgs a;
+    a.seq = s.d_seq;
+    a.off = s.d_off;
+    a.n = s.n;
+    a.F = s.d_F;
+    a.NM = s.d_NM;
+    a.H1 = s.d_H1;
+    a.H2 = s.d_H2;
+    a.info = s.d_info;
+    a.res = s.d_res;
+    a.scratch = s.d_scratch;
+    a.scratch_ints = s.scratch_ints;
+    a.pool = s.d_pool;
+    a.pool_cap = s.cap_pool;
+    a.cnt = s.d_cnt;
+    a.errors = s.params.errors;
+    a.effort = s.params.effort;
+    a.mode = s.params.mode;
+    return a;
+}
+
+// scratch + pool sized for the current batch and mode
+int ensure_work_buffers(bgr_ctx* ctx, Slot& s) {
+    int rc;
+    if ((rc = grow(ctx, s.d_scratch, s.cap_scratch, (size_t)s.n * s.scratch_ints, 1, 1))) return rc;
+    if ((rc = grow(ctx, s.d_pool, s.cap_pool, std::max<size_t>((size_t)s.n * 8, 1024), 1, 1))) return rc;
+    return BGR_OK;
+}
+
+int enqueue_extension(bgr_ctx* ctx, Slot& s) {
+    int rc = ensure_work_buffers(ctx, s);
+    if (rc) return rc;
+    BatchArgs a = make_args(s);
+    if ((rc = launch_extension(ctx, s, a))) return rc;
+    CK(cudaEventRecord(s.ev[2], s.stream));
+    CK(cudaMemcpyAsync(s.h_cnt, s.d_cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
+    return BGR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bgr_abi_version(void) { return BGR_ABI_VERSION; }
+
+const char* bgr_last_error(const bgr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int bgr_ctx_create(int device, int n_slots, bgr_ctx** out) {
+    bgr_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, BGR_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n_slots < 1 || n_slots > 8) return fail(nullptr, BGR_ERR_ARG, "n_slots must be in [1,8]");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(nullptr, BGR_ERR_CUDA, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, BGR_ERR_CUDA,
+                    std::string("device is not sm_100 class (") + prop.name + "): the kernels are built for sm_100a only");
+    ctx = new bgr_ctx();
+    ctx->device = device;
+    ctx->n_slots = n_slots;
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < n_slots; ++i) {
+        Slot& s = ctx->slots[i];
+        cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        for (int j = 0; j < 3 && e == cudaSuccess; ++j) e = cudaEventCreate(&s.ev[j]);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.d_cnt, sizeof(DevCounters));
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.h_cnt, sizeof(DevCounters), cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            std::string m = std::string("slot setup: ") + cudaGetErrorString(e);
+            bgr_ctx_destroy(ctx);
+            return fail(nullptr, BGR_ERR_CUDA, m);
+        }
+    }
+    *out = ctx;
+    return BGR_OK;
+}
+
+void bgr_ctx_destroy(bgr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < ctx->n_slots; ++i) {
+        Slot& s = ctx->slots[i];
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_seq);
+        cudaFree(s.d_off);
+        cudaFree(s.d_res);
+        cudaFree(s.d_info);
+        cudaFree(s.d_F);
+        cudaFree(s.d_NM);
+        cudaFree(s.d_H1);
+        cudaFree(s.d_H2);
+        cudaFree(s.d_scratch);
+        cudaFree(s.d_pool);
+        cudaFree(s.d_cnt);
+        if (s.h_cnt) cudaFreeHost(s.h_cnt);
+        for (int j = 0; j < 3; ++j)
+            if (s.ev[j]) cudaEventDestroy(s.ev[j]);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(ctx->d_blob);
+    delete ctx;
+}
+
+int bgr_host_alloc(size_t bytes, void** out) {
+    bgr_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, BGR_ERR_ARG, "out is null");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return BGR_OK;
+}
+
+void bgr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------- index
+
+int bgr_index_build(bgr_ctx* ctx, const char* seqs, const uint64_t* off, uint32_t n_unitigs, uint32_t k) {
+    if (!ctx || !off || (!seqs && n_unitigs)) return fail(ctx, BGR_ERR_ARG, "null argument");
+    std::vector<uint64_t> blob;
+    std::string err;
+    int rc = build_index_blob(seqs, off, n_unitigs, k, blob, err);
+    if (rc) return fail(ctx, rc, err);
+    return install_host_blob(ctx, blob.data(), blob.size() * 8);
+}
+
+int bgr_index_build_file(bgr_ctx* ctx, const char* unitig_fasta, uint32_t k) {
+    if (!ctx || !unitig_fasta) return fail(ctx, BGR_ERR_ARG, "null argument");
+    std::string seqs;
+    std::vector<uint64_t> off;
+    bool opened = load_unitig_file(unitig_fasta, k, seqs, off);
+    int rc = bgr_index_build(ctx, seqs.data(), off.data(), (uint32_t)(off.size() - 1), k);
+    if (rc) return rc;
+    if (!opened) return fail(ctx, BGR_ERR_IO, std::string("cannot open unitig file ") + unitig_fasta);
+    return BGR_OK;
+}
+
+int bgr_index_stats(const bgr_ctx* ctx, uint64_t* n_unitigs, uint64_t* n_keys, uint64_t* device_bytes) {
+    if (!ctx || !ctx->has_index) return BGR_ERR_NO_INDEX;
+    if (n_unitigs) *n_unitigs = ctx->hdr.n_unitigs;
+    if (n_keys) *n_keys = ctx->hdr.n_keys;
+    if (device_bytes) *device_bytes = ctx->hdr.total_bytes;
+    return BGR_OK;
+}
+
+int bgr_index_blob_size(const bgr_ctx* ctx, uint64_t* bytes) {
+    if (!ctx || !ctx->has_index || !bytes) return BGR_ERR_NO_INDEX;
+    *bytes = ctx->hdr.total_bytes;
+    return BGR_OK;
+}
+
+int bgr_index_export_device(const bgr_ctx* cctx, void* dev_dst, uint64_t bytes) {
+    bgr_ctx* ctx = const_cast<bgr_ctx*>(cctx);
+    if (!ctx || !ctx->has_index) return fail(ctx, BGR_ERR_NO_INDEX, "no index");
+    if (!dev_dst || bytes < ctx->hdr.total_bytes) return fail(ctx, BGR_ERR_ARG, "destination too small");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(dev_dst, ctx->d_blob, ctx->hdr.total_bytes, cudaMemcpyDeviceToDevice));
+    return BGR_OK;
+}
+
+int bgr_index_import_device(bgr_ctx* ctx, const void* dev_src, uint64_t bytes) {
+    if (!ctx || !dev_src || bytes < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = drop_index(ctx);
+    if (rc) return rc;
+    CK(cudaMalloc(&ctx->d_blob, bytes));
+    CK(cudaMemcpy(ctx->d_blob, dev_src, bytes, cudaMemcpyDeviceToDevice));
+    rc = set_index_from_device_blob(ctx);
+    if (rc == BGR_OK && ctx->hdr.total_bytes != bytes) {
+        drop_index(ctx);
+        return fail(ctx, BGR_ERR_FORMAT, "index blob: size mismatch");
+    }
+    return rc;
+}
+
+int bgr_index_export_host(const bgr_ctx* cctx, void* host_dst, uint64_t bytes) {
+    bgr_ctx* ctx = const_cast<bgr_ctx*>(cctx);
+    if (!ctx || !ctx->has_index) return fail(ctx, BGR_ERR_NO_INDEX, "no index");
+    if (!host_dst || bytes < ctx->hdr.total_bytes) return fail(ctx, BGR_ERR_ARG, "destination too small");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(host_dst, ctx->d_blob, ctx->hdr.total_bytes, cudaMemcpyDeviceToHost));
+    return BGR_OK;
+}
+
+int bgr_index_import_host(bgr_ctx* ctx, const void* host_src, uint64_t bytes) {
+    if (!ctx || !host_src) return fail(ctx, BGR_ERR_ARG, "null argument");
+    return install_host_blob(ctx, host_src, bytes);
+}
+
+int bgr_index_query(const bgr_ctx* cctx, uint64_t kmer_code, int want_end, int32_t ids[4]) {
+    bgr_ctx* ctx = const_cast<bgr_ctx*>(cctx);
+    if (!ctx || !ctx->has_index) return -BGR_ERR_NO_INDEX;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -BGR_ERR_CUDA;
+    i32* d = nullptr;
+    if (cudaMalloc((void**)&d, 5 * sizeof(i32)) != cudaSuccess) return -BGR_ERR_CUDA;
+    k_index_query<<<1, 1>>>(ctx->ix, kmer_code, want_end, d);
+    ctx->launches++;
+    i32 h[5] = {0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        fail(ctx, BGR_ERR_CUDA, cudaGetErrorString(e));
+        return -BGR_ERR_CUDA;
+    }
+    for (int i = 0; i < h[0]; ++i) ids[i] = h[1 + i];
+    return h[0];
+}
+
+// ---------------------------------------------------------------------------------- mapping
+
+int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* off, uint32_t n) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    if (!off || (!seqs && n)) return fail(ctx, BGR_ERR_ARG, "null argument");
+    if (off[0] != 0) return fail(ctx, BGR_ERR_ARG, "off[0] must be 0");
+    Slot& s = ctx->slots[slot];
+    CK(cudaSetDevice(ctx->device));
+    const u64 chars = off[n];
+    const u64 words = (chars >> 5) + 3ull * n + 4;
+    int rc;
+    if ((rc = grow(ctx, s.d_seq, s.cap_seq, (size_t)chars + 16))) return rc;
+    if (n + 1 > s.cap_reads || !s.d_off) {
+        size_t cap = 0, c2 = 0, c3 = 0;
+        if ((rc = grow(ctx, s.d_off, cap, (size_t)n + 1))) return rc;
+        if ((rc = grow(ctx, s.d_res, c2, (size_t)n + 1))) return rc;
+        if ((rc = grow(ctx, s.d_info, c3, (size_t)n + 1))) return rc;
+        s.cap_reads = std::min(cap, std::min(c2, c3));
+    }
+    if (words > s.cap_words || !s.d_F) {
+        size_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if ((rc = grow(ctx, s.d_F, c0, (size_t)words))) return rc;
+        if ((rc = grow(ctx, s.d_NM, c1, (size_t)words))) return rc;
+        if ((rc = grow(ctx, s.d_H1, c2, (size_t)words))) return rc;
+        if ((rc = grow(ctx, s.d_H2, c3, (size_t)words))) return rc;
+        s.cap_words = std::min(std::min(c0, c1), std::min(c2, c3));
+    }
+    if (chars) CK(cudaMemcpyAsync(s.d_seq, seqs, chars, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_off, off, ((size_t)n + 1) * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
+    s.n = n;
+    s.chars = chars;
+    s.words = words;
+    s.uploaded = true;
+    s.ran = false;
+    s.want_download = false;
+    return BGR_OK;
+}
+
+int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots || !p) return fail(ctx, BGR_ERR_ARG, "bad argument");
+    if (!ctx->has_index) return fail(ctx, BGR_ERR_NO_INDEX, "no index built or imported");
+    Slot& s = ctx->slots[slot];
+    if (!s.uploaded) return fail(ctx, BGR_ERR_ARG, "slot has no batch uploaded");
+    if (p->mode > BGR_MODE_EXHAUSTIVE_PATH) return fail(ctx, BGR_ERR_ARG, "unknown mode");
+    if (p->mode == BGR_MODE_GREEDY_PATH)
+        return fail(ctx, BGR_ERR_ARG, "BGR_MODE_GREEDY_PATH is not implemented on the device yet");
+    CK(cudaSetDevice(ctx->device));
+    s.params = *p;
+    s.scratch_ints = (p->mode == BGR_MODE_GREEDY) ? ctx->scratch_greedy : ctx->scratch_exhaustive;
+    CK(cudaMemsetAsync(s.d_cnt, 0, sizeof(DevCounters), s.stream));
+    CK(cudaEventRecord(s.ev[0], s.stream));
+    if (s.n) {
+        BatchArgs a = make_args(s);
+        u32 blocks = (s.n + PS_WARPS - 1) / PS_WARPS;
+        u32 maxb = (u32)ctx->sm_count * 8;
+        if (blocks > maxb) blocks = maxb;
+        k_pack_scan<<<blocks, PS_WARPS * 32, 0, s.stream>>>(ctx->ix, a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(s.ev[1], s.stream));
+    if (s.n) {
+        int rc = enqueue_extension(ctx, s);
+        if (rc) return rc;
+    } else {
+        CK(cudaEventRecord(s.ev[2], s.stream));
+        CK(cudaMemcpyAsync(s.h_cnt, s.d_cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
+    }
+    s.ran = true;
+    s.timed = true;
+    return BGR_OK;
+}
+
+int bgr_slot_download(bgr_ctx* ctx, int slot, bgr_result* results, int32_t* path_pool, uint64_t pool_cap) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    Slot& s = ctx->slots[slot];
+    if (!s.ran) return fail(ctx, BGR_ERR_ARG, "slot has not been run");
+    if (!results || (!path_pool && pool_cap)) return fail(ctx, BGR_ERR_ARG, "null argument");
+    s.h_res = results;
+    s.h_pool = path_pool;
+    s.h_pool_cap = pool_cap;
+    s.want_download = true;
+    return BGR_OK;
+}
+
+int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    Slot& s = ctx->slots[slot];
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(s.stream));
+    if (!s.ran) return BGR_OK;
+    // scratch / pool too small: grow and redo the extension kernel (the seed scan's output is kept)
+    for (int attempt = 0; s.n && (s.h_cnt->scratch_overflow || s.h_cnt->pool_overflow); ++attempt) {
+        if (attempt > 24) return fail(ctx, BGR_ERR_LIMIT, "extension scratch keeps overflowing");
+        unsigned long long windows = s.h_cnt->c[BGR_C_WINDOWS];
+        if (s.h_cnt->scratch_overflow) {
+            s.scratch_ints *= 4;
+            if (s.params.mode == BGR_MODE_GREEDY) ctx->scratch_greedy = s.scratch_ints;
+            else ctx->scratch_exhaustive = s.scratch_ints;
+        }
+        if (s.h_cnt->pool_overflow) {
+            int rc = grow(ctx, s.d_pool, s.cap_pool, (size_t)s.h_cnt->pool_cursor + 1024, 5, 4);
+            if (rc) return rc;
+        }
+        CK(cudaMemsetAsync(s.d_cnt, 0, sizeof(DevCounters), s.stream));
+        int rc = enqueue_extension(ctx, s);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(s.stream));
+        s.h_cnt->c[BGR_C_WINDOWS] = windows;
+        s.timed = false;  // event pair no longer brackets a single pass
+    }
+    const u64 used = s.h_cnt->pool_cursor;
+    if (pool_used) *pool_used = used;
+    for (int i = 0; i < BGR_C_COUNT; ++i) ctx->totals[i] += s.h_cnt->c[i];
+    s.ran = false;
+    if (s.want_download) {
+        s.want_download = false;
+        if (used > s.h_pool_cap) return fail(ctx, BGR_ERR_LIMIT, "path pool buffer too small");
+        if (s.n) CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.n * sizeof(bgr_result), cudaMemcpyDeviceToHost, s.stream));
+        if (used) CK(cudaMemcpyAsync(s.h_pool, s.d_pool, (size_t)used * sizeof(i32), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    return BGR_OK;
+}
+
+int bgr_slot_kernel_ms(bgr_ctx* ctx, int slot, float ms[3]) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots || !ms) return fail(ctx, BGR_ERR_ARG, "bad argument");
+    Slot& s = ctx->slots[slot];
+    if (!s.timed) return fail(ctx, BGR_ERR_ARG, "no timed run on this slot");
+    CK(cudaEventSynchronize(s.ev[2]));
+    CK(cudaEventElapsedTime(&ms[0], s.ev[0], s.ev[1]));
+    CK(cudaEventElapsedTime(&ms[1], s.ev[1], s.ev[2]));
+    CK(cudaEventElapsedTime(&ms[2], s.ev[0], s.ev[2]));
+    return BGR_OK;
+}
+
+int bgr_map_batch(bgr_ctx* ctx, const char* seqs, const uint64_t* off, uint32_t n, const bgr_params* p,
+                  bgr_result* results, int32_t* path_pool, uint64_t pool_cap, uint64_t* pool_used) {
+    int rc;
+    if ((rc = bgr_slot_upload(ctx, 0, seqs, off, n))) return rc;
+    if ((rc = bgr_slot_run(ctx, 0, p))) return rc;
+    if ((rc = bgr_slot_download(ctx, 0, results, path_pool, pool_cap))) return rc;
+    return bgr_slot_wait(ctx, 0, pool_used);
+}
+
+int bgr_counters(bgr_ctx* ctx, uint64_t out[BGR_C_COUNT]) {
+    if (!ctx || !out) return BGR_ERR_ARG;
+    for (int i = 0; i < BGR_C_COUNT; ++i) out[i] = ctx->totals[i];
+    return BGR_OK;
+}
+
+int bgr_counters_reset(bgr_ctx* ctx) {
+    if (!ctx) return BGR_ERR_ARG;
+    for (int i = 0; i < BGR_C_COUNT; ++i) ctx->totals[i] = 0;
+    return BGR_OK;
+}
+
+uint64_t bgr_launch_count(const bgr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// TEST INFRASTRUCTURE ONLY -- host single-stepper for the device code.
+//
+// The build container has no GPU, so the per-read __host__ __device__ bodies of
+// bgreat_b200/csrc/bgr_kernels.cuh (pack4, scan_window, greedy_read, exhaustive_read and
+// everything under them) are compiled here for the host and driven by plain loops that
+// stand in for the kernels' thread/warp structure. This lets `pytest -m "not gpu"` check
+// the device LOGIC against the oracle. It is not a fallback: nothing under bgreat_b200/
+// links, loads or calls this library, and the product fails loudly without a GPU.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../bgreat_b200/csrc/bgr_host.h"
+#include "../../bgreat_b200/csrc/bgr_kernels.cuh"
+
+using namespace bgr;
+
+extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uint32_t k, const char* seqs,
+                       const uint64_t* off, uint32_t n, uint32_t mode, uint32_t errors, uint32_t effort,
+                       uint32_t scratch_ints, bgr_result* res, int32_t* pool, uint64_t pool_cap, uint64_t* used,
+                       uint64_t counters[BGR_C_COUNT], int* scratch_overflow) {
+    std::vector<uint64_t> blob;
+    std::string err;
+    int rc = build_index_blob(useqs, uoff, nu, k, blob, err);
+    if (rc) return rc;
+    BlobHeader h;
+    memcpy(&h, blob.data(), sizeof h);
+    char* B = (char*)blob.data();
+    DevIndex ix;
+    ix.keys = (const u64*)(B + h.off_keys);
+    ix.payload = (const Payload*)(B + h.off_payload);
+    ix.meta = (const UnitigMeta*)(B + h.off_meta);
+    ix.pool = (const u64*)(B + h.off_pool);
+    ix.n_buckets = h.n_buckets;
+    ix.k = h.k;
+    ix.pad = 0;
+
+    const u64 chars = off[n];
+    const u64 words = (chars >> 5) + 3ull * n + 4;
+    std::vector<u64> F(words, 0xDEADBEEFDEADBEEFull), NM(words, 0xDEADBEEFDEADBEEFull);
+    std::vector<u32> H1(words, 0xFFFFFFFFu), H2(words, 0xFFFFFFFFu), info(n + 1, 0);
+    std::vector<i32> scratch((size_t)n * scratch_ints + 1, 0);
+    DevCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    BatchArgs a;
+    a.seq = seqs;
+    a.off = off;
+    a.n = n;
+    a.F = F.data();
+    a.NM = NM.data();
+    a.H1 = H1.data();
+    a.H2 = H2.data();
+    a.info = info.data();
+    a.res = res;
+    a.scratch = scratch.data();
+    a.scratch_ints = scratch_ints;
+    a.pool = pool;
+    a.pool_cap = pool_cap;
+    a.cnt = &cnt;
+    a.errors = errors;
+    a.effort = effort;
+    a.mode = mode;
+    const u32 km1 = k - 1;
+    const bool exhaustive = mode != BGR_MODE_GREEDY;
+
+    // ---- k_pack_scan, one "warp" per read
+    for (u32 r = 0; r < n; ++r) {
+        const u64 o = off[r];
+        const u32 len = (u32)(off[r + 1] - o);
+        const u64 wb = read_word_base(o, r);
+        const u32 nw = (len + 31) >> 5;
+        u64* gF = a.F + wb;
+        u64* gN = a.NM + wb;
+        gF[0] = gN[0] = 0;
+        gF[nw + 1] = gN[nw + 1] = 0;
+        bool anyN = false;
+        for (u32 c0 = 0; c0 < nw * 32; c0 += 4) {
+            u32 x = 0x41414141u;
+            if (c0 < len) {
+                u32 left = len - c0;
+                unsigned char b[4] = {'A', 'A', 'A', 'A'};
+                for (u32 j = 0; j < 4 && j < left; ++j) b[j] = (unsigned char)seqs[o + c0 + j];
+                x = b[0] | (b[1] << 8) | (b[2] << 16) | ((u32)b[3] << 24);
+            }
+            u32 code8, nm8;
+            pack4(x, code8, nm8);
+            u32 byte = packed_byte(c0);
+            ((unsigned char*)gF)[byte] = (unsigned char)code8;
+            ((unsigned char*)gN)[byte] = (unsigned char)nm8;
+            anyN |= nm8 != 0;
+        }
+        const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
+        u32 any1 = 0, any2 = 0;
+        for (u32 base = 0; base < nwin; base += 32) {
+            u32 m1 = 0, m2 = 0;
+            for (u32 lane = 0; lane < 32; ++lane) {
+                u32 i = base + lane;
+                bool h1 = false, h2 = false;
+                if (i < nwin) scan_window(ix, gF + 1, gN + 1, anyN, exhaustive, i, h1, h2);
+                m1 |= (u32)h1 << lane;
+                m2 |= (u32)h2 << lane;
+            }
+            any1 |= m1;
+            any2 |= m2;
+            a.H1[wb + (base >> 5)] = m1;
+            if (anyN) a.H2[wb + (base >> 5)] = m2;
+        }
+        a.info[r] = (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
+        cnt.c[BGR_C_WINDOWS] += nwin;
+    }
+
+    // ---- k_extend_*, one "thread" per read, then emit_result / count_classes
+    *scratch_overflow = 0;
+    for (u32 r = 0; r < n; ++r) {
+        Scratch sc;
+        sc.base = a.scratch + r;
+        sc.stride = n;
+        sc.cap = scratch_ints;
+        sc.overflow = false;
+        u32 flags = 0, np = 0, nl = 0, overlaps = 0;
+        if (mode == BGR_MODE_GREEDY) flags = greedy_read(ix, a, r, sc, np, nl);
+        else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH)
+            flags = exhaustive_read(ix, a, r, sc, np, overlaps);
+        else return BGR_ERR_ARG;
+        cnt.c[BGR_C_READS]++;
+        if (flags & BGR_F_CNT_ALIGNED) cnt.c[BGR_C_ALIGNED]++;
+        if (flags & BGR_F_CNT_NOTALIGNED) cnt.c[BGR_C_NOTALIGNED]++;
+        if (flags & BGR_F_CNT_NOOVERLAP) cnt.c[BGR_C_NOOVERLAP]++;
+        cnt.c[BGR_C_OVERLAPS] += overlaps;
+        u32 plen = (flags & BGR_F_MAPPED) ? np : 0;
+        if (sc.overflow) {
+            *scratch_overflow = 1;
+            plen = 0;
+        }
+        u64 offp = cnt.pool_cursor;
+        cnt.pool_cursor += plen;
+        if (offp + plen > pool_cap) return BGR_ERR_LIMIT;
+        for (u32 j = 0; j < plen; ++j) pool[offp + j] = (j < nl) ? sc.get(nl - 1 - j) : sc.get(j);
+        res[r].flags_len = (flags & 0xFFu) | (plen << 8);
+        res[r].path_off = (u32)offp;
+    }
+    *used = cnt.pool_cursor;
+    for (int i = 0; i < BGR_C_COUNT; ++i) counters[i] = cnt.c[i];
+    return BGR_OK;
+}

@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes view of tests/emu/libbgr_emu.so, the host single-stepper of the
+device code (see tests/emu/bgr_emu.cu). Built on demand with nvcc (host code only runs)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emu", "bgr_emu.cu")
+LIB = os.path.join(HERE, "emu", "libbgr_emu.so")
+DEPS = [SRC] + [os.path.join(ROOT, "bgreat_b200", "csrc", f)
+                for f in ("bgr_kernels.cuh", "bgr_common.h", "bgr_host.cpp", "bgr_host.h")]
+
+_lib = None
+
+
+def build():
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS):
+        return
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler",
+                           "-fPIC", "-shared", "-o", LIB, SRC,
+                           os.path.join(ROOT, "bgreat_b200", "csrc", "bgr_host.cpp")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.emu_map.restype = C.c_int
+    return _lib
+
+
+def _concat(seqs):
+    b = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(b) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(x) for x in b], dtype=np.uint64)
+    return b"".join(b), off
+
+
+def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64):
+    """-> ([(overlap_found, rc, path)], counters dict, flags list, scratch_overflow)"""
+    L = lib()
+    us, uoff = _concat(unitigs)
+    rs, roff = _concat(reads)
+    n = len(reads)
+    res = np.zeros((max(n, 1), 2), dtype=np.uint32)
+    pool_cap = max(1024, (len(rs) + 2 * n) * 2)
+    pool = np.zeros(pool_cap, dtype=np.int32)
+    used = C.c_uint64(0)
+    counters = (C.c_uint64 * 8)()
+    ovf = C.c_int(0)
+    rc = L.emu_map(us, uoff.ctypes.data_as(C.c_void_p), C.c_uint32(len(unitigs)), C.c_uint32(k), rs,
+                   roff.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(mode), C.c_uint32(errors),
+                   C.c_uint32(effort), C.c_uint32(scratch_ints), res.ctypes.data_as(C.c_void_p),
+                   pool.ctypes.data_as(C.c_void_p), C.c_uint64(pool_cap), C.byref(used), counters, C.byref(ovf))
+    if rc != 0:
+        raise RuntimeError("emu_map failed: %d" % rc)
+    out, flags = [], []
+    for i in range(n):
+        fl = int(res[i, 0]) & 0xFF
+        ln = int(res[i, 0]) >> 8
+        o = int(res[i, 1])
+        out.append((bool(fl & 2), bool(fl & 4), [int(x) for x in pool[o:o + ln]]))
+        flags.append(fl)
+    names = ["reads", "aligned", "not_aligned", "no_overlap", "overlaps", "windows"]
+    return out, dict(zip(names, [int(c) for c in counters[:6]])), flags, bool(ovf.value)

@@ -1,0 +1,209 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden vectors of the
+compiled reference. Bit-exact: paths, start offsets, orientation signs, overlapFound / rc flags, counters."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import synth_small as S
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HARNESS = json.load(open(os.path.join(GOLDEN, "harness_cases.json")))
+MODES = {"greedy": 0, "exhaustive": 1, "exhaustive_path": 3}
+COUNTERS = ("reads", "aligned", "not_aligned", "no_overlap", "overlaps")
+
+
+@pytest.fixture(scope="module")
+def bg():
+    import bgreat_b200
+    return bgreat_b200
+
+
+def oracle_results(k, m, e, unitigs, reads, mode):
+    o = O.Oracle(k, m, e)
+    o.index_unitigs(unitigs)
+    res = [o.align(r, mode) for r in reads]
+    return res, o.counters()
+
+
+@pytest.mark.parametrize("case", HARNESS, ids=[c["name"] for c in HARNESS])
+def test_golden_vectors_of_the_reference(bg, case):
+    k = case["k"]
+    for mode_name, mode in MODES.items():
+        al = bg.Aligner(k, case["m"], case["effort"])
+        al.index_unitigs(case["unitigs"])
+        got = al.align_batch(case["reads"], mode).as_tuples()
+        want = case["results"][mode_name]
+        for read, w, g in zip(case["reads"], want["reads"], got):
+            if len(read) < k - 1:
+                continue  # no defined reference result (short reads)
+            assert [int(g[0]), int(g[1])] + g[2] == w, (mode_name, read)
+        if all(len(r) >= k - 1 for r in case["reads"]):
+            c = al.counters()
+            for name in COUNTERS:
+                assert c[name] == want["counters"][name], (mode_name, name)
+        al.close()
+
+
+@pytest.mark.parametrize("seed", range(2000, 2060))
+def test_fuzz_against_oracle(bg, seed):
+    c = S.fuzz_case(seed)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(c["k"], c["m"], c["effort"], c["unitigs"], c["reads"], mode)
+        al = bg.Aligner(c["k"], c["m"], c["effort"])
+        al.index_unitigs(c["unitigs"])
+        got = al.align_batch(c["reads"], mode).as_tuples()
+        assert got == want
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        al.close()
+
+
+def _k31_case(seed, n_reads, read_len=150, genome=20000, sub=0.01, n_rate=0.0005):
+    rng = random.Random(seed)
+    unitigs, haps = S.make_graph(rng, 31, genome_len=genome, mean_unitig=70, n_variants=genome // 150)
+    reads = S.make_reads(rng, haps, n_reads, read_len, sub_rate=sub, n_rate=n_rate)
+    return unitigs, reads
+
+
+@pytest.mark.parametrize("m", [0, 1, 2, 5])
+def test_k31_reads_greedy_and_exhaustive(bg, m):
+    unitigs, reads = _k31_case(7, 3000)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(31, m, 2, unitigs, reads, mode)
+        al = bg.Aligner(31, m, 2)
+        al.index_unitigs(unitigs)
+        got = al.align_batch(reads, mode).as_tuples()
+        assert got == want
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        assert gc["windows"] == sum(max(0, len(r) - 30 + 1) for r in reads)
+        al.close()
+
+
+def test_ragged_and_long_reads(bg):
+    """reads from k-1 bases up to 3000 bases in one batch (the >576-base path keeps words in HBM)."""
+    rng = random.Random(11)
+    unitigs, haps = S.make_graph(rng, 21, genome_len=6000, mean_unitig=40, n_variants=30)
+    reads = []
+    for ln in [20, 21, 22, 31, 32, 33, 63, 64, 65, 127, 128, 129, 575, 576, 577, 1000, 3000]:
+        reads += S.make_reads(rng, haps, 6, ln, sub_rate=0.002, n_rate=0.001, off_graph=0.0)
+    rng.shuffle(reads)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(21, 3, 2, unitigs, reads, mode)
+        al = bg.Aligner(21, 3, 2)
+        al.index_unitigs(unitigs)
+        got = al.align_batch(reads, mode).as_tuples()
+        assert got == want
+        al.close()
+
+
+def test_empty_batch_and_unmappable(bg):
+    al = bg.Aligner(5, 2, 2)
+    al.index_unitigs(["ACGTACGTTT", "CGTTTGGA"])
+    r = al.align_batch([], 0)
+    assert len(r) == 0
+    r = al.align_batch(["GGGGGGGGGGGG"], 0).as_tuples()
+    assert r == [(False, False, [])]
+    c = al.counters()
+    assert c["reads"] == 1 and c["no_overlap"] == 1
+    al.close()
+
+
+def test_empty_index(bg):
+    al = bg.Aligner(5, 2, 2)
+    al.index_unitigs([])
+    assert al.align_batch(["ACGTACGTAC"], 0).as_tuples() == [(False, False, [])]
+    assert al.align_batch(["ACGTACGTAC"], 1).as_tuples() == [(True, False, [])]
+    al.close()
+
+
+def test_long_paths_grow_the_scratch(bg):
+    rng = random.Random(5)
+    unitigs, haps = S.make_graph(rng, 10, genome_len=600, mean_unitig=2, n_variants=0)
+    reads = S.make_reads(rng, haps, 200, 300, sub_rate=0.0, off_graph=0.0)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, _ = oracle_results(10, 2, 2, unitigs, reads, mode)
+        al = bg.Aligner(10, 2, 2)
+        al.index_unitigs(unitigs)
+        got = al.align_batch(reads, mode).as_tuples()
+        assert got == want
+        assert max(len(p) for _, _, p in got) > 100
+        al.close()
+
+
+def test_index_queries_match_reference_semantics(bg):
+    """getBegin / getEnd on the K6 slot-overflow and K10 hairpin graphs."""
+    al = bg.Aligner(4, 0, 2)
+    al.index_unitigs(["ATCAA", "ATCCC", "ATCGG", "ATCTT", "ATCAG", "GGATC", "TTGATC"])
+    atc = O.str2num("ATC")
+    assert al.get_begin(atc) == [1, 2, 3, 5]  # the 5th arrival overwrote slot 4 (aligner.cpp:487)
+    assert al.get_end(atc) == [6, 7]
+    assert al.get_end(O.str2num("GAT")) == [-1, -2, -3, -5]  # rc(ATC): the same unitigs reversed
+    al.close()
+    al = bg.Aligner(4, 0, 2)
+    al.index_unitigs(["AACTGTT", "CCAAC", "AACGG"])
+    assert al.get_begin(O.str2num("AAC")) == [1, 1, 3]  # hairpin inserted twice, forward both times
+    al.close()
+
+
+def test_index_blob_roundtrip_host_and_device(bg):
+    import torch
+    unitigs, reads = _k31_case(3, 500)
+    a = bg.Aligner(31, 2, 2)
+    a.index_unitigs(unitigs)
+    want = a.align_batch(reads, 0).as_tuples()
+    blob = a.export_index_host()
+    b = bg.Aligner(31, 2, 2)
+    b.import_index_host(blob)
+    assert b.align_batch(reads, 0).as_tuples() == want
+    # device path: what bench.py does around a NCCL broadcast
+    n = a.index_blob_size()
+    t = torch.empty(n, dtype=torch.uint8, device="cuda")
+    a.export_index_device(t.data_ptr(), n)
+    torch.cuda.synchronize()
+    c = bg.Aligner(31, 2, 2)
+    c.import_index_device(t.data_ptr(), n)
+    assert c.align_batch(reads, 0).as_tuples() == want
+    assert c.index_stats() == a.index_stats()
+    bad = blob.copy()
+    bad[0] ^= 0xFF
+    with pytest.raises(bg.BgrError):
+        b.import_index_host(bad)
+    for x in (a, b, c):
+        x.close()
+
+
+def test_errors_are_reported(bg):
+    al = bg.Aligner(31, 2, 2)
+    with pytest.raises(bg.BgrError):
+        al.align_batch(["ACGT" * 20], 0)  # no index yet
+    with pytest.raises(bg.BgrError):
+        al.index_unitigs(["ACGTNACGTACGTACGTACGTACGTACGTACGTACGT"])  # N in a unitig
+    with pytest.raises(bg.BgrError):
+        bg.Aligner(40).index_unitigs(["A" * 50])  # k > 32
+    al.close()
+
+
+def test_effort_and_mismatch_sweep_properties(bg):
+    """Size-independent properties on a larger batch: more budget never maps fewer reads exhaustively,
+    counters partition the reads, exact reads map with m=0."""
+    unitigs, reads = _k31_case(21, 20000, genome=50000, n_rate=0.0)
+    prev = -1
+    for m in range(0, 6):
+        al = bg.Aligner(31, m, 2)
+        al.index_unitigs(unitigs)
+        r = al.align_batch(reads, 1)
+        c = al.counters()
+        assert c["reads"] == len(reads) == c["aligned"] + c["not_aligned"] + c["no_overlap"]
+        assert c["aligned"] >= prev
+        prev = c["aligned"]
+        assert int((r.flags & 1).sum()) == c["aligned"]
+        al.close()
