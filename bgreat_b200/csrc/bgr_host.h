@@ -3,6 +3,8 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -52,22 +54,68 @@ bool load_unitig_file(const char* path, uint32_t k, std::string& seqs, std::vect
 int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t k, std::vector<uint64_t>& blob,
                      std::string& err);
 
-// One read as the reference's getReads delivers it.
+// Growable POD buffer over a caller-chosen allocator (the CLI plugs in pinned host memory so that
+// the batch can be copied to the GPU asynchronously).
+typedef void* (*AllocFn)(size_t);
+typedef void (*FreeFn)(void*);
+template <typename T>
+struct PodBuf {
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    AllocFn alloc = nullptr;
+    FreeFn dealloc = nullptr;
+    PodBuf() {}
+    PodBuf(const PodBuf&) = delete;
+    PodBuf& operator=(const PodBuf&) = delete;
+    ~PodBuf() { release(); }
+    void release() {
+        if (p) (dealloc ? dealloc : ::free)(p);
+        p = nullptr;
+        n = cap = 0;
+    }
+    void reserve(size_t need) {
+        if (need <= cap) return;
+        size_t c = cap ? cap : 1024;
+        while (c < need) c += c / 2 + 1;
+        T* q = (T*)(alloc ? alloc(c * sizeof(T)) : ::malloc(c * sizeof(T)));
+        if (p) {
+            memcpy(q, p, n * sizeof(T));
+            (dealloc ? dealloc : ::free)(p);
+        }
+        p = q;
+        cap = c;
+    }
+    void append(const T* s, size_t m) {
+        reserve(n + m + 16);
+        memcpy(p + n, s, m * sizeof(T));
+        n += m;
+    }
+    void push(T x) {
+        reserve(n + 1);
+        p[n++] = x;
+    }
+};
+
+// The reads one or more getReads calls delivered: headers and sequences, concatenated.
 struct ReadBatch {
-    std::string headers, seqs;
-    std::vector<uint64_t> hoff{0}, soff{0};
-    size_t size() const { return soff.size() - 1; }
+    PodBuf<char> headers, seqs;
+    PodBuf<uint64_t> hoff, soff;
+    ReadBatch() { clear(); }
+    void set_allocator(AllocFn a, FreeFn f) {
+        seqs.alloc = soff.alloc = a;
+        seqs.dealloc = soff.dealloc = f;
+    }
+    size_t size() const { return soff.n - 1; }
     void clear() {
-        headers.clear();
-        seqs.clear();
-        hoff.assign(1, 0);
-        soff.assign(1, 0);
+        headers.n = seqs.n = hoff.n = soff.n = 0;
+        hoff.push(0);
+        soff.push(0);
     }
     void push(const char* h, size_t hn, const char* s, size_t sn) {
         headers.append(h, hn);
         seqs.append(s, sn);
-        hoff.push_back(headers.size());
-        soff.push_back(seqs.size());
+        hoff.push(headers.n);
+        soff.push(seqs.n);
     }
 };
 

@@ -752,8 +752,10 @@ BGR_HD bool exhaustive_side(const DevIndex& ix, const ReadView& v, bool right, u
                                  : mismatches(ix, v, u, 0, rl - (i32)L, (i32)L, cap);
                 if (miss <= cap) {
                     if ((u32)depth + 1 >= lay.D) {
+                        // search stack too small: give up on this read at once, the host re-runs the
+                        // batch with a larger scratch (carrying on would only enumerate dead ends)
                         sc.overflow = true;
-                        continue;
+                        return false;
                     }
                     sc.set(lay.cur0 + (u32)depth, u.sid);
                     sc.set(fb + 4, (i32)(i + 1));
@@ -804,12 +806,18 @@ BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratc
         if (pos == 0) {
             sc.set(w++, 0);  // checkBeginExhaustive:159
         } else {
-            if (!exhaustive_side(ix, v, false, code, pos, a.errors, sc, lay, eb, nb, tb)) continue;
+            if (!exhaustive_side(ix, v, false, code, pos, a.errors, sc, lay, eb, nb, tb)) {
+                if (sc.overflow) break;
+                continue;
+            }
             // left part in output order: [offset] then the ids from the far end to the anchor
             if (tb >= 0) sc.set(w++, tb);
             for (u32 j = 0; j < nb; ++j) sc.set(w++, sc.get(lay.best0 + nb - 1 - j));
         }
-        if (!exhaustive_side(ix, v, true, code, pos, a.errors - eb, sc, lay, ee, ne, te)) continue;
+        if (!exhaustive_side(ix, v, true, code, pos, a.errors - eb, sc, lay, ee, ne, te)) {
+            if (sc.overflow) break;
+            continue;
+        }
         for (u32 j = 0; j < ne; ++j) sc.set(w++, sc.get(lay.best0 + j));
         sc.set(w++, te);
         n = w;

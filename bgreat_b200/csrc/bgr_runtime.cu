@@ -41,7 +41,7 @@ struct Slot {
     u64 chars = 0, words = 0;
     bgr_params params{};
     u32 scratch_ints = 0;
-    bool uploaded = false, ran = false, timed = false;
+    bool uploaded = false, ran = false, timed = false, counted = false;
     bgr_result* h_res = nullptr;
     i32* h_pool = nullptr;
     u64 h_pool_cap = 0;
@@ -423,6 +423,7 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     }
     s.ran = true;
     s.timed = true;
+    s.counted = false;
     return BGR_OK;
 }
 
@@ -466,10 +467,13 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
     }
     const u64 used = s.h_cnt->pool_cursor;
     if (pool_used) *pool_used = used;
-    for (int i = 0; i < BGR_C_COUNT; ++i) ctx->totals[i] += s.h_cnt->c[i];
-    s.ran = false;
+    if (!s.counted) {
+        for (int i = 0; i < BGR_C_COUNT; ++i) ctx->totals[i] += s.h_cnt->c[i];
+        s.counted = true;
+    }
     if (s.want_download) {
         s.want_download = false;
+        // the caller may come back with a larger pool: bgr_slot_download + bgr_slot_wait again
         if (used > s.h_pool_cap) return fail(ctx, BGR_ERR_LIMIT, "path pool buffer too small");
         if (s.n) CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.n * sizeof(bgr_result), cudaMemcpyDeviceToHost, s.stream));
         if (used) CK(cudaMemcpyAsync(s.h_pool, s.d_pool, (size_t)used * sizeof(i32), cudaMemcpyDeviceToHost, s.stream));

@@ -144,3 +144,42 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     for (int i = 0; i < BGR_C_COUNT; ++i) counters[i] = cnt.c[i];
     return BGR_OK;
 }
+
+// ---- host-logic hooks: the product's own parser / unitig loader (bgr_host.cpp), for CPU tests
+
+static char* dup_bytes(const char* p, size_t n) {
+    char* q = (char*)malloc(n + 1);
+    if (n) memcpy(q, p, n);
+    q[n] = 0;
+    return q;
+}
+static uint64_t* dup_u64(const uint64_t* p, size_t n) {
+    uint64_t* q = (uint64_t*)malloc(n * sizeof(uint64_t));
+    memcpy(q, p, n * sizeof(uint64_t));
+    return q;
+}
+
+extern "C" long emu_parse_reads(const char* path, uint32_t k, int fastq, uint32_t chunk, char** headers,
+                                uint64_t** hoff, char** seqs, uint64_t** soff) {
+    MappedFile mf;
+    if (!mf.open(path)) return -1;
+    ReadParser rp(mf.data, mf.size, k, fastq != 0);
+    ReadBatch rb;
+    while (!rp.done()) rp.next_chunk(chunk, rb);
+    *headers = dup_bytes(rb.headers.p, rb.headers.n);
+    *seqs = dup_bytes(rb.seqs.p, rb.seqs.n);
+    *hoff = dup_u64(rb.hoff.p, rb.hoff.n);
+    *soff = dup_u64(rb.soff.p, rb.soff.n);
+    return (long)rb.size();
+}
+
+extern "C" long emu_load_unitigs(const char* path, uint32_t k, char** seqs, uint64_t** off, int* opened) {
+    std::string s;
+    std::vector<uint64_t> o;
+    *opened = load_unitig_file(path, k, s, o) ? 1 : 0;
+    *seqs = dup_bytes(s.data(), s.size());
+    *off = dup_u64(o.data(), o.size());
+    return (long)o.size() - 1;
+}
+
+extern "C" void emu_free(void* p) { free(p); }

@@ -68,3 +68,38 @@ def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64):
         flags.append(fl)
     names = ["reads", "aligned", "not_aligned", "no_overlap", "overlaps", "windows"]
     return out, dict(zip(names, [int(c) for c in counters[:6]])), flags, bool(ovf.value)
+
+
+def parse_reads(path, k, fastq=False, chunk=10000):
+    """The PRODUCT's read parser (bgr_host.cpp ReadParser) -> [(header, read)] or None."""
+    L = lib()
+    L.emu_parse_reads.restype = C.c_long
+    ph, pho, ps, pso = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n = L.emu_parse_reads(os.fsencode(path), C.c_uint32(k), C.c_int(int(fastq)), C.c_uint32(chunk), C.byref(ph),
+                          C.byref(pho), C.byref(ps), C.byref(pso))
+    if n < 0:
+        return None
+    ho = C.cast(pho, C.POINTER(C.c_uint64))
+    so = C.cast(pso, C.POINTER(C.c_uint64))
+    hb = C.string_at(ph, ho[n])
+    sb = C.string_at(ps, so[n])
+    out = [(hb[ho[i]:ho[i + 1]], sb[so[i]:so[i + 1]]) for i in range(n)]
+    L.emu_free.argtypes = [C.c_void_p]
+    for p in (ph, pho, ps, pso):
+        L.emu_free(p)
+    return out
+
+
+def load_unitigs(path, k):
+    """The PRODUCT's unitig loader (bgr_host.cpp load_unitig_file) -> (opened, [sequences])."""
+    L = lib()
+    L.emu_load_unitigs.restype = C.c_long
+    ps, po, opened = C.c_void_p(), C.c_void_p(), C.c_int()
+    n = L.emu_load_unitigs(os.fsencode(path), C.c_uint32(k), C.byref(ps), C.byref(po), C.byref(opened))
+    off = C.cast(po, C.POINTER(C.c_uint64))
+    sb = C.string_at(ps, off[n])
+    out = [sb[off[i]:off[i + 1]] for i in range(n)]
+    L.emu_free.argtypes = [C.c_void_p]
+    L.emu_free(ps)
+    L.emu_free(po)
+    return bool(opened.value), out
