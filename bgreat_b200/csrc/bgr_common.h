@@ -98,24 +98,29 @@ BGR_HD u64 rev2(u64 x) { return rc64(~x); }
 // rcb(x, n) of the reference (utils.cpp:182-192): reverse complement of an n-base code
 BGR_HD u64 rcb(u64 x, u32 n) { return rc64(x) >> (64 - 2 * n); }
 
-// hash of a canonical (k-1)-mer -> bucket
-BGR_HD u64 key_hash(u64 key) {
-    key ^= key >> 29;
-    key *= 0x9E3779B97F4A7C15ull;
-    key ^= key >> 32;
-    return key * 0xD6E8FEB86659FD93ull;
+// hash of a canonical (k-1)-mer -> bucket. Kept to 32-bit integer ops on purpose: the seed-scan
+// kernel is instruction-issue bound (profiles/r01_ncu_k_pack_scan_v1.txt) and computes one per window.
+// n_buckets < 2^32.
+BGR_HD u32 key_hash(u64 key) {
+    u32 lo = (u32)key, hi = (u32)(key >> 32);
+    u32 h = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
 }
 BGR_HD u64 bucket_of(u64 key, u64 n_buckets) {
 #if defined(__CUDA_ARCH__)
-    return __umul64hi(key_hash(key), n_buckets);
+    return __umulhi(key_hash(key), (u32)n_buckets);
 #else
-    return (u64)(((unsigned __int128)key_hash(key) * n_buckets) >> 64);
+    return ((u64)key_hash(key) * (u64)(u32)n_buckets) >> 32;
 #endif
 }
 
 // word offset of read r's packed words inside a batch whose reads are concatenated characters:
-// read r occupies chars [o, o') and gets ceil(len/32)+2 words (one zero pad word in front, one
-// behind); floor(o/32) + 3r is a closed form that leaves at least that much room.
-BGR_HD u64 read_word_base(u64 char_off, u64 r) { return (char_off >> 5) + 3 * r; }
+// read r occupies chars [o, o') and gets ceil(len/32)+3 words (one zero pad word in front, two
+// behind); floor(o/32) + 4r is a closed form that leaves at least that much room.
+BGR_HD u64 read_word_base(u64 char_off, u64 r) { return (char_off >> 5) + 4 * r; }
+BGR_HD u64 batch_words(u64 chars, u64 n_reads) { return (chars >> 5) + 4 * n_reads + 8; }
 
 }  // namespace bgr

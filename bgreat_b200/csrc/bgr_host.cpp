@@ -234,6 +234,10 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     const u64 n_keys = keys.size();
     const u64 n_buckets = std::max<u64>(4, (n_keys + 1) / 2);  // <= 50% load: 2 of 4 slots on average
+    if (n_buckets >= 0xFFFFFFFFull) {
+        err = "too many distinct border k-mers for the 32-bit bucket hash";
+        return BGR_ERR_LIMIT;
+    }
 
     // ---- blob
     BlobHeader h;

@@ -43,12 +43,19 @@ struct DevIndex {
     u32 pad;
 };
 
+// Written by the extension kernel; reset before every (re-)run of it.
 struct DevCounters {
     unsigned long long pool_cursor;
     unsigned long long c[BGR_C_COUNT];
     u32 scratch_overflow;  // some path / search stack did not fit the per-read scratch
     u32 pool_overflow;     // the path pool was too small (pool_cursor = ints needed)
     u32 pad[2];
+};
+// Written by the pack + seed-scan kernel.
+struct ScanCounters {
+    unsigned long long c[BGR_C_COUNT];
+    u32 list_n;  // reads handed to the extension kernel (those with at least one border hit)
+    u32 pad[3];
 };
 
 struct BatchArgs {
@@ -66,6 +73,8 @@ struct BatchArgs {
     i32* pool;
     u64 pool_cap;
     DevCounters* cnt;
+    ScanCounters* scnt;
+    u32* list;  // indices of the reads the extension kernel has to look at (unordered)
     u32 errors, effort, mode;
 };
 
@@ -117,7 +126,7 @@ BGR_HD i64 index_find(const DevIndex& ix, u64 key) {
 // ------------------------------------------------------------------------------ pack + seed scan
 
 static const int PS_WARPS = 8;    // warps per block
-static const int PS_SWORDS = 20;  // shared words per warp and array: reads up to 576 bases stay on chip
+static const int PS_SWORDS = 21;  // shared words per warp and array: reads up to 576 bases stay on chip
 
 // 4 characters (one 32-bit word, first character in the low byte) -> 8 bits of 2-bit codes (first
 // character most significant) and 8 bits of N mask (0b11 per character that is not A/C/G/T; in the
@@ -173,96 +182,214 @@ BGR_HD void scan_window(const DevIndex& ix, const u64* D, const u64* ND, bool an
     }
 }
 
+// What the seed scan already knows about a read that has no border hit at all: greedy ->
+// getNOverlap returns an empty list -> ++noOverlapRead (alignerGreedy.cpp:37); exhaustive -> every
+// window fails -> ++notAligned (alignerExhaustive.cpp:55). A read of exactly k-1 bases maps trivially
+// in exhaustive mode ([0,0]) and is therefore always passed on.
+BGR_HD u32 no_hit_flags(bool exhaustive) {
+    return exhaustive ? (BGR_F_OVERLAP_FOUND | BGR_F_CNT_NOTALIGNED) : BGR_F_CNT_NOOVERLAP;
+}
+
+// spread the 8 bits of x to bit positions 0,4,8,...,28
+BGR_HD u32 spread8x4(u32 x) {
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x;
+}
+
+static const u32 PS_WPL = 4;  // consecutive windows per lane and round: 128 windows per round
+
+// Fast path of the seed scan (read without N): PS_WPL consecutive windows starting at w0. The first
+// one is extracted, the following ones roll the forward and the reverse-complement code like
+// update / updateRC do (aligner.cpp:305-315). Bit j of the result = window w0+j is a border.
+BGR_HD u32 scan_lane_rolling(const DevIndex& ix, const u64* D, u32 w0, u32 nwin) {
+    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1, top = 2 * (km1 - 1);
+    const u64 mask = ~0ull >> sh;
+    u32 hits = 0;
+    if (w0 < nwin) {
+        u64 num = ld_bases(D, w0) >> sh;
+        u64 nxt = ld_bases(D, w0 + km1);  // the bases that follow the first window
+        u64 rc = rcb(num, km1);
+#pragma unroll
+        for (u32 j = 0; j < PS_WPL; ++j) {
+            if (w0 + j < nwin) {
+                u64 rep = num < rc ? num : rc;
+                hits |= (u32)(index_find(ix, rep) >= 0) << j;
+            }
+            u64 nb = nxt >> 62;
+            nxt <<= 2;
+            num = ((num << 2) | nb) & mask;
+            rc = (rc >> 2) | ((3 - nb) << top);
+        }
+    }
+    return hits;
+}
+
+// Lane l holds windows 4l..4l+3; ballot[j] has window 4l+j in bit l. The hit mask wants window i in
+// bit i%32 of word i/32: word w = OR_j spread(byte w of ballot[j]) << j.
+BGR_HD u32 transpose_hits(const u32 ballot[PS_WPL], u32 w) {
+    u32 word = 0;
+#pragma unroll
+    for (u32 j = 0; j < PS_WPL; ++j) word |= spread8x4((ballot[j] >> (8 * w)) & 0xFFu) << j;
+    return word;
+}
+
 #if defined(__CUDACC__)
+// Pack one read into F/N (shared or global words, one call site each so that the address space is
+// known at compile time), then scan its windows. Returns (any hit in H1, any in H2, has N).
+__device__ __forceinline__ u32 pack_and_scan(const DevIndex& ix, const BatchArgs& a, u64* F, u64* N, const u64 o,
+                                             const u32 len, const u64 wb, const bool exhaustive, const u32 lane) {
+    const u32 km1 = ix.k - 1;
+    const u32 nw = (len + 31) >> 5;
+    if (lane == 0) {  // pad words: one in front, two behind (the rolling scan looks one word ahead)
+        F[0] = 0;
+        N[0] = 0;
+        F[nw + 1] = 0;
+        N[nw + 1] = 0;
+        F[nw + 2] = 0;
+        N[nw + 2] = 0;
+    }
+    // ---- pack: 128 characters per pass, 4 per lane, coalesced 4-byte loads
+    const unsigned char* src = (const unsigned char*)a.seq + o;
+    bool anyN = false;
+    for (u32 base = 0; base < nw * 32; base += 128) {
+        u32 c0 = base + 4 * lane;
+        if (c0 < nw * 32) {
+            u32 x = 0x41414141u;
+            if (c0 < len) {
+                uintptr_t ad = (uintptr_t)(src + c0);
+                const u32* wp = (const u32*)(ad & ~(uintptr_t)3);
+                u32 bs = (u32)(ad & 3) * 8;
+                u32 w0 = __ldg(wp), w1 = bs ? __ldg(wp + 1) : 0u;
+                x = __funnelshift_r(w0, w1, bs);
+                u32 left = len - c0;  // characters of this word that belong to the read
+                if (left < 4) {
+                    u32 keep = (1u << (8 * left)) - 1;
+                    x = (x & keep) | (0x41414141u & ~keep);
+                }
+            }
+            u32 code8, nm8;
+            pack4(x, code8, nm8);
+            u32 byte = packed_byte(c0);
+            ((unsigned char*)F)[byte] = (unsigned char)code8;
+            ((unsigned char*)N)[byte] = (unsigned char)nm8;
+            anyN |= nm8 != 0;
+        }
+    }
+    anyN = __any_sync(0xFFFFFFFFu, anyN);
+    __syncwarp();
+    // ---- seed scan
+    const u64* D = F + 1;
+    const u64* ND = N + 1;
+    const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
+    u32 any1 = 0, any2 = 0;
+    if (!anyN) {
+        for (u32 base = 0; base < nwin; base += 32 * PS_WPL) {
+            const u32 hits = scan_lane_rolling(ix, D, base + PS_WPL * lane, nwin);
+            u32 ballot[PS_WPL];
+#pragma unroll
+            for (u32 j = 0; j < PS_WPL; ++j) ballot[j] = __ballot_sync(0xFFFFFFFFu, (hits >> j) & 1u);
+            // lanes 0..3 hold the words for windows base+32*lane ..
+            const u32 word = transpose_hits(ballot, lane & 3);
+            if (lane < 4 && base + 32 * lane < nwin) a.H1[wb + (base >> 5) + lane] = word;
+            any1 |= ballot[0] | ballot[1] | ballot[2] | ballot[3];
+        }
+    } else {
+        for (u32 base = 0; base < nwin; base += 32) {
+            u32 i = base + lane;
+            bool hit1 = false, hit2 = false;
+            if (i < nwin) scan_window(ix, D, ND, true, exhaustive, i, hit1, hit2);
+            u32 m1 = __ballot_sync(0xFFFFFFFFu, hit1);
+            u32 m2 = __ballot_sync(0xFFFFFFFFu, hit2);
+            any1 |= m1;
+            any2 |= m2;
+            if (lane == 0) {
+                a.H1[wb + (base >> 5)] = m1;
+                a.H2[wb + (base >> 5)] = m2;
+            }
+        }
+    }
+    return (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
+}
+
 __global__ void __launch_bounds__(PS_WARPS * 32) k_pack_scan(DevIndex ix, BatchArgs a) {
     __shared__ u64 sF[PS_WARPS][PS_SWORDS];
     __shared__ u64 sN[PS_WARPS][PS_SWORDS];
+    __shared__ u32 s_list[PS_WARPS][32];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 nwarps = gridDim.x * PS_WARPS;
     const u32 km1 = ix.k - 1;
     const bool exhaustive = a.mode != BGR_MODE_GREEDY;
-    unsigned long long windows = 0;
+    unsigned long long windows = 0, n_reads = 0, n_nohit = 0;
+    u32 n_list = 0;  // reads buffered in s_list[warp]
 
     for (u32 r = blockIdx.x * PS_WARPS + warp; r < a.n; r += nwarps) {
         const u64 o = a.off[r];
         const u32 len = (u32)(a.off[r + 1] - o);
         const u64 wb = read_word_base(o, r);
         const u32 nw = (len + 31) >> 5;
-        const bool on_chip = nw + 2 <= (u32)PS_SWORDS;
+        const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
         u64* gF = a.F + wb;
         u64* gN = a.NM + wb;
-        u64* F = on_chip ? sF[warp] : gF;
-        u64* N = on_chip ? sN[warp] : gN;
+        u32 info;
         __syncwarp();  // the previous read's shared words are no longer in use
-        if (lane == 0) {  // pad words, front and back
-            F[0] = 0;
-            N[0] = 0;
-            F[nw + 1] = 0;
-            N[nw + 1] = 0;
-        }
-        // ---- pack: 128 characters per pass, 4 per lane
-        const unsigned char* src = (const unsigned char*)a.seq + o;
-        bool anyN = false;
-        for (u32 base = 0; base < nw * 32; base += 128) {
-            u32 c0 = base + 4 * lane;
-            if (c0 < nw * 32) {
-                u32 x = 0x41414141u;
-                if (c0 < len) {
-                    // unaligned 4-byte load out of two aligned words
-                    uintptr_t ad = (uintptr_t)(src + c0);
-                    const u32* wp = (const u32*)(ad & ~(uintptr_t)3);
-                    u32 bs = (u32)(ad & 3) * 8;
-                    u32 w0 = __ldg(wp), w1 = bs ? __ldg(wp + 1) : 0u;
-                    x = __funnelshift_r(w0, w1, bs);
-                    u32 left = len - c0;  // characters of this word that belong to the read
-                    if (left < 4) {
-                        u32 keep = (1u << (8 * left)) - 1;
-                        x = (x & keep) | (0x41414141u & ~keep);
-                    }
+        if (nw + 3 <= (u32)PS_SWORDS) {
+            info = pack_and_scan(ix, a, sF[warp], sN[warp], o, len, wb, exhaustive, lane);
+            // keep the packed words for the extension kernel
+            const bool hasN = (info & INFO_HAS_N) != 0;
+            const bool needed = (info & (INFO_HIT1 | INFO_HIT2)) != 0;
+            if (needed)
+                for (u32 j = lane; j < nw + 3; j += 32) {
+                    gF[j] = sF[warp][j];
+                    if (hasN) gN[j] = sN[warp][j];
                 }
-                u32 code8, nm8;
-                pack4(x, code8, nm8);
-                u32 byte = packed_byte(c0);
-                ((unsigned char*)F)[byte] = (unsigned char)code8;
-                ((unsigned char*)N)[byte] = (unsigned char)nm8;
-                anyN |= nm8 != 0;
-            }
-        }
-        anyN = __any_sync(0xFFFFFFFFu, anyN);
-        __syncwarp();
-        if (on_chip) {
-            for (u32 j = lane; j < nw + 2; j += 32) {
-                gF[j] = F[j];
-                if (anyN) gN[j] = N[j];
-            }
         } else {
-            __threadfence_block();
-            __syncwarp();
+            // long read: the words live in HBM; the warp reads back what it wrote
+            info = pack_and_scan(ix, a, gF, gN, o, len, wb, exhaustive, lane);
         }
-        // ---- seed scan
-        const u64* D = F + 1;
-        const u64* ND = N + 1;
-        const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
-        u32 any1 = 0, any2 = 0;
-        for (u32 base = 0; base < nwin; base += 32) {
-            u32 i = base + lane;
-            bool hit1 = false, hit2 = false;
-            if (i < nwin) scan_window(ix, D, ND, anyN, exhaustive, i, hit1, hit2);
-            u32 m1 = __ballot_sync(0xFFFFFFFFu, hit1);
-            any1 |= m1;
-            if (lane == 0) a.H1[wb + (base >> 5)] = m1;
-            if (anyN) {
-                u32 m2 = __ballot_sync(0xFFFFFFFFu, hit2);
-                any2 |= m2;
-                if (lane == 0) a.H2[wb + (base >> 5)] = m2;
+        const bool pass_on = (info & INFO_HIT1) || (exhaustive && len == km1);
+        if (lane == 0) {
+            a.info[r] = info;
+            windows += nwin;
+            n_reads += 1;
+            if (pass_on) {
+                s_list[warp][n_list] = r;
+            } else {
+                bgr_result res;
+                res.flags_len = no_hit_flags(exhaustive);
+                res.path_off = 0;
+                a.res[r] = res;
+                n_nohit += 1;
             }
         }
-        if (lane == 0) {
-            a.info[r] = (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
-            windows += nwin;
+        if (pass_on) ++n_list;
+        if (n_list == 32) {  // flush: one atomic per 32 listed reads
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(&a.scnt->list_n, 32u);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            __syncwarp();
+            a.list[base + lane] = s_list[warp][lane];
+            n_list = 0;
         }
     }
-    if (lane == 0 && windows) atomicAdd(&a.cnt->c[BGR_C_WINDOWS], windows);
+    __syncwarp();
+    if (n_list) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(&a.scnt->list_n, n_list);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (lane < n_list) a.list[base + lane] = s_list[warp][lane];
+    }
+    if (lane == 0) {
+        if (windows) atomicAdd(&a.scnt->c[BGR_C_WINDOWS], windows);
+        if (n_reads) atomicAdd(&a.scnt->c[BGR_C_READS], n_reads);
+        if (exhaustive) {
+            if (windows) atomicAdd(&a.scnt->c[BGR_C_OVERLAPS], windows);  // overlaps += listOverlap.size()
+            if (n_nohit) atomicAdd(&a.scnt->c[BGR_C_NOTALIGNED], n_nohit);
+        } else if (n_nohit) {
+            atomicAdd(&a.scnt->c[BGR_C_NOOVERLAP], n_nohit);
+        }
+    }
 }
 #endif  // __CUDACC__
 
@@ -626,12 +753,213 @@ BGR_HD ReadSetup setup_read(const DevIndex& ix, const BatchArgs& a, u32 r) {
 
 // alignReadGreedy (alignerGreedy.cpp:35-57) for read r. The path is left in scratch as
 // [0, nl) = pathBegin in push order (to be reversed) followed by [nl, n) = pathEnd.
+//
+// Written as ONE loop whose body is "settle the current level / pick the next seed / query the index"
+// followed by "compare one candidate unitig": threads of a warp work on different reads and are at
+// different points of their walks, but they all execute this same body, so the warp stays converged
+// (the first version, a call tree of walkers, ran with 1.65 of 32 lanes active:
+// profiles/r01_ncu_k_extend_greedy_v1.txt). The walkers greedy_left / greedy_right above are the
+// readable statement of the same procedure and are kept for the emulator's cross-check.
+enum { GP_SEED = 0, GP_LEFT = 1, GP_RIGHT_FIRST = 2, GP_RIGHT_MORE = 3, GP_DONE = 4 };
+
 BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    const i64 km1 = ix.k - 1;
+    u32 flags = 0;
+    n = nl = 0;
+    // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
+    const i32 lim = a.effort ? s.nwin : 1;
+    const u32 max_seeds = a.effort ? a.effort : 1;
+    SeedIter it;
+    it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, lim);
+    u32 tried = 0, phase = GP_SEED;
+    // walk state
+    u64 code = 0, seed_c = 0, next_code = 0;
+    i32 pos = 0, seed_pos = 0, offset = 0, best_sid = 0;
+    i64 next_L = 0;
+    u32 budget = 0, acc = 0, best = 0, eb = 0;
+    bool ended = false, level_open = false;
+    // candidates of the current level
+    Cands c;
+    c.n = 0;
+    c.fwd_bit = 0;
+    c.raw[0] = c.raw[1] = c.raw[2] = c.raw[3] = 0;
+    int ci = 0;
+
+    while (phase != GP_DONE) {
+        if (ci >= c.n) {
+            // ---- settle the level whose candidates have all been compared
+            if (level_open) {
+                level_open = false;
+                if (best > budget) {
+                    phase = GP_SEED;  // this seed failed
+                } else {
+                    sc.set(n++, best_sid);
+                    if (ended) {
+                        if (phase == GP_LEFT) {
+                            sc.set(n++, offset);
+                            eb = acc + best;
+                            nl = n;
+                            phase = GP_RIGHT_FIRST;
+                            budget = a.errors - eb;
+                            acc = 0;
+                            code = seed_c;
+                            pos = seed_pos;
+                        } else {
+                            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
+                            phase = GP_DONE;
+                        }
+                    } else {
+                        acc += best;
+                        budget -= best;
+                        code = next_code;
+                        if (phase == GP_LEFT) pos -= (i32)next_L;
+                        else {
+                            pos += (i32)next_L;
+                            phase = GP_RIGHT_MORE;
+                        }
+                    }
+                }
+            }
+            // ---- next seed (possibly switching to the reverse-complement pass)
+            for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
+                i32 p = tried < max_seeds ? it.next() : -1;
+                if (p >= 0) {
+                    ++tried;
+                    seed_c = code = seed_code(ix, v, p);
+                    seed_pos = pos = p;
+                    budget = a.errors;
+                    acc = 0;
+                    n = 0;
+                    phase = GP_LEFT;
+                } else if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
+                    flags |= BGR_F_CNT_NOOVERLAP;
+                    n = 0;
+                    phase = GP_DONE;
+                } else if (!v.pass) {  // every seed failed: rc=true, retry on the reverse complement
+                    flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
+                    v.pass = true;
+                    const bool useH2 = v.hasN;
+                    const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
+                    it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, true, lim);
+                    tried = 0;
+                } else {
+                    flags |= BGR_F_CNT_NOTALIGNED;
+                    n = 0;
+                    phase = GP_DONE;
+                }
+            }
+            // ---- ends of walks that need no index query
+            if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
+                sc.set(n++, 0);
+                eb = acc;
+                nl = n;
+                phase = GP_RIGHT_FIRST;
+                budget = a.errors - eb;
+                acc = 0;
+                code = seed_c;
+                pos = seed_pos;
+            }
+            if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) {  // checkEndGreedy:324
+                flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
+                phase = GP_DONE;
+            }
+            if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) {  // mapOnRightEndGreedy:223
+                flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
+                phase = GP_DONE;
+            }
+            // ---- candidates of the new level: getEnd on the way left, getBegin on the way right
+            if (phase != GP_DONE) {
+                c = index_query(ix, code, phase == GP_LEFT);
+                ci = 0;
+                best = budget + 1;
+                ended = false;
+                level_open = true;
+            } else {
+                c.n = 0;
+                ci = 0;
+            }
+        }
+        // ---- compare one candidate
+        if (phase != GP_DONE && ci < c.n) {
+            Oriented u = orient(ix, c, ci);
+            ++ci;
+            const i64 L = u.len - km1;
+            bool ends_here;
+            i64 upos;
+            i32 rpos, nn;
+            if (phase == GP_LEFT) {
+                // unitig covers the rest: unitig[L-pos, L) vs read[0,pos); else unitig[0,L) vs read[pos-L,pos)
+                ends_here = L >= pos;
+                upos = ends_here ? L - pos : 0;
+                rpos = ends_here ? 0 : pos - (i32)L;
+                nn = ends_here ? pos : (i32)L;
+            } else if (phase == GP_RIGHT_FIRST) {
+                // comparisons start after the anchor overlap
+                const i32 rstart = pos + (i32)km1, rl = v.len - rstart;
+                ends_here = L >= rl;
+                upos = km1;
+                rpos = rstart;
+                nn = ends_here ? rl : (i32)L;
+            } else {
+                // the remaining read starts AT the overlap; whole unitig compared, cut at the read end
+                const i32 rl = v.len - pos;
+                ends_here = L >= rl;
+                upos = 0;
+                rpos = pos;
+                nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
+            }
+            const u32 miss = mismatches(ix, v, u, upos, rpos, nn, budget);
+            if (miss == 0) {  // accepted at once (quirk 9)
+                sc.set(n++, u.sid);
+                level_open = false;
+                ci = c.n;
+                if (ends_here) {
+                    if (phase == GP_LEFT) {
+                        sc.set(n++, (i32)(L - pos));
+                        eb = acc;
+                        nl = n;
+                        phase = GP_RIGHT_FIRST;
+                        budget = a.errors - eb;
+                        acc = 0;
+                        code = seed_c;
+                        pos = seed_pos;
+                    } else {
+                        flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
+                        phase = GP_DONE;
+                    }
+                } else if (phase == GP_LEFT) {
+                    code = first_code(ix, u);
+                    pos -= (i32)L;
+                } else {
+                    code = last_code(ix, u);
+                    pos += (i32)L;
+                    phase = GP_RIGHT_MORE;
+                }
+            } else if (miss < best) {
+                best = miss;
+                best_sid = u.sid;
+                ended = ends_here;
+                if (ends_here) {
+                    offset = (i32)(L - pos);
+                } else {
+                    next_L = L;
+                    next_code = (phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u);
+                }
+            }
+        }
+    }
+    if (!(flags & BGR_F_MAPPED)) n = 0;
+    return flags;
+}
+
+// Reference-shaped version (walkers called in sequence); tests/emu checks that both agree.
+BGR_HD u32 greedy_read_walkers(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
     ReadSetup s = setup_read(ix, a, r);
     ReadView& v = s.v;
     u32 flags = 0;
     n = nl = 0;
-    // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
     const i32 lim = a.effort ? s.nwin : 1;
     const u32 max_seeds = a.effort ? a.effort : 1;
     for (int pass = 0; pass < 2; ++pass) {
@@ -654,12 +982,11 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
             flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (pass ? BGR_F_RC : 0u);
             return flags;
         }
-        if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
+        if (tried == 0) {
             flags |= BGR_F_CNT_NOOVERLAP;
             n = 0;
             return flags;
         }
-        // every seed failed: rc=true, retry on the reverse complement (alignerGreedy.cpp:54), or give up
         flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
     }
     flags |= BGR_F_CNT_NOTALIGNED;
@@ -865,51 +1192,49 @@ __device__ __forceinline__ void emit_result(const BatchArgs& a, u32 r, bool vali
     a.res[r] = res;
 }
 
-__device__ __forceinline__ void count_classes(const BatchArgs& a, bool valid, u32 flags, u32 overlaps) {
+__device__ __forceinline__ void count_classes(const BatchArgs& a, bool valid, u32 flags) {
+    // reads and window counts are tallied by the seed-scan kernel; here only the outcome classes
     const u32 lane = threadIdx.x & 31;
-    u32 m_reads = __ballot_sync(0xFFFFFFFFu, valid);
     u32 m_al = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_ALIGNED));
     u32 m_na = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_NOTALIGNED));
     u32 m_no = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_NOOVERLAP));
-    u32 ov = valid ? overlaps : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ov += __shfl_xor_sync(0xFFFFFFFFu, ov, d);
     if (lane == 0) {
-        if (m_reads) atomicAdd(&a.cnt->c[BGR_C_READS], (unsigned long long)__popc(m_reads));
         if (m_al) atomicAdd(&a.cnt->c[BGR_C_ALIGNED], (unsigned long long)__popc(m_al));
         if (m_na) atomicAdd(&a.cnt->c[BGR_C_NOTALIGNED], (unsigned long long)__popc(m_na));
         if (m_no) atomicAdd(&a.cnt->c[BGR_C_NOOVERLAP], (unsigned long long)__popc(m_no));
-        if (ov) atomicAdd(&a.cnt->c[BGR_C_OVERLAPS], (unsigned long long)ov);
     }
 }
 
 static const int EXT_THREADS = 128;
 
+// thread t takes the t-th read of the hit list the seed-scan kernel produced
 __global__ void __launch_bounds__(EXT_THREADS) k_extend_greedy(DevIndex ix, BatchArgs a) {
-    const u32 r = blockIdx.x * EXT_THREADS + threadIdx.x;
-    const bool valid = r < a.n;
+    const u32 t = blockIdx.x * EXT_THREADS + threadIdx.x;
+    const bool valid = t < a.scnt->list_n;
+    const u32 r = valid ? a.list[t] : 0;
     Scratch sc;
-    sc.base = a.scratch + (valid ? r : 0);
+    sc.base = a.scratch + (valid ? t : 0);
     sc.stride = a.n;
     sc.cap = a.scratch_ints;
     sc.overflow = false;
     u32 flags = 0, n = 0, nl = 0;
     if (valid) flags = greedy_read(ix, a, r, sc, n, nl);
-    count_classes(a, valid, flags, 0);
+    count_classes(a, valid, flags);
     emit_result(a, r, valid, flags, sc, n, nl);
 }
 
 __global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, BatchArgs a) {
-    const u32 r = blockIdx.x * EXT_THREADS + threadIdx.x;
-    const bool valid = r < a.n;
+    const u32 t = blockIdx.x * EXT_THREADS + threadIdx.x;
+    const bool valid = t < a.scnt->list_n;
+    const u32 r = valid ? a.list[t] : 0;
     Scratch sc;
-    sc.base = a.scratch + (valid ? r : 0);
+    sc.base = a.scratch + (valid ? t : 0);
     sc.stride = a.n;
     sc.cap = a.scratch_ints;
     sc.overflow = false;
     u32 flags = 0, n = 0, overlaps = 0;
     if (valid) flags = exhaustive_read(ix, a, r, sc, n, overlaps);
-    count_classes(a, valid, flags, overlaps);
+    count_classes(a, valid, flags);
     emit_result(a, r, valid, flags, sc, n, 0);
 }
 

@@ -36,6 +36,9 @@ struct Slot {
     size_t cap_pool = 0;  // ints
     DevCounters* d_cnt = nullptr;
     DevCounters* h_cnt = nullptr;  // pinned
+    ScanCounters* d_scnt = nullptr;
+    ScanCounters* h_scnt = nullptr;  // pinned
+    u32* d_list = nullptr;
     // current batch
     u32 n = 0;
     u64 chars = 0, words = 0;
@@ -157,6 +160,8 @@ BatchArgs make_args(Slot& s) {
     a.pool = s.d_pool;
     a.pool_cap = s.cap_pool;
     a.cnt = s.d_cnt;
+    a.scnt = s.d_scnt;
+    a.list = s.d_list;
     a.errors = s.params.errors;
     a.effort = s.params.effort;
     a.mode = s.params.mode;
@@ -213,6 +218,8 @@ int bgr_ctx_create(int device, int n_slots, bgr_ctx** out) {
         for (int j = 0; j < 3 && e == cudaSuccess; ++j) e = cudaEventCreate(&s.ev[j]);
         if (e == cudaSuccess) e = cudaMalloc((void**)&s.d_cnt, sizeof(DevCounters));
         if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.h_cnt, sizeof(DevCounters), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.d_scnt, sizeof(ScanCounters));
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.h_scnt, sizeof(ScanCounters), cudaHostAllocDefault);
         if (e != cudaSuccess) {
             std::string m = std::string("slot setup: ") + cudaGetErrorString(e);
             bgr_ctx_destroy(ctx);
@@ -240,7 +247,10 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
         cudaFree(s.d_scratch);
         cudaFree(s.d_pool);
         cudaFree(s.d_cnt);
+        cudaFree(s.d_scnt);
+        cudaFree(s.d_list);
         if (s.h_cnt) cudaFreeHost(s.h_cnt);
+        if (s.h_scnt) cudaFreeHost(s.h_scnt);
         for (int j = 0; j < 3; ++j)
             if (s.ev[j]) cudaEventDestroy(s.ev[j]);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -362,15 +372,16 @@ int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* of
     Slot& s = ctx->slots[slot];
     CK(cudaSetDevice(ctx->device));
     const u64 chars = off[n];
-    const u64 words = (chars >> 5) + 3ull * n + 4;
+    const u64 words = batch_words(chars, n);
     int rc;
     if ((rc = grow(ctx, s.d_seq, s.cap_seq, (size_t)chars + 16))) return rc;
     if (n + 1 > s.cap_reads || !s.d_off) {
-        size_t cap = 0, c2 = 0, c3 = 0;
+        size_t cap = 0, c2 = 0, c3 = 0, c4 = 0;
         if ((rc = grow(ctx, s.d_off, cap, (size_t)n + 1))) return rc;
         if ((rc = grow(ctx, s.d_res, c2, (size_t)n + 1))) return rc;
         if ((rc = grow(ctx, s.d_info, c3, (size_t)n + 1))) return rc;
-        s.cap_reads = std::min(cap, std::min(c2, c3));
+        if ((rc = grow(ctx, s.d_list, c4, (size_t)n + 1))) return rc;
+        s.cap_reads = std::min(std::min(cap, c4), std::min(c2, c3));
     }
     if (words > s.cap_words || !s.d_F) {
         size_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -403,6 +414,7 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     s.params = *p;
     s.scratch_ints = (p->mode == BGR_MODE_GREEDY) ? ctx->scratch_greedy : ctx->scratch_exhaustive;
     CK(cudaMemsetAsync(s.d_cnt, 0, sizeof(DevCounters), s.stream));
+    CK(cudaMemsetAsync(s.d_scnt, 0, sizeof(ScanCounters), s.stream));
     CK(cudaEventRecord(s.ev[0], s.stream));
     if (s.n) {
         BatchArgs a = make_args(s);
@@ -414,6 +426,7 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[1], s.stream));
+    CK(cudaMemcpyAsync(s.h_scnt, s.d_scnt, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s.stream));
     if (s.n) {
         int rc = enqueue_extension(ctx, s);
         if (rc) return rc;
@@ -448,7 +461,6 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
     // scratch / pool too small: grow and redo the extension kernel (the seed scan's output is kept)
     for (int attempt = 0; s.n && (s.h_cnt->scratch_overflow || s.h_cnt->pool_overflow); ++attempt) {
         if (attempt > 24) return fail(ctx, BGR_ERR_LIMIT, "extension scratch keeps overflowing");
-        unsigned long long windows = s.h_cnt->c[BGR_C_WINDOWS];
         if (s.h_cnt->scratch_overflow) {
             s.scratch_ints *= 4;
             if (s.params.mode == BGR_MODE_GREEDY) ctx->scratch_greedy = s.scratch_ints;
@@ -462,13 +474,12 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
         int rc = enqueue_extension(ctx, s);
         if (rc) return rc;
         CK(cudaStreamSynchronize(s.stream));
-        s.h_cnt->c[BGR_C_WINDOWS] = windows;
         s.timed = false;  // event pair no longer brackets a single pass
     }
     const u64 used = s.h_cnt->pool_cursor;
     if (pool_used) *pool_used = used;
     if (!s.counted) {
-        for (int i = 0; i < BGR_C_COUNT; ++i) ctx->totals[i] += s.h_cnt->c[i];
+        for (int i = 0; i < BGR_C_COUNT; ++i) ctx->totals[i] += s.h_cnt->c[i] + s.h_scnt->c[i];
         s.counted = true;
     }
     if (s.want_download) {

@@ -37,12 +37,14 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     ix.pad = 0;
 
     const u64 chars = off[n];
-    const u64 words = (chars >> 5) + 3ull * n + 4;
+    const u64 words = batch_words(chars, n);
     std::vector<u64> F(words, 0xDEADBEEFDEADBEEFull), NM(words, 0xDEADBEEFDEADBEEFull);
-    std::vector<u32> H1(words, 0xFFFFFFFFu), H2(words, 0xFFFFFFFFu), info(n + 1, 0);
+    std::vector<u32> H1(words, 0xFFFFFFFFu), H2(words, 0xFFFFFFFFu), info(n + 1, 0), list(n + 1, 0);
     std::vector<i32> scratch((size_t)n * scratch_ints + 1, 0);
     DevCounters cnt;
+    ScanCounters scnt;
     memset(&cnt, 0, sizeof cnt);
+    memset(&scnt, 0, sizeof scnt);
     BatchArgs a;
     a.seq = seqs;
     a.off = off;
@@ -58,6 +60,8 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     a.pool = pool;
     a.pool_cap = pool_cap;
     a.cnt = &cnt;
+    a.scnt = &scnt;
+    a.list = list.data();
     a.errors = errors;
     a.effort = effort;
     a.mode = mode;
@@ -74,6 +78,7 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         u64* gN = a.NM + wb;
         gF[0] = gN[0] = 0;
         gF[nw + 1] = gN[nw + 1] = 0;
+        gF[nw + 2] = gN[nw + 2] = 0;
         bool anyN = false;
         for (u32 c0 = 0; c0 < nw * 32; c0 += 4) {
             u32 x = 0x41414141u;
@@ -92,42 +97,80 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         }
         const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
         u32 any1 = 0, any2 = 0;
-        for (u32 base = 0; base < nwin; base += 32) {
-            u32 m1 = 0, m2 = 0;
-            for (u32 lane = 0; lane < 32; ++lane) {
-                u32 i = base + lane;
-                bool h1 = false, h2 = false;
-                if (i < nwin) scan_window(ix, gF + 1, gN + 1, anyN, exhaustive, i, h1, h2);
-                m1 |= (u32)h1 << lane;
-                m2 |= (u32)h2 << lane;
+        if (!anyN) {
+            for (u32 base = 0; base < nwin; base += 32 * PS_WPL) {
+                u32 ballot[PS_WPL] = {0, 0, 0, 0};
+                for (u32 lane = 0; lane < 32; ++lane) {
+                    u32 hits = scan_lane_rolling(ix, gF + 1, base + PS_WPL * lane, nwin);
+                    for (u32 j = 0; j < PS_WPL; ++j) ballot[j] |= ((hits >> j) & 1u) << lane;
+                }
+                for (u32 lane = 0; lane < 4; ++lane)
+                    if (base + 32 * lane < nwin) a.H1[wb + (base >> 5) + lane] = transpose_hits(ballot, lane);
+                any1 |= ballot[0] | ballot[1] | ballot[2] | ballot[3];
             }
-            any1 |= m1;
-            any2 |= m2;
-            a.H1[wb + (base >> 5)] = m1;
-            if (anyN) a.H2[wb + (base >> 5)] = m2;
+        } else {
+            for (u32 base = 0; base < nwin; base += 32) {
+                u32 m1 = 0, m2 = 0;
+                for (u32 lane = 0; lane < 32; ++lane) {
+                    u32 i = base + lane;
+                    bool h1 = false, h2 = false;
+                    if (i < nwin) scan_window(ix, gF + 1, gN + 1, true, exhaustive, i, h1, h2);
+                    m1 |= (u32)h1 << lane;
+                    m2 |= (u32)h2 << lane;
+                }
+                any1 |= m1;
+                any2 |= m2;
+                a.H1[wb + (base >> 5)] = m1;
+                a.H2[wb + (base >> 5)] = m2;
+            }
         }
-        a.info[r] = (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
-        cnt.c[BGR_C_WINDOWS] += nwin;
+        const u32 inf = (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
+        a.info[r] = inf;
+        scnt.c[BGR_C_WINDOWS] += nwin;
+        scnt.c[BGR_C_READS] += 1;
+        if (exhaustive) scnt.c[BGR_C_OVERLAPS] += nwin;
+        const bool pass_on = (inf & INFO_HIT1) || (exhaustive && len == km1);
+        if (pass_on) {
+            a.list[scnt.list_n++] = r;
+        } else {
+            res[r].flags_len = no_hit_flags(exhaustive);
+            res[r].path_off = 0;
+            scnt.c[exhaustive ? BGR_C_NOTALIGNED : BGR_C_NOOVERLAP] += 1;
+        }
     }
 
-    // ---- k_extend_*, one "thread" per read, then emit_result / count_classes
+    // ---- k_extend_*, one "thread" per listed read, then emit_result / count_classes
     *scratch_overflow = 0;
-    for (u32 r = 0; r < n; ++r) {
+    for (u32 t = 0; t < scnt.list_n; ++t) {
+        const u32 r = a.list[t];
         Scratch sc;
-        sc.base = a.scratch + r;
+        sc.base = a.scratch + t;
         sc.stride = n;
         sc.cap = scratch_ints;
         sc.overflow = false;
         u32 flags = 0, np = 0, nl = 0, overlaps = 0;
-        if (mode == BGR_MODE_GREEDY) flags = greedy_read(ix, a, r, sc, np, nl);
-        else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH)
+        if (mode == BGR_MODE_GREEDY) {
+            flags = greedy_read(ix, a, r, sc, np, nl);
+            // cross-check: the loop-shaped kernel body against the walker-shaped statement
+            Scratch sc2 = sc;
+            std::vector<i32> tmp((size_t)scratch_ints + 1, 0);
+            sc2.base = tmp.data();
+            sc2.stride = 1;
+            sc2.overflow = false;
+            u32 np2 = 0, nl2 = 0;
+            u32 flags2 = greedy_read_walkers(ix, a, r, sc2, np2, nl2);
+            bool same = flags2 == flags && (!(flags & BGR_F_MAPPED) || (np2 == np && nl2 == nl));
+            if (same && (flags & BGR_F_MAPPED) && !sc.overflow && !sc2.overflow)
+                for (u32 j = 0; j < np; ++j) same = same && sc.get(j) == sc2.get(j);
+            if (!same && !sc.overflow && !sc2.overflow) return 1000;  // the two formulations disagree
+        } else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH) {
             flags = exhaustive_read(ix, a, r, sc, np, overlaps);
-        else return BGR_ERR_ARG;
-        cnt.c[BGR_C_READS]++;
+        } else {
+            return BGR_ERR_ARG;
+        }
         if (flags & BGR_F_CNT_ALIGNED) cnt.c[BGR_C_ALIGNED]++;
         if (flags & BGR_F_CNT_NOTALIGNED) cnt.c[BGR_C_NOTALIGNED]++;
         if (flags & BGR_F_CNT_NOOVERLAP) cnt.c[BGR_C_NOOVERLAP]++;
-        cnt.c[BGR_C_OVERLAPS] += overlaps;
         u32 plen = (flags & BGR_F_MAPPED) ? np : 0;
         if (sc.overflow) {
             *scratch_overflow = 1;
@@ -141,7 +184,7 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         res[r].path_off = (u32)offp;
     }
     *used = cnt.pool_cursor;
-    for (int i = 0; i < BGR_C_COUNT; ++i) counters[i] = cnt.c[i];
+    for (int i = 0; i < BGR_C_COUNT; ++i) counters[i] = cnt.c[i] + scnt.c[i];
     return BGR_OK;
 }
 
