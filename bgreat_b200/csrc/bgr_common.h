@@ -10,6 +10,12 @@
 //   payload : Payload[n_buckets * 4]  per key slot: left[4] + right[4] unitig slots (32 bytes),
 //                                     the reference's two unitigIndices tables merged
 //                                     (reference aligner.h:49-55, aligner.cpp:463-533)
+//   filter  : u32[n_fbuckets * 8]     negative filter in front of `keys` for the seed scan: one bucket =
+//                                     8 tags = one 32-byte sector, ~2 tags per bucket on average. Every
+//                                     key has its tag in its home bucket (no probing), so "no tag equal"
+//                                     proves absence; a bucket that received more than 8 keys is marked
+//                                     saturated (FILTER_SAT in its last slot) and always answers "maybe".
+//                                     A "maybe" is settled exactly against `keys` by whoever consumes it.
 //   meta    : UnitigMeta[n_unitigs+1] first base of the unitig in `pool`, and its length; ids are
 //                                     1-based like the reference's (aligner.cpp:408)
 //   pool    : u64[pool_words]         all unitigs, 2 bits per base, first base in the most
@@ -63,6 +69,8 @@ struct BlobHeader {
     u64 pool_words;
     u64 off_keys, off_payload, off_meta, off_pool;  // byte offsets from the blob start
     u64 total_bytes;
+    u64 n_fbuckets;  // filter buckets (8 tags each)
+    u64 off_filter;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
 
@@ -115,6 +123,17 @@ BGR_HD u64 bucket_of(u64 key, u64 n_buckets) {
 #else
     return ((u64)key_hash(key) * (u64)(u32)n_buckets) >> 32;
 #endif
+}
+
+// filter: bucket from key_hash, tag from an independent mix; tags are odd, 0 = empty slot
+static const u32 FILTER_SAT = 0xFFFFFFFEu;
+BGR_HD u32 key_tag(u64 key) {
+    u32 lo = (u32)key, hi = (u32)(key >> 32);
+    u32 t = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
+    t ^= t >> 16;
+    t *= 0x85EBCA6Bu;
+    t ^= t >> 13;
+    return t | 1u;
 }
 
 // word offset of read r's packed words inside a batch whose reads are concatenated characters:

@@ -243,7 +243,7 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     BlobHeader h;
     memset(&h, 0, sizeof h);
     h.magic = BLOB_MAGIC;
-    h.version = 1;
+    h.version = 2;
     h.k = k;
     h.n_unitigs = nu;
     h.n_keys = n_keys;
@@ -254,7 +254,9 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     h.off_payload = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
     h.off_meta = align_up(h.off_payload + n_buckets * 4 * sizeof(Payload));
     h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
-    h.total_bytes = align_up(h.off_pool + pool_words * sizeof(u64));
+    h.n_fbuckets = std::max<u64>(4, (n_keys + 1) / 2);  // ~2 tags per 8-slot bucket
+    h.off_filter = align_up(h.off_pool + pool_words * sizeof(u64));
+    h.total_bytes = align_up(h.off_filter + h.n_fbuckets * 8 * sizeof(u32));
     blob.assign(h.total_bytes / 8, 0);
     char* B = (char*)blob.data();
     memcpy(B, &h, sizeof h);
@@ -280,6 +282,20 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
         }
     };
     for (u64 i = 0; i < n_keys; ++i) find_or_insert(keys[i], true);
+
+    // ---- negative filter: every key leaves its tag in its home bucket
+    {
+        memcpy(B, &h, sizeof h);
+        u32* filt = (u32*)(B + h.off_filter);
+        for (u64 i = 0; i < n_keys; ++i) {
+            u32* fb = filt + 8 * bucket_of(keys[i], h.n_fbuckets);
+            u32 tag = key_tag(keys[i]);
+            int j = 0;
+            while (j < 8 && fb[j] != 0 && fb[j] != tag) ++j;
+            if (j < 8) fb[j] = tag;
+            else fb[7] = FILTER_SAT;  // more than 8 keys here: the bucket answers "maybe" to everything
+        }
+    }
 
     // ---- slot fill in file order: first free of 4, the 5th and later overwrite slot 4
     // (aligner.cpp:481-489)

@@ -39,8 +39,9 @@ struct DevIndex {
     const UnitigMeta* meta;
     const u64* pool;
     u64 n_buckets;
+    const u32* filter;
+    u32 n_fbuckets;
     u32 k;
-    u32 pad;
 };
 
 // Written by the extension kernel; reset before every (re-)run of it.
@@ -123,6 +124,23 @@ BGR_HD i64 index_find(const DevIndex& ix, u64 key) {
     }
 }
 
+// Negative filter in front of the key table: false = the key is certainly absent, true = maybe
+// (settled exactly by index_find where it matters). One 256-bit load, eight 32-bit compares, no loop.
+BGR_HD bool filter_maybe(const DevIndex& ix, u64 key) {
+    const u32 tag = key_tag(key);
+    const u32* p = ix.filter + 8 * (size_t)bucket_of(key, ix.n_fbuckets);
+    u32 t0, t1, t2, t3, t4, t5, t6, t7;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7)
+                 : "l"(p));
+#else
+    t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4], t5 = p[5], t6 = p[6], t7 = p[7];
+#endif
+    return (t0 == tag) | (t1 == tag) | (t2 == tag) | (t3 == tag) | (t4 == tag) | (t5 == tag) | (t6 == tag) |
+           (t7 == tag) | (t7 == FILTER_SAT);
+}
+
 // ------------------------------------------------------------------------------ pack + seed scan
 
 static const int PS_WARPS = 8;    // warps per block
@@ -159,6 +177,8 @@ BGR_HD u32 packed_byte(u32 c0) { return 8 * (1 + (c0 >> 5)) + 7 - ((c0 >> 2) & 7
 //     absolute positions < k-1; the rolling RC stream takes N as 3 everywhere (nuc2intrc default 0 =
 //     complement of 3). hit1 is that test; hit2 is the test for the same window of the
 //     reverse-complemented read (N->A, utils.cpp:52-73), needed only when the read has N.
+//     Both are answered by the negative filter: "maybe" bits may (about 1e-9 per window) be false and
+//     are settled exactly when a seed is taken (greedy_read).
 //   exhaustive modes: getListOverlap stores the same forward code; getBegin/getEnd canonicalise it
 //     with a true rcb (aligner.cpp:149,211), so hit1 tests min(num, rcb(num)).
 BGR_HD void scan_window(const DevIndex& ix, const u64* D, const u64* ND, bool anyN, bool exhaustive, u32 i,
@@ -174,12 +194,30 @@ BGR_HD void scan_window(const DevIndex& ix, const u64* D, const u64* ND, bool an
     }
     u64 rc = rcb(exhaustive ? num : x2, km1);
     u64 rep = num < rc ? num : rc;
-    hit1 = index_find(ix, rep) >= 0;
+    hit1 = filter_maybe(ix, rep);
     hit2 = false;
     if (anyN && !exhaustive) {
         u64 rep2 = x2 < rc ? x2 : rc;
-        hit2 = (rep2 == rep) ? hit1 : (index_find(ix, rep2) >= 0);
+        hit2 = (rep2 == rep) ? hit1 : filter_maybe(ix, rep2);
     }
+}
+
+// The canonical (k-1)-mer scan_window tested for window i of the pass's read: what a "maybe" of the
+// hit mask has to be settled against before the window counts as a seed.
+BGR_HD u64 seed_rep(const DevIndex& ix, const u64* D, const u64* ND, bool hasN, bool pass, i32 len, i32 i) {
+    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
+    const i32 j = pass ? len - (i32)km1 - i : i;  // stored coordinates
+    u64 x0 = ld_bases(D, j) >> sh;
+    u64 num = x0, x2 = x0;
+    if (hasN) {
+        u64 nm = ld_bases(ND, j) >> sh;
+        x2 = x0 | nm;
+        u64 first = ((u32)j < km1) ? (nm & ~((1ull << (2 * j)) - 1)) : 0ull;
+        num = x0 | first;
+    }
+    u64 rc = rcb(x2, km1);
+    if (pass) return x2 < rc ? x2 : rc;
+    return num < rc ? num : rc;
 }
 
 // What the seed scan already knows about a read that has no border hit at all: greedy ->
@@ -215,7 +253,7 @@ BGR_HD u32 scan_lane_rolling(const DevIndex& ix, const u64* D, u32 w0, u32 nwin)
         for (u32 j = 0; j < PS_WPL; ++j) {
             if (w0 + j < nwin) {
                 u64 rep = num < rc ? num : rc;
-                hits |= (u32)(index_find(ix, rep) >= 0) << j;
+                hits |= (u32)filter_maybe(ix, rep) << j;
             }
             u64 nb = nxt >> 62;
             nxt <<= 2;
@@ -244,40 +282,71 @@ __device__ __forceinline__ u32 pack_and_scan(const DevIndex& ix, const BatchArgs
     const u32 nw = (len + 31) >> 5;
     if (lane == 0) {  // pad words: one in front, two behind (the rolling scan looks one word ahead)
         F[0] = 0;
-        N[0] = 0;
         F[nw + 1] = 0;
-        N[nw + 1] = 0;
         F[nw + 2] = 0;
-        N[nw + 2] = 0;
     }
-    // ---- pack: 128 characters per pass, 4 per lane, coalesced 4-byte loads
+    // ---- pack: 256 characters per pass, 8 per lane (a 150-base read takes one pass on 19 lanes)
     const unsigned char* src = (const unsigned char*)a.seq + o;
     bool anyN = false;
-    for (u32 base = 0; base < nw * 32; base += 128) {
-        u32 c0 = base + 4 * lane;
+    for (u32 base = 0; base < nw * 32; base += 256) {
+        const u32 c0 = base + 8 * lane;
         if (c0 < nw * 32) {
-            u32 x = 0x41414141u;
+            u32 x0 = 0x41414141u, x1 = 0x41414141u;
             if (c0 < len) {
-                uintptr_t ad = (uintptr_t)(src + c0);
+                // 8 unaligned bytes out of three aligned words
+                const uintptr_t ad = (uintptr_t)(src + c0);
                 const u32* wp = (const u32*)(ad & ~(uintptr_t)3);
-                u32 bs = (u32)(ad & 3) * 8;
-                u32 w0 = __ldg(wp), w1 = bs ? __ldg(wp + 1) : 0u;
-                x = __funnelshift_r(w0, w1, bs);
-                u32 left = len - c0;  // characters of this word that belong to the read
-                if (left < 4) {
-                    u32 keep = (1u << (8 * left)) - 1;
-                    x = (x & keep) | (0x41414141u & ~keep);
+                const u32 bs = (u32)(ad & 3) * 8;
+                const u32 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = bs ? __ldg(wp + 2) : 0u;
+                x0 = __funnelshift_r(w0, w1, bs);
+                x1 = __funnelshift_r(w1, w2, bs);
+                const u32 left = len - c0;  // characters from c0 on that belong to the read
+                if (left < 8) {
+                    // bytes past the end of the read become 'A' (code 0, not N)
+                    const u32 k0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1;
+                    const u32 k1 = left <= 4 ? 0u : (1u << (8 * (left - 4))) - 1;
+                    x0 = (x0 & k0) | (0x41414141u & ~k0);
+                    x1 = (x1 & k1) | (0x41414141u & ~k1);
                 }
             }
-            u32 code8, nm8;
-            pack4(x, code8, nm8);
-            u32 byte = packed_byte(c0);
-            ((unsigned char*)F)[byte] = (unsigned char)code8;
-            ((unsigned char*)N)[byte] = (unsigned char)nm8;
-            anyN |= nm8 != 0;
+            u32 ca, na, cb, nb;
+            pack4(x0, ca, na);
+            pack4(x1, cb, nb);
+            // chars c0..c0+3 go to the higher byte, c0+4..c0+7 to the byte below it
+            *(unsigned short*)((unsigned char*)F + packed_byte(c0 + 4)) = (unsigned short)((ca << 8) | cb);
+            anyN |= (na | nb) != 0;
         }
     }
     anyN = __any_sync(0xFFFFFFFFu, anyN);
+    if (anyN) {
+        // rare: write the N mask words too (same walk, mask bytes only)
+        if (lane == 0) {
+            N[0] = 0;
+            N[nw + 1] = 0;
+            N[nw + 2] = 0;
+        }
+        for (u32 base = 0; base < nw * 32; base += 128) {
+            const u32 c0 = base + 4 * lane;
+            if (c0 < nw * 32) {
+                u32 x = 0x41414141u;
+                if (c0 < len) {
+                    const uintptr_t ad = (uintptr_t)(src + c0);
+                    const u32* wp = (const u32*)(ad & ~(uintptr_t)3);
+                    const u32 bs = (u32)(ad & 3) * 8;
+                    const u32 w0 = __ldg(wp), w1 = bs ? __ldg(wp + 1) : 0u;
+                    x = __funnelshift_r(w0, w1, bs);
+                    const u32 left = len - c0;
+                    if (left < 4) {
+                        const u32 keep = (1u << (8 * left)) - 1;
+                        x = (x & keep) | (0x41414141u & ~keep);
+                    }
+                }
+                u32 code8, nm8;
+                pack4(x, code8, nm8);
+                ((unsigned char*)N)[packed_byte(c0)] = (unsigned char)nm8;
+            }
+        }
+    }
     __syncwarp();
     // ---- seed scan
     const u64* D = F + 1;
@@ -825,6 +894,8 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
             // ---- next seed (possibly switching to the reverse-complement pass)
             for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
                 i32 p = tried < max_seeds ? it.next() : -1;
+                // the hit mask comes from the negative filter: settle the "maybe" exactly
+                while (p >= 0 && index_find(ix, seed_rep(ix, v.D, v.ND, v.hasN, v.pass, v.len, p)) < 0) p = it.next();
                 if (p >= 0) {
                     ++tried;
                     seed_c = code = seed_code(ix, v, p);
@@ -971,6 +1042,7 @@ BGR_HD u32 greedy_read_walkers(const DevIndex& ix, const BatchArgs& a, u32 r, Sc
         u32 tried = 0;
         while (tried < max_seeds) {
             i32 pos = it.next();
+            while (pos >= 0 && index_find(ix, seed_rep(ix, v.D, v.ND, v.hasN, v.pass, v.len, pos)) < 0) pos = it.next();
             if (pos < 0) break;
             ++tried;
             u64 code = seed_code(ix, v, pos);

@@ -97,15 +97,16 @@ int grow(bgr_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack_num = 5, si
 int set_index_from_device_blob(bgr_ctx* ctx) {
     CK(cudaMemcpy(&ctx->hdr, ctx->d_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost));
     const BlobHeader& h = ctx->hdr;
-    if (h.magic != BLOB_MAGIC || h.version != 1) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
+    if (h.magic != BLOB_MAGIC || h.version != 2) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
     char* B = (char*)ctx->d_blob;
     ctx->ix.keys = (const u64*)(B + h.off_keys);
     ctx->ix.payload = (const Payload*)(B + h.off_payload);
     ctx->ix.meta = (const UnitigMeta*)(B + h.off_meta);
     ctx->ix.pool = (const u64*)(B + h.off_pool);
     ctx->ix.n_buckets = h.n_buckets;
+    ctx->ix.filter = (const u32*)(B + h.off_filter);
+    ctx->ix.n_fbuckets = (u32)h.n_fbuckets;
     ctx->ix.k = h.k;
-    ctx->ix.pad = 0;
     ctx->has_index = true;
     return BGR_OK;
 }
@@ -121,7 +122,7 @@ int install_host_blob(bgr_ctx* ctx, const void* blob, u64 bytes) {
     if (bytes < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index blob too small");
     BlobHeader h;
     memcpy(&h, blob, sizeof h);
-    if (h.magic != BLOB_MAGIC || h.version != 1 || h.total_bytes != bytes)
+    if (h.magic != BLOB_MAGIC || h.version != 2 || h.total_bytes != bytes)
         return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version/size");
     CK(cudaSetDevice(ctx->device));
     int rc = drop_index(ctx);

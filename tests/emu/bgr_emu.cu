@@ -34,7 +34,8 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     ix.pool = (const u64*)(B + h.off_pool);
     ix.n_buckets = h.n_buckets;
     ix.k = h.k;
-    ix.pad = 0;
+    ix.filter = (const u32*)(B + h.off_filter);
+    ix.n_fbuckets = (u32)h.n_fbuckets;
 
     const u64 chars = off[n];
     const u64 words = batch_words(chars, n);
