@@ -284,23 +284,15 @@ def run_b200_arm(args):
     # ---- graph + index: built once on rank 0, replicated by one NCCL broadcast of the flat blob
     graph = synth.Graph(args.genome, K, seed=1)
     al = bgreat_b200.Aligner(K, ERRORS, EFFORT, device=local, n_slots=3)
+    from bgreat_b200 import shard
     t0 = time.perf_counter()
-    if rank == 0:
+
+    def build_index():
         useqs, uoff = graph.unitig_arrays()
         al.index_unitigs_packed(useqs, uoff)
+
+    shard.replicate_index(al, build_index, src=0)  # rank 0 builds; NCCL broadcast of the blob; import
     index_build_s = time.perf_counter() - t0
-    if world > 1:
-        size = torch.zeros(1, dtype=torch.int64, device="cuda")
-        if rank == 0:
-            size[0] = al.index_blob_size()
-        dist.broadcast(size, 0)
-        blob = torch.empty(int(size.item()), dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            al.export_index_device(blob.data_ptr(), blob.numel())
-        dist.broadcast(blob, 0)
-        if rank != 0:
-            al.import_index_device(blob.data_ptr(), blob.numel())
-        del blob
     stats = al.index_stats()
 
     # ---- this rank's reads (weak scaling: reads [rank*n, (rank+1)*n)), in pinned host memory
@@ -343,7 +335,7 @@ def run_b200_arm(args):
     barrier()
     t_res1 = time.perf_counter()
     launches = al.launch_count() - launches0
-    counters = al.counters()
+    counters = shard.reduce_counters(al.counters(), device="cuda")  # whole-job totals
     dev_ms = torch.tensor(dev, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
@@ -463,7 +455,7 @@ def run_b200_arm(args):
                              "HBM fraction is reported as the contract asks" % (stats["device_bytes"] / 1e6)},
         "kernel_ms": {"pack_scan": scan_ms, "extend": dev_ms[1] / steps},
         "wall_ms_per_step_resident": 1e3 * (t_res1 - t_res0) / steps,
-        "outcome": {"reads": counters["reads"] // steps, "aligned": counters["aligned"] // steps,
+        "outcome": {"scope": "all ranks, per step", "reads": counters["reads"] // steps, "aligned": counters["aligned"] // steps,
                     "not_aligned": counters["not_aligned"] // steps, "no_overlap": counters["no_overlap"] // steps,
                     "mapped_e2e_last_step": mapped_e2e},
         "index_build_s": index_build_s,
