@@ -46,11 +46,12 @@ struct DevIndex {
 
 // Written by the extension kernel; reset before every (re-)run of it.
 struct DevCounters {
-    unsigned long long pool_cursor;
+    unsigned long long pool_cursor;  // ints the batch's paths need (written by the compaction)
     unsigned long long c[BGR_C_COUNT];
     u32 scratch_overflow;  // some path / search stack did not fit the per-read scratch
     u32 pool_overflow;     // the path pool was too small (pool_cursor = ints needed)
-    u32 pad[2];
+    u32 ext_cursor;        // next hit-list entry to hand to a warp of the extension kernel
+    u32 pad;
 };
 // Written by the pack + seed-scan kernel.
 struct ScanCounters {
@@ -831,33 +832,63 @@ BGR_HD ReadSetup setup_read(const DevIndex& ix, const BatchArgs& a, u32 r) {
 // readable statement of the same procedure and are kept for the emulator's cross-check.
 enum { GP_SEED = 0, GP_LEFT = 1, GP_RIGHT_FIRST = 2, GP_RIGHT_MORE = 3, GP_DONE = 4 };
 
-BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
-    ReadSetup s = setup_read(ix, a, r);
-    ReadView& v = s.v;
-    const i64 km1 = ix.k - 1;
-    u32 flags = 0;
-    n = nl = 0;
-    // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
-    const i32 lim = a.effort ? s.nwin : 1;
-    const u32 max_seeds = a.effort ? a.effort : 1;
+struct GreedyState {
+    ReadSetup s;
+    Scratch sc;
     SeedIter it;
-    it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, lim);
-    u32 tried = 0, phase = GP_SEED;
+    u32 flags, n, nl, tried, phase;
     // walk state
-    u64 code = 0, seed_c = 0, next_code = 0;
-    i32 pos = 0, seed_pos = 0, offset = 0, best_sid = 0;
-    i64 next_L = 0;
-    u32 budget = 0, acc = 0, best = 0, eb = 0;
-    bool ended = false, level_open = false;
-    // candidates of the current level
-    Cands c;
-    c.n = 0;
-    c.fwd_bit = 0;
-    c.raw[0] = c.raw[1] = c.raw[2] = c.raw[3] = 0;
-    int ci = 0;
+    u64 code, seed_c, next_code;
+    i32 pos, seed_pos, offset, best_sid;
+    i64 next_L;
+    u32 budget, acc, best, eb;
+    bool ended, level_open;
+    // candidates of the current level (kept in scalars: no dynamically indexed array)
+    u32 raw0, raw1, raw2, raw3, fwd_bit;
+    int cn, ci;
 
-    while (phase != GP_DONE) {
-        if (ci >= c.n) {
+    BGR_HD bool done() const { return phase == GP_DONE; }
+
+    BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
+        s = setup_read(ix, a, r);
+        sc.base = scratch_row;
+        sc.stride = a.n;
+        sc.cap = a.scratch_ints;
+        sc.overflow = false;
+        flags = 0;
+        n = nl = 0;
+        tried = 0;
+        phase = GP_SEED;
+        // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
+        it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, a.effort ? s.nwin : 1);
+        code = seed_c = next_code = 0;
+        pos = seed_pos = offset = best_sid = 0;
+        next_L = 0;
+        budget = acc = best = eb = 0;
+        ended = level_open = false;
+        raw0 = raw1 = raw2 = raw3 = fwd_bit = 0;
+        cn = ci = 0;
+    }
+
+    BGR_HD void succeed() {
+        flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (s.v.pass ? BGR_F_RC : 0u);
+        phase = GP_DONE;
+    }
+    BGR_HD void go_right(const BatchArgs& a) {  // the left walk is complete with `eb` mismatches
+        nl = n;
+        phase = GP_RIGHT_FIRST;
+        budget = a.errors - eb;
+        acc = 0;
+        code = seed_c;
+        pos = seed_pos;
+    }
+
+    // one turn of the loop: settle / seed / query, then one candidate
+    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+        ReadView& v = s.v;
+        const i64 km1 = ix.k - 1;
+        const u32 max_seeds = a.effort ? a.effort : 1;
+        if (ci >= cn) {
             // ---- settle the level whose candidates have all been compared
             if (level_open) {
                 level_open = false;
@@ -869,15 +900,9 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
                         if (phase == GP_LEFT) {
                             sc.set(n++, offset);
                             eb = acc + best;
-                            nl = n;
-                            phase = GP_RIGHT_FIRST;
-                            budget = a.errors - eb;
-                            acc = 0;
-                            code = seed_c;
-                            pos = seed_pos;
+                            go_right(a);
                         } else {
-                            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
-                            phase = GP_DONE;
+                            succeed();
                         }
                     } else {
                         acc += best;
@@ -906,18 +931,16 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
                     phase = GP_LEFT;
                 } else if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
                     flags |= BGR_F_CNT_NOOVERLAP;
-                    n = 0;
                     phase = GP_DONE;
                 } else if (!v.pass) {  // every seed failed: rc=true, retry on the reverse complement
                     flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
                     v.pass = true;
                     const bool useH2 = v.hasN;
                     const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
-                    it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, true, lim);
+                    it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, true, a.effort ? s.nwin : 1);
                     tried = 0;
                 } else {
                     flags |= BGR_F_CNT_NOTALIGNED;
-                    n = 0;
                     phase = GP_DONE;
                 }
             }
@@ -925,36 +948,33 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
             if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
                 sc.set(n++, 0);
                 eb = acc;
-                nl = n;
-                phase = GP_RIGHT_FIRST;
-                budget = a.errors - eb;
-                acc = 0;
-                code = seed_c;
-                pos = seed_pos;
+                go_right(a);
             }
-            if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) {  // checkEndGreedy:324
-                flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
-                phase = GP_DONE;
-            }
-            if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) {  // mapOnRightEndGreedy:223
-                flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
-                phase = GP_DONE;
-            }
+            if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) succeed();  // checkEndGreedy:324
+            if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) succeed();         // mapOnRightEndGreedy:223
             // ---- candidates of the new level: getEnd on the way left, getBegin on the way right
+            cn = 0;
+            ci = 0;
             if (phase != GP_DONE) {
-                c = index_query(ix, code, phase == GP_LEFT);
-                ci = 0;
+                Cands c = index_query(ix, code, phase == GP_LEFT);
+                raw0 = c.raw[0];
+                raw1 = c.raw[1];
+                raw2 = c.raw[2];
+                raw3 = c.raw[3];
+                fwd_bit = c.fwd_bit;
+                cn = c.n;
                 best = budget + 1;
                 ended = false;
                 level_open = true;
-            } else {
-                c.n = 0;
-                ci = 0;
             }
         }
         // ---- compare one candidate
-        if (phase != GP_DONE && ci < c.n) {
-            Oriented u = orient(ix, c, ci);
+        if (phase != GP_DONE && ci < cn) {
+            Cands c1;
+            c1.raw[0] = ci == 0 ? raw0 : ci == 1 ? raw1 : ci == 2 ? raw2 : raw3;
+            c1.fwd_bit = fwd_bit;
+            c1.n = 1;
+            Oriented u = orient(ix, c1, 0);
             ++ci;
             const i64 L = u.len - km1;
             bool ends_here;
@@ -985,20 +1005,14 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
             if (miss == 0) {  // accepted at once (quirk 9)
                 sc.set(n++, u.sid);
                 level_open = false;
-                ci = c.n;
+                ci = cn;
                 if (ends_here) {
                     if (phase == GP_LEFT) {
                         sc.set(n++, (i32)(L - pos));
                         eb = acc;
-                        nl = n;
-                        phase = GP_RIGHT_FIRST;
-                        budget = a.errors - eb;
-                        acc = 0;
-                        code = seed_c;
-                        pos = seed_pos;
+                        go_right(a);
                     } else {
-                        flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (v.pass ? BGR_F_RC : 0u);
-                        phase = GP_DONE;
+                        succeed();
                     }
                 } else if (phase == GP_LEFT) {
                     code = first_code(ix, u);
@@ -1021,8 +1035,31 @@ BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& s
             }
         }
     }
-    if (!(flags & BGR_F_MAPPED)) n = 0;
-    return flags;
+
+    // Path in final order in scratch [0, plen): pathBegin is reversed in place (alignerGreedy.cpp:48).
+    // Returns the path length (0 when unmapped or when the scratch overflowed).
+    BGR_HD u32 finish() {
+        if (!(flags & BGR_F_MAPPED) || sc.overflow) return 0;
+        for (u32 i = 0, j = nl; i + 1 < j; ++i) {
+            --j;
+            i32 x = sc.get(i), y = sc.get(j);
+            sc.set(i, y);
+            sc.set(j, x);
+        }
+        return n;
+    }
+};
+
+// whole read in one go (emulator, and the shape the persistent kernel unrolls over time)
+BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
+    GreedyState g;
+    g.start(ix, a, r, sc.base);
+    g.sc.stride = sc.stride;
+    while (!g.done()) g.step(ix, a);
+    sc.overflow = g.sc.overflow;
+    n = (g.flags & BGR_F_MAPPED) ? g.n : 0;
+    nl = g.nl;
+    return g.flags;
 }
 
 // Reference-shaped version (walkers called in sequence); tests/emu checks that both agree.
@@ -1227,72 +1264,85 @@ BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratc
 }
 
 #if defined(__CUDACC__)
-// Write-out shared by the extension kernels: a warp-wide prefix sum over the path lengths allocates
-// pool space with a single atomic per warp.
-__device__ __forceinline__ void emit_result(const BatchArgs& a, u32 r, bool valid, u32 flags, const Scratch& sc,
-                                            u32 n, u32 nl) {
-    const u32 lane = threadIdx.x & 31;
-    u32 plen = (valid && (flags & BGR_F_MAPPED)) ? n : 0;
-    if (valid && sc.overflow) {  // did not fit the scratch: the host re-runs the batch with a larger one
-        atomicExch(&a.cnt->scratch_overflow, 1u);
-        plen = 0;
-    }
-    u32 incl = plen;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (u32)d) incl += t;
-    }
-    u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 31 && total) base = atomicAdd(&a.cnt->pool_cursor, (unsigned long long)total);
-    base = __shfl_sync(0xFFFFFFFFu, base, 31);
-    if (!valid) return;
-    unsigned long long off = base + (incl - plen);
-    if (plen) {
-        if (off + plen <= a.pool_cap) {
-            i32* dst = a.pool + off;
-            // [0, nl) is reversed on the way out (alignerGreedy.cpp:48)
-            for (u32 j = 0; j < plen; ++j) dst[j] = (j < nl) ? sc.get(nl - 1 - j) : sc.get(j);
-        } else {
-            atomicExch(&a.cnt->pool_overflow, 1u);
-        }
-    }
-    bgr_result res;
-    res.flags_len = (flags & 0xFFu) | (plen << 8);
-    res.path_off = (u32)off;
-    a.res[r] = res;
-}
+// ---- extension kernels. A finished read leaves its path (final order) in its scratch row, its flags
+// and path length in res[r].flags_len and the scratch row number in res[r].path_off; the compaction
+// kernels below then build the pool in read order (no atomics, deterministic layout).
 
-__device__ __forceinline__ void count_classes(const BatchArgs& a, bool valid, u32 flags) {
-    // reads and window counts are tallied by the seed-scan kernel; here only the outcome classes
+__device__ __forceinline__ void count_classes(const BatchArgs& a, u32 n_al, u32 n_na, u32 n_no) {
+    // per-thread tallies -> one atomic per warp and class
     const u32 lane = threadIdx.x & 31;
-    u32 m_al = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_ALIGNED));
-    u32 m_na = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_NOTALIGNED));
-    u32 m_no = __ballot_sync(0xFFFFFFFFu, valid && (flags & BGR_F_CNT_NOOVERLAP));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        n_al += __shfl_xor_sync(0xFFFFFFFFu, n_al, d);
+        n_na += __shfl_xor_sync(0xFFFFFFFFu, n_na, d);
+        n_no += __shfl_xor_sync(0xFFFFFFFFu, n_no, d);
+    }
     if (lane == 0) {
-        if (m_al) atomicAdd(&a.cnt->c[BGR_C_ALIGNED], (unsigned long long)__popc(m_al));
-        if (m_na) atomicAdd(&a.cnt->c[BGR_C_NOTALIGNED], (unsigned long long)__popc(m_na));
-        if (m_no) atomicAdd(&a.cnt->c[BGR_C_NOOVERLAP], (unsigned long long)__popc(m_no));
+        if (n_al) atomicAdd(&a.cnt->c[BGR_C_ALIGNED], (unsigned long long)n_al);
+        if (n_na) atomicAdd(&a.cnt->c[BGR_C_NOTALIGNED], (unsigned long long)n_na);
+        if (n_no) atomicAdd(&a.cnt->c[BGR_C_NOOVERLAP], (unsigned long long)n_no);
     }
 }
 
 static const int EXT_THREADS = 128;
 
-// thread t takes the t-th read of the hit list the seed-scan kernel produced
+// Persistent warps: every lane walks one read with GreedyState::step; lanes that finish hand in their
+// result and take the next read of the hit list (a warp draws 32 list entries per atomic), so the
+// warp stays full until the list runs dry.
 __global__ void __launch_bounds__(EXT_THREADS) k_extend_greedy(DevIndex ix, BatchArgs a) {
-    const u32 t = blockIdx.x * EXT_THREADS + threadIdx.x;
-    const bool valid = t < a.scnt->list_n;
-    const u32 r = valid ? a.list[t] : 0;
-    Scratch sc;
-    sc.base = a.scratch + (valid ? t : 0);
-    sc.stride = a.n;
-    sc.cap = a.scratch_ints;
-    sc.overflow = false;
-    u32 flags = 0, n = 0, nl = 0;
-    if (valid) flags = greedy_read(ix, a, r, sc, n, nl);
-    count_classes(a, valid, flags);
-    emit_result(a, r, valid, flags, sc, n, nl);
+    const u32 lane = threadIdx.x & 31;
+    const u32 list_n = a.scnt->list_n;
+    GreedyState g;
+    g.phase = GP_DONE;
+    g.sc.overflow = false;
+    bool have = false;  // this lane holds a read
+    u32 r = 0, t = 0;
+    u32 chunk_base = 0, chunk_left = 0;  // warp-uniform: list entries drawn but not handed out yet
+    bool dry = false;                    // the list has no more chunks
+    u32 n_al = 0, n_na = 0, n_no = 0;
+    bool any_overflow = false;
+    for (;;) {
+        const bool fin = have && g.done();
+        if (fin) {  // hand in
+            const u32 plen = g.finish();
+            any_overflow |= g.sc.overflow;
+            bgr_result res;
+            res.flags_len = (g.flags & 0xFFu) | (plen << 8);
+            res.path_off = t;
+            a.res[r] = res;
+            n_al += (g.flags & BGR_F_CNT_ALIGNED) != 0;
+            n_na += (g.flags & BGR_F_CNT_NOTALIGNED) != 0;
+            n_no += (g.flags & BGR_F_CNT_NOOVERLAP) != 0;
+            have = false;
+        }
+        const u32 want = __ballot_sync(0xFFFFFFFFu, !have);
+        if (want) {
+            if (chunk_left == 0 && !dry) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&a.cnt->ext_cursor, 32u);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base >= list_n) dry = true;
+                else {
+                    chunk_base = base;
+                    chunk_left = min(32u, list_n - base);
+                }
+            }
+            const u32 rank = __popc(want & ((1u << lane) - 1));
+            if (!have && rank < chunk_left) {
+                t = chunk_base + rank;
+                r = a.list[t];
+                g.start(ix, a, r, a.scratch + t);
+                have = true;
+            }
+            const u32 taken = min((u32)__popc(want), chunk_left);
+            chunk_base += taken;
+            chunk_left -= taken;
+            if (dry && want == 0xFFFFFFFFu) break;  // nobody holds a read and nothing is left
+        }
+        if (have && !g.done()) g.step(ix, a);
+    }
+    if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
+    count_classes(a, n_al, n_na, n_no);
 }
 
 __global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, BatchArgs a) {
@@ -1305,9 +1355,102 @@ __global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, 
     sc.cap = a.scratch_ints;
     sc.overflow = false;
     u32 flags = 0, n = 0, overlaps = 0;
-    if (valid) flags = exhaustive_read(ix, a, r, sc, n, overlaps);
-    count_classes(a, valid, flags);
-    emit_result(a, r, valid, flags, sc, n, 0);
+    if (valid) {
+        flags = exhaustive_read(ix, a, r, sc, n, overlaps);
+        u32 plen = (flags & BGR_F_MAPPED) && !sc.overflow ? n : 0;
+        if (sc.overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
+        bgr_result res;
+        res.flags_len = (flags & 0xFFu) | (plen << 8);
+        res.path_off = t;
+        a.res[r] = res;
+    }
+    count_classes(a, valid && (flags & BGR_F_CNT_ALIGNED), valid && (flags & BGR_F_CNT_NOTALIGNED),
+                  valid && (flags & BGR_F_CNT_NOOVERLAP));
+}
+
+// ---- path compaction: exclusive scan of the path lengths in read order, then gather
+static const int CP_THREADS = 256, CP_PER_THREAD = 4, CP_BLOCK = CP_THREADS * CP_PER_THREAD;
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total) {
+    // 256 threads; returns the exclusive prefix of v, *total = block sum
+    __shared__ u32 warp_sums[CP_THREADS / 32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += x;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    u32 base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+        u32 sw = warp_sums[w];
+        if ((u32)w < warp) base += sw;
+        tot += sw;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) k_path_block_sums(BatchArgs a, unsigned long long* bsum) {
+    const u32 r0 = blockIdx.x * CP_BLOCK + threadIdx.x * CP_PER_THREAD;
+    u32 v = 0;
+#pragma unroll
+    for (int j = 0; j < CP_PER_THREAD; ++j)
+        if (r0 + j < a.n) v += a.res[r0 + j].flags_len >> 8;
+    u32 total;
+    block_exclusive_scan(v, &total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the block sums in place; total -> pool_cursor
+__global__ void __launch_bounds__(CP_THREADS) k_path_scan_blocks(BatchArgs a, unsigned long long* bsum, u32 nb) {
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < nb; base += CP_THREADS) {
+        const u32 i = base + threadIdx.x;
+        const u32 v = i < nb ? (u32)bsum[i] : 0;  // a block sum is < 2^32 (1024 reads)
+        u32 total;
+        const u32 ex = block_exclusive_scan(v, &total);
+        const unsigned long long c = carry;
+        if (i < nb) bsum[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.cnt->pool_cursor = carry;
+        if (carry > a.pool_cap) a.cnt->pool_overflow = 1;
+    }
+}
+
+__global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const unsigned long long* bsum) {
+    if (a.cnt->pool_overflow) return;  // the host grows the pool and runs the compaction again
+    const u32 r0 = blockIdx.x * CP_BLOCK + threadIdx.x * CP_PER_THREAD;
+    u32 len[CP_PER_THREAD], v = 0;
+#pragma unroll
+    for (int j = 0; j < CP_PER_THREAD; ++j) {
+        len[j] = (r0 + j < a.n) ? a.res[r0 + j].flags_len >> 8 : 0;
+        v += len[j];
+    }
+    u32 total;
+    unsigned long long off = bsum[blockIdx.x] + block_exclusive_scan(v, &total);
+#pragma unroll
+    for (int j = 0; j < CP_PER_THREAD; ++j) {
+        if (len[j]) {
+            const u32 r = r0 + j;
+            const u32 t = a.res[r].path_off;  // scratch row
+            const i32* src = a.scratch + t;
+            i32* dst = a.pool + off;
+            for (u32 q = 0; q < len[j]; ++q) dst[q] = src[(size_t)q * a.n];
+            a.res[r].path_off = (u32)off;
+            off += len[j];
+        }
+    }
 }
 
 // getBegin / getEnd for one code, for tests (bgr_index_query)

@@ -39,6 +39,8 @@ struct Slot {
     ScanCounters* d_scnt = nullptr;
     ScanCounters* h_scnt = nullptr;  // pinned
     u32* d_list = nullptr;
+    unsigned long long* d_bsum = nullptr;  // per-1024-read path length sums (compaction)
+    size_t cap_bsum = 0;
     // current batch
     u32 n = 0;
     u64 chars = 0, words = 0;
@@ -65,6 +67,7 @@ struct bgr_ctx {
     unsigned long long totals[BGR_C_COUNT] = {0};
     uint64_t launches = 0;
     u32 scratch_greedy = 32, scratch_exhaustive = 128;  // ints per read, grown on overflow
+    u32 ext_blocks_per_sm = 5;  // 96 registers x 128 threads: 5 CTAs per SM
     std::string err;
 };
 
@@ -133,11 +136,21 @@ int install_host_blob(bgr_ctx* ctx, const void* blob, u64 bytes) {
 }
 
 int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
-    const u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
     switch (s.params.mode) {
-        case BGR_MODE_GREEDY: k_extend_greedy<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+        case BGR_MODE_GREEDY: {
+            // persistent warps: enough CTAs to fill the SMs, never more than the batch can use
+            u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
+            const u32 maxb = (u32)ctx->sm_count * ctx->ext_blocks_per_sm;
+            if (blocks > maxb) blocks = maxb;
+            k_extend_greedy<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
+            break;
+        }
         case BGR_MODE_EXHAUSTIVE:
-        case BGR_MODE_EXHAUSTIVE_PATH: k_extend_exhaustive<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+        case BGR_MODE_EXHAUSTIVE_PATH: {
+            const u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
+            k_extend_exhaustive<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
+            break;
+        }
         default: return fail(ctx, BGR_ERR_ARG, "mode not supported");
     }
     ctx->launches++;
@@ -177,14 +190,31 @@ int ensure_work_buffers(bgr_ctx* ctx, Slot& s) {
     return BGR_OK;
 }
 
-int enqueue_extension(bgr_ctx* ctx, Slot& s) {
-    int rc = ensure_work_buffers(ctx, s);
+// path compaction: lengths -> offsets (read order) -> gather into the pool; then counters to the host
+int enqueue_compaction(bgr_ctx* ctx, Slot& s) {
+    const u32 nb = (s.n + CP_BLOCK - 1) / CP_BLOCK;
+    int rc = grow(ctx, s.d_bsum, s.cap_bsum, (size_t)nb + 1);
     if (rc) return rc;
+    CK(cudaMemsetAsync(&s.d_cnt->pool_cursor, 0, sizeof(unsigned long long), s.stream));
+    CK(cudaMemsetAsync(&s.d_cnt->pool_overflow, 0, sizeof(u32), s.stream));
     BatchArgs a = make_args(s);
-    if ((rc = launch_extension(ctx, s, a))) return rc;
+    k_path_block_sums<<<nb, CP_THREADS, 0, s.stream>>>(a, s.d_bsum);
+    k_path_scan_blocks<<<1, CP_THREADS, 0, s.stream>>>(a, s.d_bsum, nb);
+    k_path_gather<<<nb, CP_THREADS, 0, s.stream>>>(a, s.d_bsum);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
     CK(cudaEventRecord(s.ev[2], s.stream));
     CK(cudaMemcpyAsync(s.h_cnt, s.d_cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
     return BGR_OK;
+}
+
+int enqueue_extension(bgr_ctx* ctx, Slot& s) {
+    int rc = ensure_work_buffers(ctx, s);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(s.d_cnt, 0, sizeof(DevCounters), s.stream));
+    BatchArgs a = make_args(s);
+    if ((rc = launch_extension(ctx, s, a))) return rc;
+    return enqueue_compaction(ctx, s);
 }
 
 }  // namespace
@@ -250,6 +280,7 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
         cudaFree(s.d_cnt);
         cudaFree(s.d_scnt);
         cudaFree(s.d_list);
+        cudaFree(s.d_bsum);
         if (s.h_cnt) cudaFreeHost(s.h_cnt);
         if (s.h_scnt) cudaFreeHost(s.h_scnt);
         for (int j = 0; j < 3; ++j)
@@ -462,17 +493,16 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
     // scratch / pool too small: grow and redo the extension kernel (the seed scan's output is kept)
     for (int attempt = 0; s.n && (s.h_cnt->scratch_overflow || s.h_cnt->pool_overflow); ++attempt) {
         if (attempt > 24) return fail(ctx, BGR_ERR_LIMIT, "extension scratch keeps overflowing");
+        int rc;
         if (s.h_cnt->scratch_overflow) {
             s.scratch_ints *= 4;
             if (s.params.mode == BGR_MODE_GREEDY) ctx->scratch_greedy = s.scratch_ints;
             else ctx->scratch_exhaustive = s.scratch_ints;
+            rc = enqueue_extension(ctx, s);  // the seed scan's output is kept
+        } else {
+            rc = grow(ctx, s.d_pool, s.cap_pool, (size_t)s.h_cnt->pool_cursor + 1024, 5, 4);
+            if (rc == BGR_OK) rc = enqueue_compaction(ctx, s);  // paths are still in the scratch rows
         }
-        if (s.h_cnt->pool_overflow) {
-            int rc = grow(ctx, s.d_pool, s.cap_pool, (size_t)s.h_cnt->pool_cursor + 1024, 5, 4);
-            if (rc) return rc;
-        }
-        CK(cudaMemsetAsync(s.d_cnt, 0, sizeof(DevCounters), s.stream));
-        int rc = enqueue_extension(ctx, s);
         if (rc) return rc;
         CK(cudaStreamSynchronize(s.stream));
         s.timed = false;  // event pair no longer brackets a single pass

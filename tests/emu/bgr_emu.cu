@@ -151,7 +151,14 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         sc.overflow = false;
         u32 flags = 0, np = 0, nl = 0, overlaps = 0;
         if (mode == BGR_MODE_GREEDY) {
-            flags = greedy_read(ix, a, r, sc, np, nl);
+            // the persistent kernel's per-lane life cycle: start, step until done, finish
+            GreedyState g;
+            g.start(ix, a, r, sc.base);
+            while (!g.done()) g.step(ix, a);
+            flags = g.flags;
+            np = g.finish();  // pathBegin reversed in place: scratch [0, np) is the final path
+            nl = 0;
+            sc.overflow = g.sc.overflow;
             // cross-check: the loop-shaped kernel body against the walker-shaped statement
             Scratch sc2 = sc;
             std::vector<i32> tmp((size_t)scratch_ints + 1, 0);
@@ -160,9 +167,9 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
             sc2.overflow = false;
             u32 np2 = 0, nl2 = 0;
             u32 flags2 = greedy_read_walkers(ix, a, r, sc2, np2, nl2);
-            bool same = flags2 == flags && (!(flags & BGR_F_MAPPED) || (np2 == np && nl2 == nl));
+            bool same = flags2 == flags && (!(flags & BGR_F_MAPPED) || np2 == np);
             if (same && (flags & BGR_F_MAPPED) && !sc.overflow && !sc2.overflow)
-                for (u32 j = 0; j < np; ++j) same = same && sc.get(j) == sc2.get(j);
+                for (u32 j = 0; j < np; ++j) same = same && sc.get(j) == (j < nl2 ? sc2.get(nl2 - 1 - j) : sc2.get(j));
             if (!same && !sc.overflow && !sc2.overflow) return 1000;  // the two formulations disagree
         } else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH) {
             flags = exhaustive_read(ix, a, r, sc, np, overlaps);
