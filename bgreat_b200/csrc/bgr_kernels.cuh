@@ -383,7 +383,8 @@ __device__ __forceinline__ u32 pack_and_scan(const DevIndex& ix, const BatchArgs
     return (anyN ? INFO_HAS_N : 0u) | (any1 ? INFO_HIT1 : 0u) | (any2 ? INFO_HIT2 : 0u);
 }
 
-__global__ void __launch_bounds__(PS_WARPS * 32) k_pack_scan(DevIndex ix, BatchArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(PS_WARPS * 32, MINB) k_pack_scan(DevIndex ix, BatchArgs a) {
     __shared__ u64 sF[PS_WARPS][PS_SWORDS];
     __shared__ u64 sN[PS_WARPS][PS_SWORDS];
     __shared__ u32 s_list[PS_WARPS][32];
@@ -838,14 +839,9 @@ struct GreedyState {
     SeedIter it;
     u32 flags, n, nl, tried, phase;
     // walk state
-    u64 code, seed_c, next_code;
-    i32 pos, seed_pos, offset, best_sid;
-    i64 next_L;
-    u32 budget, acc, best, eb;
-    bool ended, level_open;
-    // candidates of the current level (kept in scalars: no dynamically indexed array)
-    u32 raw0, raw1, raw2, raw3, fwd_bit;
-    int cn, ci;
+    u64 code, seed_c;
+    i32 pos, seed_pos;
+    u32 budget, acc, eb;
 
     BGR_HD bool done() const { return phase == GP_DONE; }
 
@@ -861,13 +857,9 @@ struct GreedyState {
         phase = GP_SEED;
         // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
         it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, a.effort ? s.nwin : 1);
-        code = seed_c = next_code = 0;
-        pos = seed_pos = offset = best_sid = 0;
-        next_L = 0;
-        budget = acc = best = eb = 0;
-        ended = level_open = false;
-        raw0 = raw1 = raw2 = raw3 = fwd_bit = 0;
-        cn = ci = 0;
+        code = seed_c = 0;
+        pos = seed_pos = 0;
+        budget = acc = eb = 0;
     }
 
     BGR_HD void succeed() {
@@ -883,155 +875,120 @@ struct GreedyState {
         pos = seed_pos;
     }
 
-    // one turn of the loop: settle / seed / query, then one candidate
+    // One turn of the loop = one level of a walk: (pick a seed if needed) -> query the index ->
+    // compare the <= 4 candidates -> settle. Every lane of a warp runs these same stages every turn.
     BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
         ReadView& v = s.v;
         const i64 km1 = ix.k - 1;
         const u32 max_seeds = a.effort ? a.effort : 1;
-        if (ci >= cn) {
-            // ---- settle the level whose candidates have all been compared
-            if (level_open) {
-                level_open = false;
-                if (best > budget) {
-                    phase = GP_SEED;  // this seed failed
-                } else {
-                    sc.set(n++, best_sid);
-                    if (ended) {
-                        if (phase == GP_LEFT) {
-                            sc.set(n++, offset);
-                            eb = acc + best;
-                            go_right(a);
-                        } else {
-                            succeed();
-                        }
-                    } else {
-                        acc += best;
-                        budget -= best;
-                        code = next_code;
-                        if (phase == GP_LEFT) pos -= (i32)next_L;
-                        else {
-                            pos += (i32)next_L;
-                            phase = GP_RIGHT_MORE;
-                        }
-                    }
-                }
-            }
-            // ---- next seed (possibly switching to the reverse-complement pass)
-            for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
-                i32 p = tried < max_seeds ? it.next() : -1;
-                // the hit mask comes from the negative filter: settle the "maybe" exactly
-                while (p >= 0 && index_find(ix, seed_rep(ix, v.D, v.ND, v.hasN, v.pass, v.len, p)) < 0) p = it.next();
-                if (p >= 0) {
-                    ++tried;
-                    seed_c = code = seed_code(ix, v, p);
-                    seed_pos = pos = p;
-                    budget = a.errors;
-                    acc = 0;
-                    n = 0;
-                    phase = GP_LEFT;
-                } else if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
-                    flags |= BGR_F_CNT_NOOVERLAP;
-                    phase = GP_DONE;
-                } else if (!v.pass) {  // every seed failed: rc=true, retry on the reverse complement
-                    flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
-                    v.pass = true;
-                    const bool useH2 = v.hasN;
-                    const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
-                    it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, true, a.effort ? s.nwin : 1);
-                    tried = 0;
-                } else {
-                    flags |= BGR_F_CNT_NOTALIGNED;
-                    phase = GP_DONE;
-                }
-            }
-            // ---- ends of walks that need no index query
-            if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
-                sc.set(n++, 0);
-                eb = acc;
-                go_right(a);
-            }
-            if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) succeed();  // checkEndGreedy:324
-            if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) succeed();         // mapOnRightEndGreedy:223
-            // ---- candidates of the new level: getEnd on the way left, getBegin on the way right
-            cn = 0;
-            ci = 0;
-            if (phase != GP_DONE) {
-                Cands c = index_query(ix, code, phase == GP_LEFT);
-                raw0 = c.raw[0];
-                raw1 = c.raw[1];
-                raw2 = c.raw[2];
-                raw3 = c.raw[3];
-                fwd_bit = c.fwd_bit;
-                cn = c.n;
-                best = budget + 1;
-                ended = false;
-                level_open = true;
+        // ---- next seed (possibly switching to the reverse-complement pass)
+        for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
+            i32 p = tried < max_seeds ? it.next() : -1;
+            // the hit mask comes from the negative filter: settle the "maybe" exactly
+            while (p >= 0 && index_find(ix, seed_rep(ix, v.D, v.ND, v.hasN, v.pass, v.len, p)) < 0) p = it.next();
+            if (p >= 0) {
+                ++tried;
+                seed_c = code = seed_code(ix, v, p);
+                seed_pos = pos = p;
+                budget = a.errors;
+                acc = 0;
+                n = 0;
+                phase = GP_LEFT;
+            } else if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
+                flags |= BGR_F_CNT_NOOVERLAP;
+                phase = GP_DONE;
+            } else if (!v.pass) {  // every seed failed: rc=true, retry on the reverse complement
+                flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
+                v.pass = true;
+                const bool useH2 = v.hasN;
+                const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
+                it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, true, a.effort ? s.nwin : 1);
+                tried = 0;
+            } else {
+                flags |= BGR_F_CNT_NOTALIGNED;
+                phase = GP_DONE;
             }
         }
-        // ---- compare one candidate
-        if (phase != GP_DONE && ci < cn) {
-            Cands c1;
-            c1.raw[0] = ci == 0 ? raw0 : ci == 1 ? raw1 : ci == 2 ? raw2 : raw3;
-            c1.fwd_bit = fwd_bit;
-            c1.n = 1;
-            Oriented u = orient(ix, c1, 0);
-            ++ci;
-            const i64 L = u.len - km1;
-            bool ends_here;
-            i64 upos;
-            i32 rpos, nn;
-            if (phase == GP_LEFT) {
-                // unitig covers the rest: unitig[L-pos, L) vs read[0,pos); else unitig[0,L) vs read[pos-L,pos)
-                ends_here = L >= pos;
-                upos = ends_here ? L - pos : 0;
-                rpos = ends_here ? 0 : pos - (i32)L;
-                nn = ends_here ? pos : (i32)L;
-            } else if (phase == GP_RIGHT_FIRST) {
-                // comparisons start after the anchor overlap
-                const i32 rstart = pos + (i32)km1, rl = v.len - rstart;
-                ends_here = L >= rl;
-                upos = km1;
-                rpos = rstart;
-                nn = ends_here ? rl : (i32)L;
-            } else {
-                // the remaining read starts AT the overlap; whole unitig compared, cut at the read end
-                const i32 rl = v.len - pos;
-                ends_here = L >= rl;
-                upos = 0;
-                rpos = pos;
-                nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
-            }
-            const u32 miss = mismatches(ix, v, u, upos, rpos, nn, budget);
-            if (miss == 0) {  // accepted at once (quirk 9)
-                sc.set(n++, u.sid);
-                level_open = false;
-                ci = cn;
-                if (ends_here) {
-                    if (phase == GP_LEFT) {
-                        sc.set(n++, (i32)(L - pos));
-                        eb = acc;
-                        go_right(a);
-                    } else {
-                        succeed();
-                    }
-                } else if (phase == GP_LEFT) {
-                    code = first_code(ix, u);
-                    pos -= (i32)L;
+        // ---- ends of walks that need no index query
+        if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
+            sc.set(n++, 0);
+            eb = acc;
+            go_right(a);
+        }
+        if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) succeed();  // checkEndGreedy:324
+        if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) succeed();         // mapOnRightEndGreedy:223
+        if (phase == GP_DONE) return;
+        // ---- candidates of this level: getEnd on the way left, getBegin on the way right
+        const Cands c = index_query(ix, code, phase == GP_LEFT);
+        u32 best = budget + 1;
+        i32 best_sid = 0, offset = 0;
+        i64 next_L = 0;
+        u64 next_code = 0;
+        bool ended = false, accepted = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < c.n && !accepted) {
+                const Oriented u = orient(ix, c, i);
+                const i64 L = u.len - km1;
+                bool ends_here;
+                i64 upos;
+                i32 rpos, nn;
+                if (phase == GP_LEFT) {
+                    // unitig covers the rest: unitig[L-pos, L) vs read[0,pos); else unitig[0,L) vs read[pos-L,pos)
+                    ends_here = L >= pos;
+                    upos = ends_here ? L - pos : 0;
+                    rpos = ends_here ? 0 : pos - (i32)L;
+                    nn = ends_here ? pos : (i32)L;
+                } else if (phase == GP_RIGHT_FIRST) {
+                    // comparisons start after the anchor overlap
+                    const i32 rstart = pos + (i32)km1, rl = v.len - rstart;
+                    ends_here = L >= rl;
+                    upos = km1;
+                    rpos = rstart;
+                    nn = ends_here ? rl : (i32)L;
                 } else {
-                    code = last_code(ix, u);
-                    pos += (i32)L;
-                    phase = GP_RIGHT_MORE;
+                    // the remaining read starts AT the overlap; whole unitig compared, cut at the read end
+                    const i32 rl = v.len - pos;
+                    ends_here = L >= rl;
+                    upos = 0;
+                    rpos = pos;
+                    nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
                 }
-            } else if (miss < best) {
-                best = miss;
-                best_sid = u.sid;
-                ended = ends_here;
-                if (ends_here) {
+                const u32 miss = mismatches(ix, v, u, upos, rpos, nn, budget);
+                if (miss < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
+                    best = miss;
+                    best_sid = u.sid;
+                    ended = ends_here;
                     offset = (i32)(L - pos);
-                } else {
                     next_L = L;
-                    next_code = (phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u);
+                    if (!ends_here) next_code = (phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u);
+                    accepted = miss == 0;
                 }
+            }
+        }
+        // ---- settle the level
+        if (best > budget) {
+            phase = GP_SEED;  // this seed failed
+            return;
+        }
+        sc.set(n++, best_sid);
+        // an exact candidate leaves the budget untouched, an inexact one pays for its mismatches
+        if (ended) {
+            if (phase == GP_LEFT) {
+                sc.set(n++, offset);
+                eb = acc + best;
+                go_right(a);
+            } else {
+                succeed();
+            }
+        } else {
+            acc += best;
+            budget -= best;
+            code = next_code;
+            if (phase == GP_LEFT) pos -= (i32)next_L;
+            else {
+                pos += (i32)next_L;
+                phase = GP_RIGHT_MORE;
             }
         }
     }
@@ -1289,7 +1246,8 @@ static const int EXT_THREADS = 128;
 // Persistent warps: every lane walks one read with GreedyState::step; lanes that finish hand in their
 // result and take the next read of the hit list (a warp draws 32 list entries per atomic), so the
 // warp stays full until the list runs dry.
-__global__ void __launch_bounds__(EXT_THREADS) k_extend_greedy(DevIndex ix, BatchArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix, BatchArgs a) {
     const u32 lane = threadIdx.x & 31;
     const u32 list_n = a.scnt->list_n;
     GreedyState g;

@@ -1,6 +1,7 @@
 // C ABI implementation (include/bgreat_b200.h): context, index residency, batch slots, launches.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -67,7 +68,9 @@ struct bgr_ctx {
     unsigned long long totals[BGR_C_COUNT] = {0};
     uint64_t launches = 0;
     u32 scratch_greedy = 32, scratch_exhaustive = 128;  // ints per read, grown on overflow
-    u32 ext_blocks_per_sm = 5;  // 96 registers x 128 threads: 5 CTAs per SM
+    // resident CTAs per SM the kernels are compiled for (register budget); tuned on B200, see
+    // profiles/. BGR_SCAN_MINB / BGR_EXT_MINB override for experiments.
+    u32 scan_blocks_per_sm = 4, ext_blocks_per_sm = 5;
     std::string err;
 };
 
@@ -142,7 +145,11 @@ int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
             u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
             const u32 maxb = (u32)ctx->sm_count * ctx->ext_blocks_per_sm;
             if (blocks > maxb) blocks = maxb;
-            k_extend_greedy<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
+            switch (ctx->ext_blocks_per_sm) {
+                case 8: k_extend_greedy<8><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+                case 6: k_extend_greedy<6><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+                default: k_extend_greedy<5><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+            }
             break;
         }
         case BGR_MODE_EXHAUSTIVE:
@@ -243,6 +250,14 @@ int bgr_ctx_create(int device, int n_slots, bgr_ctx** out) {
     ctx->device = device;
     ctx->n_slots = n_slots;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("BGR_SCAN_MINB")) {
+        int v = atoi(e);
+        if (v == 4 || v == 6 || v == 8) ctx->scan_blocks_per_sm = (u32)v;
+    }
+    if (const char* e = getenv("BGR_EXT_MINB")) {
+        int v = atoi(e);
+        if (v == 5 || v == 6 || v == 8) ctx->ext_blocks_per_sm = (u32)v;
+    }
     for (int i = 0; i < n_slots; ++i) {
         Slot& s = ctx->slots[i];
         cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -451,9 +466,13 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     if (s.n) {
         BatchArgs a = make_args(s);
         u32 blocks = (s.n + PS_WARPS - 1) / PS_WARPS;
-        u32 maxb = (u32)ctx->sm_count * 8;
+        u32 maxb = (u32)ctx->sm_count * ctx->scan_blocks_per_sm;
         if (blocks > maxb) blocks = maxb;
-        k_pack_scan<<<blocks, PS_WARPS * 32, 0, s.stream>>>(ctx->ix, a);
+        switch (ctx->scan_blocks_per_sm) {
+            case 8: k_pack_scan<8><<<blocks, PS_WARPS * 32, 0, s.stream>>>(ctx->ix, a); break;
+            case 6: k_pack_scan<6><<<blocks, PS_WARPS * 32, 0, s.stream>>>(ctx->ix, a); break;
+            default: k_pack_scan<4><<<blocks, PS_WARPS * 32, 0, s.stream>>>(ctx->ix, a); break;
+        }
         ctx->launches++;
         CK(cudaGetLastError());
     }
