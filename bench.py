@@ -36,7 +36,22 @@ ERRORS = 2
 EFFORT = 2
 READ_LEN = 150
 SUB_RATE = 0.01
+EXHAUSTIVE = False
 WORKLOAD = "configs[1]: synthetic 5 Mbp diploid genome (SNP 1/150), k=31 unitigs, 150 bp reads at 1% substitutions, -m 2 -e 2, greedy"
+
+
+def configure(args):
+    """The default run is BASELINE.json configs[1] (the configuration the metric is quoted on). The other
+    configs (larger graphs, -m sweep, exhaustive mode) are selected with flags and named in `workload`."""
+    global ERRORS, EFFORT, SUB_RATE, EXHAUSTIVE, WORKLOAD
+    ERRORS, EFFORT, SUB_RATE, EXHAUSTIVE = args.errors, args.effort, args.sub_rate, args.mode == "exhaustive"
+    default = (args.genome == 5_000_000 and ERRORS == 2 and EFFORT == 2 and SUB_RATE == 0.01 and not EXHAUSTIVE)
+    if not default:
+        g = args.genome
+        gs = "%g Gbp" % (g / 1e9) if g >= 1e9 else "%g Mbp" % (g / 1e6)
+        WORKLOAD = ("%ssynthetic %s diploid genome (SNP 1/150), k=31 unitigs, 150 bp reads at %g%% substitutions, "
+                    "-m %d -e %d, %s" % ((args.label + ": ") if args.label else "", gs, 100 * SUB_RATE, ERRORS, EFFORT,
+                                         args.mode))
 
 
 def parse_args():
@@ -50,6 +65,11 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1 << 20, help="reads per batch on the end-to-end leg")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--errors", type=int, default=2, help="-m")
+    ap.add_argument("--effort", type=int, default=2, help="-e")
+    ap.add_argument("--sub-rate", type=float, default=0.01, help="substitution error rate of the reads")
+    ap.add_argument("--mode", default="greedy", choices=["greedy", "exhaustive"])
+    ap.add_argument("--label", default="", help="name of the BASELINE.json config this run stands for")
     return ap.parse_args()
 
 
@@ -160,7 +180,7 @@ class CpuReference:
         t0 = time.perf_counter()
         out = subprocess.run([self.O.REF_BGREAT, "-r", reads_file, "-g", self.unitigs, "-k", str(K), "-m", str(ERRORS),
                               "-e", str(EFFORT), "-t", str(self.cores), "-f", os.path.join(self.dir, "paths.ref"),
-                              "-a", os.path.join(self.dir, "na.ref")], capture_output=True, text=True, cwd=self.dir,
+                              "-a", os.path.join(self.dir, "na.ref")] + (["-b"] if EXHAUSTIVE else []), capture_output=True, text=True, cwd=self.dir,
                              timeout=3600)
         dt = time.perf_counter() - t0
         if out.returncode != 0:
@@ -191,7 +211,7 @@ class CpuReference:
         o = self.O.Oracle(K, ERRORS, EFFORT)
         o.index_file(self.unitigs)
         t0 = time.perf_counter()
-        o.run(self.O.GREEDY, self.reads, False, os.path.join(self.dir, "paths.port"), os.path.join(self.dir, "na.port"))
+        o.run(self.O.EXHAUSTIVE if EXHAUSTIVE else self.O.GREEDY, self.reads, False, os.path.join(self.dir, "paths.port"), os.path.join(self.dir, "na.port"))
         return self.n, time.perf_counter() - t0
 
     def windows_per_read(self, n=20000):
@@ -202,7 +222,8 @@ class CpuReference:
         b = self.sample_seqs.tobytes()
         n = min(n, self.n)
         for i in range(n):
-            o.align(b[int(self.sample_off[i]):int(self.sample_off[i + 1])])
+            o.align(b[int(self.sample_off[i]):int(self.sample_off[i + 1])],
+                    self.O.EXHAUSTIVE if EXHAUSTIVE else self.O.GREEDY)
         c = o.counters()
         return c["windows"] / float(n), c
 
@@ -302,7 +323,7 @@ def run_b200_arm(args):
     off = off_t.numpy().view(np.uint64)
     graph.make_reads(n_reads, READ_LEN, SUB_RATE, first=rank * n_reads, seqs=seqs, off=off)
 
-    params = al.params(A.MODE_GREEDY)
+    params = al.params(A.MODE_EXHAUSTIVE if EXHAUSTIVE else A.MODE_GREEDY)
     ctx = al.ctx
 
     def ck(rc):
@@ -469,6 +490,7 @@ def run_b200_arm(args):
 
 def main():
     args = parse_args()
+    configure(args)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
