@@ -1086,8 +1086,12 @@ struct DfsLayout {
 // Search one side. Returns true and (best_total, best_n ids at best0.., term) when a walk within
 // `budget` exists. term: left side = start offset or -1 (ended exactly on a unitig start: nothing
 // emitted); right side = end marker (|readLeft|+k-1, or 0 when the read ends on a unitig boundary).
+// avoid_n > 0 (greedy "paths" aligner only): the first avoid_n ints of the scratch row are the path built
+// so far, and a first-level candidate found in it is skipped (alignerPaths.cpp:136,307,370: the deeper
+// levels of the reference test against vectors that are still empty, so only depth 0 filters).
 BGR_HD bool exhaustive_side(const DevIndex& ix, const ReadView& v, bool right, u64 code0, i32 pos0, u32 budget,
-                            Scratch& sc, const DfsLayout& lay, u32& best_total, u32& best_n, i32& term) {
+                            Scratch& sc, const DfsLayout& lay, u32& best_total, u32& best_n, i32& term,
+                            u32 avoid_n = 0) {
     const i64 km1 = ix.k - 1;
     best_total = budget + 1;
     best_n = 0;
@@ -1128,6 +1132,11 @@ BGR_HD bool exhaustive_side(const DevIndex& ix, const ReadView& v, bool right, u
         for (u32 i = next; i < (u32)c.n; ++i) {
             if (acc >= best_total) break;  // nothing below can be strictly better
             Oriented u = orient(ix, c, (int)i);
+            if (avoid_n && depth == 0) {
+                bool seen = false;
+                for (u32 j = 0; j < avoid_n; ++j) seen |= sc.get(j) == u.sid;
+                if (seen) continue;
+            }
             const i64 L = u.len - km1;
             const u32 cap = best_total - 1 - acc;  // a candidate is useful only if acc+miss < best_total
             if (L >= rl) {
@@ -1215,6 +1224,245 @@ BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratc
         sc.set(w++, te);
         n = w;
         return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+    }
+    n = 0;
+    return flags | BGR_F_CNT_NOTALIGNED;
+}
+
+// ------------------------------------------------------------------------------ greedy "paths" aligner
+//
+// alignReadGreedyPath and its helpers (alignerPaths.cpp:35-63 driver, :91-124 coverGreedyPath,
+// :178-234 mapOnRightPath, :237-286 checkPairPaths; the two ends use the exhaustive path walkers,
+// :289-411). Unreachable from the reference's command line (pathOption is never set) but part of
+// class Aligner's public interface. ONE path vector collects everything in call order: the left walk
+// of the start seed, the right walk of the END seed, then the cover between them, and it is not
+// cleared between failed (start, end) attempts: reproduced as is. "Already in the path" compares a
+// signed unitig id with every int of that vector, offsets included (std::find over vector<uNumber>).
+//
+// Scratch row: [0, P) the path | cur ids [D] | best ids [D] | search frames 5*[D].
+struct PathLayout {
+    u32 P;
+    DfsLayout dfs;
+    BGR_HD void init(u32 scratch_ints) {
+        P = scratch_ints / 2;
+        const u32 rest = scratch_ints - P;
+        dfs.D = rest >= 14 ? rest / 7 : 1;
+        dfs.out0 = 0;
+        dfs.cur0 = P;
+        dfs.best0 = dfs.cur0 + dfs.D;
+        dfs.fr0 = dfs.best0 + dfs.D;
+    }
+};
+
+struct PathBuf {
+    Scratch* sc;
+    u32 n, cap;
+    BGR_HD void push(i32 x) {
+        if (n < cap) sc->set(n, x);
+        else sc->overflow = true;
+        ++n;
+    }
+    BGR_HD bool contains(i32 x) const {
+        bool seen = false;
+        const u32 m = n < cap ? n : cap;
+        for (u32 j = 0; j < m; ++j) seen |= sc->get(j) == x;
+        return seen;
+    }
+};
+
+// checkPairPaths (alignerPaths.cpp:237-286): the unitig that begins with the (k-1)-mer of window p1
+// and ends with the one of window p2. Returns the mismatch count (allowed+1 = none) and the id in `number`.
+BGR_HD u32 check_pair_paths(const DevIndex& ix, const ReadView& v, const PathBuf& path, i32 p1, i32 p2, i32& number,
+                            u32 allowed) {
+    const i32 km1 = (i32)ix.k - 1;
+    const Cands c1 = index_query(ix, seed_code(ix, v, p1), false);  // getBegin(overlap1)
+    const Cands c2 = index_query(ix, seed_code(ix, v, p2), true);   // getEnd(overlap2)
+    if (p2 - p1 < (i32)ix.k) {
+        // the two windows overlap: any common unitig is taken without looking at the read
+        for (int i = 0; i < c1.n; ++i) {
+            const i32 id1 = orient(ix, c1, i).sid;
+            for (int j = 0; j < c2.n; ++j)
+                if (orient(ix, c2, j).sid == id1) {
+                    if (!path.contains(id1)) number = id1;
+                    return 0;
+                }
+        }
+        return allowed + 1;
+    }
+    const i32 sub_len = p2 - p1 - km1;
+    u32 best = allowed + 1;
+    i32 best_sid = 0;
+    for (int i = 0; i < c1.n; ++i) {
+        const Oriented u = orient(ix, c1, i);
+        for (int j = 0; j < c2.n; ++j) {
+            if (orient(ix, c2, j).sid == u.sid && !path.contains(u.sid)) {
+                if (u.len - 2 * (i64)km1 == (i64)sub_len) {
+                    const u32 miss = mismatches(ix, v, u, km1, p1 + km1, sub_len, allowed);
+                    if (miss < best) {
+                        best = miss;
+                        best_sid = u.sid;
+                    }
+                }
+            }
+        }
+    }
+    if (best <= allowed) number = best_sid;
+    return best;
+}
+
+// mapOnRightPath (alignerPaths.cpp:178-234), tail recursion as a loop. Walks right from window
+// `start` until the read ends (ended) or the walk lands exactly on a later listed window (first = its
+// index). Returns false when no walk within `budget` exists; second = mismatches spent.
+BGR_HD bool map_on_right_path(const DevIndex& ix, const ReadView& v, PathBuf& path, i32 start, i32 nwin, u32 budget,
+                              bool& ended, i32& first, u32& second) {
+    const i32 km1 = (i32)ix.k - 1;
+    u64 code = seed_code(ix, v, start);
+    i32 pos = start;
+    u32 total = 0;
+    for (;;) {
+        const i32 rl = v.len - (pos + km1);
+        if (rl <= 0) {  // the reference prints "should not appears" and exits; unreachable (start < end)
+            first = start;
+            second = total;
+            return true;
+        }
+        const Cands c = index_query(ix, code, false);
+        u32 best = budget + 1;
+        i32 best_sid = 0, next = start;
+        bool have_best = false;
+        u64 next_code = 0;
+        i64 next_L = 0;
+        for (int i = 0; i < c.n; ++i) {
+            const Oriented u = orient(ix, c, i);
+            if (path.contains(u.sid)) continue;
+            const i64 L = u.len - km1;
+            if ((i64)rl <= L) {
+                const u32 miss = mismatches(ix, v, u, km1, pos + km1, rl, budget);
+                if (miss < best) {
+                    ended = true;
+                    best = miss;
+                    best_sid = u.sid;
+                    have_best = true;
+                }
+            } else {
+                const u32 miss = mismatches(ix, v, u, km1, pos + km1, (i32)L, budget);
+                if (miss < best) {
+                    const u64 oc = last_code(ix, u);
+                    ended = false;
+                    best = miss;
+                    best_sid = u.sid;
+                    have_best = true;
+                    next_code = oc;
+                    next_L = L;
+                    next = start;
+                    // a later listed overlap at exactly that position with that code (list[j].pos == j)
+                    const i64 j = (i64)pos + L;
+                    if (j >= (i64)start + 1 && j < (i64)nwin && seed_code(ix, v, (i32)j) == oc) next = (i32)j;
+                }
+            }
+        }
+        if (ended) {
+            if (have_best) path.push(best_sid);
+            first = start;
+            second = total + best;
+            return true;
+        }
+        if (best > budget) return false;
+        path.push(best_sid);
+        total += best;
+        if (next > start) {
+            first = next;
+            second = total;
+            return true;
+        }
+        budget -= best;
+        code = next_code;
+        pos += (i32)next_L;
+    }
+}
+
+// coverGreedyPath (alignerPaths.cpp:91-124), recursion as a loop: joins window `start` to window
+// `end` by single unitigs between listed windows (checkPairPaths) or, failing that, by a rightward walk.
+BGR_HD bool cover_greedy_path(const DevIndex& ix, const ReadView& v, PathBuf& path, i32 start, i32 end, i32 nwin,
+                              u32 budget, u32 effort) {
+    bool ended = false;
+    for (;;) {
+        if (start == end) return true;
+        i32 indice = 0, keep = 0;
+        u32 best = budget + 1;
+        for (u32 i = 1; (i64)i + start <= (i64)end && i <= effort; ++i) {
+            i32 number = 0;
+            const u32 miss = check_pair_paths(ix, v, path, start, start + (i32)i, number, budget);
+            if (miss < best) {
+                indice = (i32)i;
+                keep = number;
+                best = miss;
+            }
+        }
+        if (best <= budget) {
+            path.push(keep);
+            budget -= best;
+            start += indice;
+            continue;
+        }
+        i32 first = start;
+        u32 second = 0;
+        if (!map_on_right_path(ix, v, path, start, nwin, budget, ended, first, second)) return false;
+        if (second > budget) return false;
+        if (ended) return true;
+        if (first <= start) return false;
+        budget -= second;
+        start = first;
+    }
+}
+
+// alignReadGreedyPath (alignerPaths.cpp:35-63) for read r; the path is left in scratch [0, n).
+BGR_HD u32 greedy_path_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    PathLayout lay;
+    lay.init(a.scratch_ints);
+    n = 0;
+    const u32 flags = BGR_F_OVERLAP_FOUND;
+    if (s.nwin == 0) return flags | BGR_F_CNT_NOTALIGNED;  // shorter than k-1: see DESIGN.md
+    const i32 nwin = s.nwin;  // listOverlap holds every window: list[j].second == j
+    const u32 last_start = (a.effort - 1u) < (u32)(nwin - 1) ? (a.effort - 1u) : (u32)(nwin - 1);
+    PathBuf path;
+    path.sc = &sc;
+    path.cap = lay.P;
+    for (u32 start = 0; start <= last_start; ++start) {
+        path.n = 0;
+        u32 eb = 0, nb = 0;
+        i32 tb = 0;
+        if (start == 0) {
+            path.push(0);  // checkBeginExhaustivePath:352
+        } else {
+            if (!exhaustive_side(ix, v, false, seed_code(ix, v, (i32)start), (i32)start, a.errors, sc, lay.dfs, eb, nb,
+                                 tb)) {
+                if (sc.overflow) return flags | BGR_F_CNT_NOTALIGNED;
+                continue;
+            }
+            if (tb >= 0) path.push(tb);
+            for (u32 j = 0; j < nb; ++j) path.push(sc.get(lay.dfs.best0 + nb - 1 - j));
+        }
+        const i32 lo = (i32)start > nwin - (i32)a.effort ? (i32)start : nwin - (i32)a.effort;
+        for (i32 end = nwin - 1; end >= lo; --end) {
+            u32 ee = 0, ne = 0;
+            i32 te = 0;
+            const u32 avoid = path.n < path.cap ? path.n : path.cap;  // >= 1: the left part is never empty
+            if (!exhaustive_side(ix, v, true, seed_code(ix, v, end), end, a.errors - eb, sc, lay.dfs, ee, ne, te,
+                                 avoid)) {
+                if (sc.overflow) return flags | BGR_F_CNT_NOTALIGNED;
+                continue;
+            }
+            for (u32 j = 0; j < ne; ++j) path.push(sc.get(lay.dfs.best0 + j));
+            path.push(te);
+            if (cover_greedy_path(ix, v, path, (i32)start, end, nwin, a.errors - ee - eb, a.effort)) {
+                n = path.n;
+                return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+            }
+            if (sc.overflow) return flags | BGR_F_CNT_NOTALIGNED;
+        }
     }
     n = 0;
     return flags | BGR_F_CNT_NOTALIGNED;
@@ -1314,7 +1562,8 @@ __global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, 
     sc.overflow = false;
     u32 flags = 0, n = 0, overlaps = 0;
     if (valid) {
-        flags = exhaustive_read(ix, a, r, sc, n, overlaps);
+        flags = (a.mode == BGR_MODE_GREEDY_PATH) ? greedy_path_read(ix, a, r, sc, n)
+                                                 : exhaustive_read(ix, a, r, sc, n, overlaps);
         u32 plen = (flags & BGR_F_MAPPED) && !sc.overflow ? n : 0;
         if (sc.overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
         bgr_result res;

@@ -153,6 +153,7 @@ int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
             break;
         }
         case BGR_MODE_EXHAUSTIVE:
+        case BGR_MODE_GREEDY_PATH:
         case BGR_MODE_EXHAUSTIVE_PATH: {
             const u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
             k_extend_exhaustive<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
@@ -455,8 +456,6 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     Slot& s = ctx->slots[slot];
     if (!s.uploaded) return fail(ctx, BGR_ERR_ARG, "slot has no batch uploaded");
     if (p->mode > BGR_MODE_EXHAUSTIVE_PATH) return fail(ctx, BGR_ERR_ARG, "unknown mode");
-    if (p->mode == BGR_MODE_GREEDY_PATH)
-        return fail(ctx, BGR_ERR_ARG, "BGR_MODE_GREEDY_PATH is not implemented on the device yet");
     CK(cudaSetDevice(ctx->device));
     s.params = *p;
     s.scratch_ints = (p->mode == BGR_MODE_GREEDY) ? ctx->scratch_greedy : ctx->scratch_exhaustive;

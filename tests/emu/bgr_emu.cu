@@ -173,6 +173,8 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
             if (!same && !sc.overflow && !sc2.overflow) return 1000;  // the two formulations disagree
         } else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH) {
             flags = exhaustive_read(ix, a, r, sc, np, overlaps);
+        } else if (mode == BGR_MODE_GREEDY_PATH) {
+            flags = greedy_path_read(ix, a, r, sc, np);
         } else {
             return BGR_ERR_ARG;
         }

@@ -14,7 +14,7 @@ from oracle import oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HARNESS = json.load(open(os.path.join(GOLDEN, "harness_cases.json")))
-MODES = {"greedy": 0, "exhaustive": 1, "exhaustive_path": 3}
+MODES = {"greedy": 0, "exhaustive": 1, "greedy_path": 2, "exhaustive_path": 3}
 
 
 @pytest.mark.parametrize("case", HARNESS, ids=[c["name"] for c in HARNESS])
@@ -37,7 +37,7 @@ def test_emulated_device_code_matches_reference_golden(case):
 @pytest.mark.parametrize("seed", range(3000, 3040))
 def test_emulated_device_code_matches_oracle_fuzz(seed):
     c = S.fuzz_case(seed)
-    for mode in (O.GREEDY, O.EXHAUSTIVE):
+    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH, O.EXHAUSTIVE_PATH):
         o = O.Oracle(c["k"], c["m"], c["effort"])
         o.index_unitigs(c["unitigs"])
         want = [o.align(r, mode) for r in c["reads"]]

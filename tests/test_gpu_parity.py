@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HARNESS = json.load(open(os.path.join(GOLDEN, "harness_cases.json")))
-MODES = {"greedy": 0, "exhaustive": 1, "exhaustive_path": 3}
+MODES = {"greedy": 0, "exhaustive": 1, "greedy_path": 2, "exhaustive_path": 3}
 COUNTERS = ("reads", "aligned", "not_aligned", "no_overlap", "overlaps")
 
 
@@ -53,7 +53,7 @@ def test_golden_vectors_of_the_reference(bg, case):
 @pytest.mark.parametrize("seed", range(2000, 2060))
 def test_fuzz_against_oracle(bg, seed):
     c = S.fuzz_case(seed)
-    for mode in (O.GREEDY, O.EXHAUSTIVE):
+    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH):
         want, wc = oracle_results(c["k"], c["m"], c["effort"], c["unitigs"], c["reads"], mode)
         al = bg.Aligner(c["k"], c["m"], c["effort"])
         al.index_unitigs(c["unitigs"])
@@ -75,7 +75,7 @@ def _k31_case(seed, n_reads, read_len=150, genome=20000, sub=0.01, n_rate=0.0005
 @pytest.mark.parametrize("m", [0, 1, 2, 5])
 def test_k31_reads_greedy_and_exhaustive(bg, m):
     unitigs, reads = _k31_case(7, 3000)
-    for mode in (O.GREEDY, O.EXHAUSTIVE):
+    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH):
         want, wc = oracle_results(31, m, 2, unitigs, reads, mode)
         al = bg.Aligner(31, m, 2)
         al.index_unitigs(unitigs)
@@ -96,7 +96,7 @@ def test_ragged_and_long_reads(bg):
     for ln in [20, 21, 22, 31, 32, 33, 63, 64, 65, 127, 128, 129, 575, 576, 577, 1000, 3000]:
         reads += S.make_reads(rng, haps, 6, ln, sub_rate=0.002, n_rate=0.001, off_graph=0.0)
     rng.shuffle(reads)
-    for mode in (O.GREEDY, O.EXHAUSTIVE):
+    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH):
         want, wc = oracle_results(21, 3, 2, unitigs, reads, mode)
         al = bg.Aligner(21, 3, 2)
         al.index_unitigs(unitigs)
@@ -129,7 +129,7 @@ def test_long_paths_grow_the_scratch(bg):
     rng = random.Random(5)
     unitigs, haps = S.make_graph(rng, 10, genome_len=600, mean_unitig=2, n_variants=0)
     reads = S.make_reads(rng, haps, 200, 300, sub_rate=0.0, off_graph=0.0)
-    for mode in (O.GREEDY, O.EXHAUSTIVE):
+    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH):
         want, _ = oracle_results(10, 2, 2, unitigs, reads, mode)
         al = bg.Aligner(10, 2, 2)
         al.index_unitigs(unitigs)
