@@ -10,12 +10,14 @@
 //   payload : Payload[n_buckets * 4]  per key slot: left[4] + right[4] unitig slots (32 bytes),
 //                                     the reference's two unitigIndices tables merged
 //                                     (reference aligner.h:49-55, aligner.cpp:463-533)
-//   filter  : u32[n_fbuckets * 8]     negative filter in front of `keys` for the seed scan: one bucket =
-//                                     8 tags = one 32-byte sector, ~2 tags per bucket on average. Every
-//                                     key has its tag in its home bucket (no probing), so "no tag equal"
-//                                     proves absence; a bucket that received more than 8 keys is marked
-//                                     saturated (FILTER_SAT in its last slot) and always answers "maybe".
-//                                     A "maybe" is settled exactly against `keys` by whoever consumes it.
+//   bloom   : u32[n_bloom]            negative filter in front of `keys` for the seed scan: a blocked Bloom
+//                                     filter whose block is ONE 32-bit word; every key sets 3 bits of its
+//                                     word. "Some bit clear" proves absence; a window that passes is
+//                                     verified against `keys` in the same kernel, so the hit masks the scan
+//                                     emits are exact. Sized by the build (bloom_words_for): small indexes
+//                                     get a filter that fits shared memory (<= 128 KB, one hash), larger
+//                                     ones 2..16 bytes per key kept L2-resident as far as possible (two
+//                                     hashes).
 //   meta    : UnitigMeta[n_unitigs+1] first base of the unitig in `pool`, and its length; ids are
 //                                     1-based like the reference's (aligner.cpp:408)
 //   pool    : u64[pool_words]         all unitigs, 2 bits per base, first base in the most
@@ -69,8 +71,10 @@ struct BlobHeader {
     u64 pool_words;
     u64 off_keys, off_payload, off_meta, off_pool;  // byte offsets from the blob start
     u64 total_bytes;
-    u64 n_fbuckets;  // filter buckets (8 tags each)
-    u64 off_filter;
+    u64 n_bloom;  // words of the Bloom filter
+    u64 off_bloom;
+    u32 bloom_two_hashes;  // 0: word and bit positions from one 32-bit hash, 1: from two
+    u32 pad;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
 
@@ -125,15 +129,50 @@ BGR_HD u64 bucket_of(u64 key, u64 n_buckets) {
 #endif
 }
 
-// filter: bucket from key_hash, tag from an independent mix; tags are odd, 0 = empty slot
-static const u32 FILTER_SAT = 0xFFFFFFFEu;
-BGR_HD u32 key_tag(u64 key) {
+// ---- Bloom filter of the seed scan. One 32-bit word per probe, three bits per key.
+//   word  = umulhi(h1, n_bloom)
+//   bits  = three 5-bit fields of p, where p = h1 (single-hash mode: n_bloom <= 2^15, so the word index
+//           consumes the top 15 bits and the fields use the low 15) or p = h2 >> 17 (two-hash mode).
+// Kept to 32-bit integer ops: the scan computes one per window and is instruction-issue bound.
+static const u32 BLOOM_SMEM_WORDS = 32768;  // 128 KB: the largest filter the scan keeps in shared memory
+BGR_HD u32 bloom_h1(u64 key) {
+    u32 lo = (u32)key, hi = (u32)(key >> 32);
+    u32 h = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return h;
+}
+BGR_HD u32 bloom_h2(u64 key) {
     u32 lo = (u32)key, hi = (u32)(key >> 32);
     u32 t = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
     t ^= t >> 16;
     t *= 0x85EBCA6Bu;
-    t ^= t >> 13;
-    return t | 1u;
+    return t;
+}
+BGR_HD u32 bloom_mask(u32 p) { return (1u << (p & 31)) | (1u << ((p >> 5) & 31)) | (1u << ((p >> 10) & 31)); }
+BGR_HD u32 bloom_word_of(u32 h1, u32 n_bloom) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(h1, n_bloom);
+#else
+    return (u32)(((u64)h1 * (u64)n_bloom) >> 32);
+#endif
+}
+// number of filter words for n_keys keys (power of two not required)
+inline u64 bloom_words_for(u64 n_keys, bool& two_hashes) {
+    if (n_keys <= 4ull * BLOOM_SMEM_WORDS) {  // shared-memory tier: <= 4 keys per word
+        two_hashes = false;
+        u64 w = 4 * n_keys;
+        if (w < 1024) w = 1024;
+        if (w > BLOOM_SMEM_WORDS) w = BLOOM_SMEM_WORDS;
+        return w;
+    }
+    // global tier: 16 bytes per key while that stays within 64 MB (L2-resident), never below 2 bytes per key
+    two_hashes = true;
+    u64 w = 4 * n_keys;
+    const u64 l2_words = 16ull << 20;
+    if (w > l2_words) w = l2_words;
+    if (w < n_keys / 2) w = n_keys / 2;
+    return w;
 }
 
 // word offset of read r's packed words inside a batch whose reads are concatenated characters:

@@ -243,7 +243,7 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     BlobHeader h;
     memset(&h, 0, sizeof h);
     h.magic = BLOB_MAGIC;
-    h.version = 2;
+    h.version = 3;
     h.k = k;
     h.n_unitigs = nu;
     h.n_keys = n_keys;
@@ -254,9 +254,21 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     h.off_payload = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
     h.off_meta = align_up(h.off_payload + n_buckets * 4 * sizeof(Payload));
     h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
-    h.n_fbuckets = std::max<u64>(4, (n_keys + 1) / 2);  // ~2 tags per 8-slot bucket
-    h.off_filter = align_up(h.off_pool + pool_words * sizeof(u64));
-    h.total_bytes = align_up(h.off_filter + h.n_fbuckets * 8 * sizeof(u32));
+    bool two_hashes = false;
+    h.n_bloom = bloom_words_for(n_keys, two_hashes);
+    if (const char* e = getenv("BGR_BLOOM")) {  // test hook: force the large-index (global, two-hash) tier
+        if (!strcmp(e, "global")) {
+            two_hashes = true;
+            h.n_bloom = std::max<u64>(1024, 4 * n_keys);
+        }
+    }
+    h.bloom_two_hashes = two_hashes ? 1u : 0u;
+    if (h.n_bloom >= 0xFFFFFFFFull) {
+        err = "too many distinct border k-mers for the 32-bit filter hash";
+        return BGR_ERR_LIMIT;
+    }
+    h.off_bloom = align_up(h.off_pool + pool_words * sizeof(u64));
+    h.total_bytes = align_up(h.off_bloom + h.n_bloom * sizeof(u32));
     blob.assign(h.total_bytes / 8, 0);
     char* B = (char*)blob.data();
     memcpy(B, &h, sizeof h);
@@ -283,17 +295,14 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     };
     for (u64 i = 0; i < n_keys; ++i) find_or_insert(keys[i], true);
 
-    // ---- negative filter: every key leaves its tag in its home bucket
+    // ---- Bloom filter of the seed scan: every key sets its three bits
     {
         memcpy(B, &h, sizeof h);
-        u32* filt = (u32*)(B + h.off_filter);
+        u32* bloom = (u32*)(B + h.off_bloom);
         for (u64 i = 0; i < n_keys; ++i) {
-            u32* fb = filt + 8 * bucket_of(keys[i], h.n_fbuckets);
-            u32 tag = key_tag(keys[i]);
-            int j = 0;
-            while (j < 8 && fb[j] != 0 && fb[j] != tag) ++j;
-            if (j < 8) fb[j] = tag;
-            else fb[7] = FILTER_SAT;  // more than 8 keys here: the bucket answers "maybe" to everything
+            const u32 h1 = bloom_h1(keys[i]);
+            const u32 p = two_hashes ? (bloom_h2(keys[i]) >> 17) : h1;
+            bloom[bloom_word_of(h1, (u32)h.n_bloom)] |= bloom_mask(p);
         }
     }
 

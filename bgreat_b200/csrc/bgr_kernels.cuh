@@ -1,10 +1,16 @@
 // sm_100a kernels of the read-to-graph mapping path.
 //
-//   k_pack_scan     warp per read: ASCII -> 2-bit words (+ N mask), then the seed scan: every
-//                   (k-1)-mer window of the read is canonicalised and probed in the border index
-//                   with one 256-bit load per probe (one 32-byte sector). Replaces getNOverlap /
-//                   getListOverlap + the BooPHF lookups (reference aligner.cpp:318-378,
-//                   BooPHF.h:783). Output: a hit bitmask per read.
+//   k_scan_tiles    the seed scan (replaces getNOverlap / getListOverlap + the BooPHF lookups, reference
+//                   aligner.cpp:318-378, BooPHF.h:783). Persistent CTAs walk tiles of consecutive reads:
+//                   the tile's characters arrive in shared memory by one TMA bulk copy (double
+//                   buffered), every thread takes one CHUNK = 32 consecutive windows of one read: packs
+//                   the 64 characters under it to 2-bit words, rolls the forward / reverse-complement
+//                   (k-1)-mer codes over them, tests each canonical code in the Bloom filter (in shared
+//                   memory when the index is small, else global/L2) and verifies the few survivors in the
+//                   key table. Output: packed words + an EXACT hit bitmask per read.
+//   k_pack_scan     warp per read, any length, N-aware: the general form of the same scan, used for the
+//                   reads the tile kernel hands over (reads containing non-ACGT characters, tiles that do
+//                   not fit the shared-memory buffer).
 //   k_extend_greedy thread per read: alignReadGreedy and its four walkers (reference
 //                   alignerGreedy.cpp:35-57,167-364) on packed words, mismatches by XOR + popc.
 //   k_extend_exhaustive  thread per read: alignReadExhaustive / alignReadExhaustivePath
@@ -39,8 +45,9 @@ struct DevIndex {
     const UnitigMeta* meta;
     const u64* pool;
     u64 n_buckets;
-    const u32* filter;
-    u32 n_fbuckets;
+    const u32* bloom;
+    u32 n_bloom;
+    u32 bloom_two_hashes;
     u32 k;
 };
 
@@ -57,7 +64,8 @@ struct DevCounters {
 struct ScanCounters {
     unsigned long long c[BGR_C_COUNT];
     u32 list_n;  // reads handed to the extension kernel (those with at least one border hit)
-    u32 pad[3];
+    u32 slow_n;  // reads the tile kernel handed to the general scan kernel
+    u32 pad[2];
 };
 
 struct BatchArgs {
@@ -76,7 +84,10 @@ struct BatchArgs {
     u64 pool_cap;
     DevCounters* cnt;
     ScanCounters* scnt;
-    u32* list;  // indices of the reads the extension kernel has to look at (unordered)
+    u32* list;       // indices of the reads the extension kernel has to look at (unordered)
+    u32* slow_list;  // reads left to the general scan kernel (null: it scans every read)
+    u32 tile_r;      // reads per tile of the tile kernel (even, <= ST_MAX_R)
+    u32 tile_cb;     // bytes of one character buffer of the tile kernel
     u32 errors, effort, mode;
 };
 
@@ -125,22 +136,8 @@ BGR_HD i64 index_find(const DevIndex& ix, u64 key) {
     }
 }
 
-// Negative filter in front of the key table: false = the key is certainly absent, true = maybe
-// (settled exactly by index_find where it matters). One 256-bit load, eight 32-bit compares, no loop.
-BGR_HD bool filter_maybe(const DevIndex& ix, u64 key) {
-    const u32 tag = key_tag(key);
-    const u32* p = ix.filter + 8 * (size_t)bucket_of(key, ix.n_fbuckets);
-    u32 t0, t1, t2, t3, t4, t5, t6, t7;
-#if defined(__CUDA_ARCH__)
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7)
-                 : "l"(p));
-#else
-    t0 = p[0], t1 = p[1], t2 = p[2], t3 = p[3], t4 = p[4], t5 = p[5], t6 = p[6], t7 = p[7];
-#endif
-    return (t0 == tag) | (t1 == tag) | (t2 == tag) | (t3 == tag) | (t4 == tag) | (t5 == tag) | (t6 == tag) |
-           (t7 == tag) | (t7 == FILTER_SAT);
-}
+// exact membership of a canonical (k-1)-mer in the border key set
+BGR_HD bool index_has(const DevIndex& ix, u64 key) { return index_find(ix, key) >= 0; }
 
 // ------------------------------------------------------------------------------ pack + seed scan
 
@@ -178,8 +175,6 @@ BGR_HD u32 packed_byte(u32 c0) { return 8 * (1 + (c0 >> 5)) + 7 - ((c0 >> 2) & 7
 //     absolute positions < k-1; the rolling RC stream takes N as 3 everywhere (nuc2intrc default 0 =
 //     complement of 3). hit1 is that test; hit2 is the test for the same window of the
 //     reverse-complemented read (N->A, utils.cpp:52-73), needed only when the read has N.
-//     Both are answered by the negative filter: "maybe" bits may (about 1e-9 per window) be false and
-//     are settled exactly when a seed is taken (greedy_read).
 //   exhaustive modes: getListOverlap stores the same forward code; getBegin/getEnd canonicalise it
 //     with a true rcb (aligner.cpp:149,211), so hit1 tests min(num, rcb(num)).
 BGR_HD void scan_window(const DevIndex& ix, const u64* D, const u64* ND, bool anyN, bool exhaustive, u32 i,
@@ -195,30 +190,12 @@ BGR_HD void scan_window(const DevIndex& ix, const u64* D, const u64* ND, bool an
     }
     u64 rc = rcb(exhaustive ? num : x2, km1);
     u64 rep = num < rc ? num : rc;
-    hit1 = filter_maybe(ix, rep);
+    hit1 = index_has(ix, rep);
     hit2 = false;
     if (anyN && !exhaustive) {
         u64 rep2 = x2 < rc ? x2 : rc;
-        hit2 = (rep2 == rep) ? hit1 : filter_maybe(ix, rep2);
+        hit2 = (rep2 == rep) ? hit1 : index_has(ix, rep2);
     }
-}
-
-// The canonical (k-1)-mer scan_window tested for window i of the pass's read: what a "maybe" of the
-// hit mask has to be settled against before the window counts as a seed.
-BGR_HD u64 seed_rep(const DevIndex& ix, const u64* D, const u64* ND, bool hasN, bool pass, i32 len, i32 i) {
-    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
-    const i32 j = pass ? len - (i32)km1 - i : i;  // stored coordinates
-    u64 x0 = ld_bases(D, j) >> sh;
-    u64 num = x0, x2 = x0;
-    if (hasN) {
-        u64 nm = ld_bases(ND, j) >> sh;
-        x2 = x0 | nm;
-        u64 first = ((u32)j < km1) ? (nm & ~((1ull << (2 * j)) - 1)) : 0ull;
-        num = x0 | first;
-    }
-    u64 rc = rcb(x2, km1);
-    if (pass) return x2 < rc ? x2 : rc;
-    return num < rc ? num : rc;
 }
 
 // What the seed scan already knows about a read that has no border hit at all: greedy ->
@@ -254,7 +231,7 @@ BGR_HD u32 scan_lane_rolling(const DevIndex& ix, const u64* D, u32 w0, u32 nwin)
         for (u32 j = 0; j < PS_WPL; ++j) {
             if (w0 + j < nwin) {
                 u64 rep = num < rc ? num : rc;
-                hits |= (u32)filter_maybe(ix, rep) << j;
+                hits |= (u32)index_has(ix, rep) << j;
             }
             u64 nb = nxt >> 62;
             nxt <<= 2;
@@ -395,7 +372,10 @@ __global__ void __launch_bounds__(PS_WARPS * 32, MINB) k_pack_scan(DevIndex ix, 
     unsigned long long windows = 0, n_reads = 0, n_nohit = 0;
     u32 n_list = 0;  // reads buffered in s_list[warp]
 
-    for (u32 r = blockIdx.x * PS_WARPS + warp; r < a.n; r += nwarps) {
+    // the reads the tile kernel handed over (slow_list), or every read of the batch (no list)
+    const u32 n_items = a.slow_list ? a.scnt->slow_n : a.n;
+    for (u32 it = blockIdx.x * PS_WARPS + warp; it < n_items; it += nwarps) {
+        const u32 r = a.slow_list ? a.slow_list[it] : it;
         const u64 o = a.off[r];
         const u32 len = (u32)(a.off[r + 1] - o);
         const u64 wb = read_word_base(o, r);
@@ -459,6 +439,392 @@ __global__ void __launch_bounds__(PS_WARPS * 32, MINB) k_pack_scan(DevIndex ix, 
             if (n_nohit) atomicAdd(&a.scnt->c[BGR_C_NOTALIGNED], n_nohit);
         } else if (n_nohit) {
             atomicAdd(&a.scnt->c[BGR_C_NOOVERLAP], n_nohit);
+        }
+    }
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------ tile scan: chunk logic
+//
+// A chunk is 32 consecutive windows of one read: windows [32l, 32l+count). It needs the bases
+// [32l, 32l + count + k-2), at most 62 <= 64 of them: two packed words w0 (bases 32l..32l+31) and w1.
+
+static const u32 TS_FLAG_HIT = 1u, TS_FLAG_BAD = 2u;
+
+// 64 characters starting at p -> w0, w1 (2 bits per base, first base most significant). `bad` != 0
+// iff some character is not A/C/G/T (then the codes are meaningless: the caller hands the read to
+// the general kernel, which knows how the reference treats such characters).
+BGR_HD void pack_span(const unsigned char* p, u64& w0, u64& w1, u32& bad) {
+    u32 acc[4] = {0, 0, 0, 0};
+    bad = 0;
+#if defined(__CUDA_ARCH__)
+    // aligned 32-bit loads + funnel shift: 17 loads for 16 groups of 4 characters
+    const u32* wp = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
+    const u32 bs = (u32)((uintptr_t)p & 3) * 8;
+    u32 prev = wp[0];
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        const u32 nxt = wp[g + 1];
+        const u32 x = __funnelshift_r(prev, nxt, bs);
+        prev = nxt;
+        const u32 t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;  // A0 C1 G2 T3 per byte
+        u32 sel = (t | (t >> 4)) & 0x00FF00FFu;
+        sel = (sel | (sel >> 8)) & 0xFFFFu;                 // nibble i = code of character i
+        bad |= x ^ __byte_perm(0x54474341u, 0u, sel);       // the character that code stands for
+        acc[g >> 2] = (acc[g >> 2] << 8) | ((t * 0x40100401u) >> 24);
+    }
+#else
+    for (int g = 0; g < 16; ++g) {
+        u32 code8 = 0;
+        for (int j = 0; j < 4; ++j) {
+            const u32 c = base_code(p[4 * g + j]);
+            if (c > 3) bad = 1;
+            code8 = (code8 << 2) | (c & 3);
+        }
+        acc[g >> 2] = (acc[g >> 2] << 8) | code8;
+    }
+#endif
+    w0 = ((u64)acc[0] << 32) | acc[1];
+    w1 = ((u64)acc[2] << 32) | acc[3];
+}
+
+// zero the bases at and after `rem` (bases of the read left from the chunk's first base on)
+BGR_HD void clip_span(u32 rem, u64& w0, u64& w1) {
+    if (rem < 32) {
+        w0 &= ~(~0ull >> (2 * rem));
+        w1 = 0;
+    } else if (rem < 64) {
+        w1 = (rem == 32) ? 0ull : (w1 & ~(~0ull >> (2 * (rem - 32))));
+    }
+}
+
+// Bloom test of the chunk's windows: bit j = window 32l+j may be a border. The first window is taken
+// from w0, the following ones roll the forward and the reverse-complement code like update / updateRC
+// (aligner.cpp:305-315). TWO: word index and bit positions come from two hashes (large filters).
+template <bool TWO>
+BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, u32 km1, u64 w0, u64 w1, u32 count) {
+    const u32 sh = 64 - 2 * km1, top = 2 * (km1 - 1);
+    const u64 mask = ~0ull >> sh;
+    u64 num = w0 >> sh;
+    u64 rc = rcb(num, km1);
+    u64 inc = (w0 << (2 * km1)) | (w1 >> sh);  // the bases that follow the first window
+    u32 hits = 0;
+#pragma unroll
+    for (u32 j = 0; j < 32; ++j) {
+        if (j < count) {
+            const u64 rep = num < rc ? num : rc;
+            const u32 h1 = bloom_h1(rep);
+            const u32 m = bloom_mask(TWO ? (bloom_h2(rep) >> 17) : h1);
+            const u32 w = bloom[bloom_word_of(h1, n_bloom)];
+            if ((w & m) == m) hits |= 1u << j;
+        }
+        const u64 nb = inc >> 62;
+        inc <<= 2;
+        num = ((num << 2) | nb) & mask;
+        rc = (rc >> 2) | ((3 - nb) << top);
+    }
+    return hits;
+}
+
+// The windows that passed the filter, checked against the key table: the returned mask is exact.
+BGR_HD u32 verify_chunk(const DevIndex& ix, u64 w0, u64 w1, u32 hits) {
+    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
+    u32 m = hits;
+    while (m) {
+        const u32 j = (u32)BGR_FFS(m) - 1;
+        m &= m - 1;
+        const u64 x = (j ? ((w0 << (2 * j)) | (w1 >> (64 - 2 * j))) : w0) >> sh;
+        const u64 rc = rcb(x, km1);
+        if (!index_has(ix, x < rc ? x : rc)) hits &= ~(1u << j);
+    }
+    return hits;
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------ tile scan kernel
+
+static const int ST_THREADS = 1024;
+static const u32 ST_MAX_R = 256;    // reads per tile (one prologue / epilogue thread each)
+static const u32 ST_CHAR_SLACK = 128;  // bytes readable behind a character buffer (look-ahead of the last span)
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA bulk copy global -> shared (1-D, 16-byte granules), completion counted on an mbarrier; the read
+// characters are used once, so they are marked evict-first in L2 (the filter and the index stay).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar, u64 policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+struct TileSmem {
+    u32* bloom;
+    unsigned char* chars[2];
+    u64* off;     // ST_MAX_R + 2
+    u32* prefix;  // ST_MAX_R + 2
+    u32* flags;   // ST_MAX_R + 2
+    u64* mbar;    // 2
+    u32* wsum;    // 32
+};
+__host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb) {
+    size_t b = ((size_t)bloom_words_in_smem * 4 + 127) & ~(size_t)127;
+    b += 2 * ((size_t)tile_cb + ST_CHAR_SLACK);
+    b += (ST_MAX_R + 2) * 8 + 2 * (ST_MAX_R + 2) * 4 + 2 * 8 + 32 * 4;
+    return b + 128;
+}
+
+template <bool BLOOM_SMEM>
+__global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, BatchArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileSmem S;
+    {
+        unsigned char* q = smem_raw;
+        S.bloom = (u32*)q;
+        q += BLOOM_SMEM ? (((size_t)ix.n_bloom * 4 + 127) & ~(size_t)127) : 0;
+        S.chars[0] = q;
+        q += a.tile_cb + ST_CHAR_SLACK;
+        S.chars[1] = q;
+        q += a.tile_cb + ST_CHAR_SLACK;
+        S.off = (u64*)q;
+        q += (ST_MAX_R + 2) * 8;
+        S.prefix = (u32*)q;
+        q += (ST_MAX_R + 2) * 4;
+        S.flags = (u32*)q;
+        q += (ST_MAX_R + 2) * 4;
+        S.mbar = (u64*)q;
+        q += 16;
+        S.wsum = (u32*)q;
+    }
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 R = a.tile_r, n = a.n, G = gridDim.x;
+    const u32 ntiles = (n + R - 1) / R;
+    const u32 km1 = ix.k - 1;
+    const bool exhaustive = a.mode != BGR_MODE_GREEDY;
+    const u32* bloom = BLOOM_SMEM ? S.bloom : ix.bloom;
+
+    u64 policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (tid == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (BLOOM_SMEM) {
+        const uint4* src = (const uint4*)ix.bloom;  // the blob pads the filter to a 256-byte boundary
+        uint4* dst = (uint4*)S.bloom;
+        for (u32 i = tid; i < (ix.n_bloom + 3) / 4; i += ST_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    // bytes the tile [lo, hi) of the character stream occupies in a buffer (16-byte granules)
+    auto tile_bytes = [](u64 lo, u64 hi) -> u64 { return ((hi + 15) & ~15ull) - (lo & ~15ull); };
+    auto load_bounds = [&](u32 t, u64& lo, u64& hi) {
+        lo = hi = 0;
+        if (t < ntiles) {
+            const u32 r0 = t * R;
+            lo = a.off[r0];
+            hi = a.off[min(n, r0 + R)];
+        }
+    };
+    auto issue = [&](u32 buf, u64 lo, u64 hi) {
+        const u64 bytes = tile_bytes(lo, hi);
+        if (bytes != 0 && bytes <= a.tile_cb) {
+            mbar_expect_tx(&S.mbar[buf], (u32)bytes);
+            bulk_g2s(S.chars[buf], a.seq + (lo & ~15ull), (u32)bytes, &S.mbar[buf], policy);
+        }
+    };
+
+    u32 tile = blockIdx.x;
+    u64 nx_lo = 0, nx_hi = 0;  // thread 0: bounds of the tile after the current one
+    if (tid == 0) {
+        u64 lo, hi;
+        load_bounds(tile, lo, hi);
+        if (tile < ntiles) issue(0, lo, hi);
+        load_bounds(tile + G, nx_lo, nx_hi);
+    }
+    u64 my_off = 0;  // off[first read of the tile + tid], fetched one tile ahead
+    if (tile < ntiles && tid <= R) {
+        const u64 idx = (u64)tile * R + tid;
+        if (idx <= n) my_off = a.off[idx];
+    }
+    u32 uses[2] = {0, 0};  // completed TMA rounds per buffer (mbarrier phase parity)
+    unsigned long long c_windows = 0;
+    u32 c_reads = 0, c_nohit = 0, c_verify = 0;
+
+    for (u32 it = 0; tile < ntiles; ++it, tile += G) {
+        const u32 buf = it & 1;
+        const u32 r0 = tile * R;
+        const u32 cnt = min(R, n - r0);
+        if (tid == 0) {  // next tile's characters start flowing now; its buffer was released by the last barrier
+            if (tile + G < ntiles) issue(buf ^ 1, nx_lo, nx_hi);
+            load_bounds(tile + 2 * G, nx_lo, nx_hi);
+        }
+        if (tid <= cnt) S.off[tid] = my_off;
+        u64 next_off = 0;
+        if (tile + G < ntiles && tid <= R) {
+            const u64 idx = (u64)(tile + G) * R + tid;
+            if (idx <= n) next_off = a.off[idx];
+        }
+        __syncthreads();
+
+        // ---- per read: length, windows, chunks; exclusive scan of the chunk counts
+        u64 o = 0;
+        u32 len = 0, nwin = 0, chunks = 0;
+        if (tid < cnt) {
+            o = S.off[tid];
+            len = (u32)(S.off[tid + 1] - o);
+            nwin = (len >= km1) ? len - km1 + 1 : 0;
+            chunks = (nwin + 31) >> 5;
+            S.flags[tid] = 0;
+        }
+        if (tid < ST_MAX_R) {
+            u32 incl = chunks;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (u32)d) incl += x;
+            }
+            if (lane == 31) S.wsum[warp] = incl;
+            chunks = incl - chunks;  // exclusive within the warp
+        }
+        __syncthreads();
+        if (tid < ST_MAX_R) {
+            u32 basew = 0;
+#pragma unroll
+            for (u32 w = 0; w < ST_MAX_R / 32; ++w)
+                if (w < warp) basew += S.wsum[w];
+            if (tid < cnt) S.prefix[tid] = basew + chunks;
+            if (tid == cnt - 1) S.prefix[cnt] = basew + chunks + ((nwin + 31) >> 5);
+        }
+        const u64 t_lo = S.off[0], t_hi = S.off[cnt];
+        const u64 t_bytes = tile_bytes(t_lo, t_hi);
+        const bool fits = t_bytes <= a.tile_cb;
+        __syncthreads();
+
+        if (fits) {
+            if (t_bytes != 0) {
+                mbar_wait(&S.mbar[buf], uses[buf] & 1);
+                ++uses[buf];
+            }
+            const u32 T = S.prefix[cnt];
+            const unsigned char* cb = S.chars[buf];
+            const u64 gs = t_lo & ~15ull;
+            for (u32 j = tid; j < T; j += ST_THREADS) {
+                // the read this chunk belongs to: last rd with prefix[rd] <= j
+                u32 rd = 0;
+#pragma unroll
+                for (u32 sft = ST_MAX_R / 2; sft; sft >>= 1) {
+                    const u32 c = rd + sft;
+                    if (c < cnt && S.prefix[c] <= j) rd = c;
+                }
+                const u32 l = j - S.prefix[rd];
+                const u64 ro = S.off[rd];
+                const u32 rlen = (u32)(S.off[rd + 1] - ro);
+                const u32 rnwin = rlen - km1 + 1;
+                const u32 rchunks = (rnwin + 31) >> 5;
+                const u32 r = r0 + rd;
+                const u64 wb = read_word_base(ro, r);
+                u64 w0, w1;
+                u32 bad;
+                pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
+                clip_span(rlen - 32 * l, w0, w1);
+                // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
+                u64* gF = a.F + wb;
+                const u32 nw = (rlen + 31) >> 5;
+                gF[1 + l] = w0;
+                if (l == 0) gF[0] = 0;
+                if (l + 1 == rchunks) {
+                    if (l + 1 < nw) gF[2 + l] = w1;
+                    gF[nw + 1] = 0;
+                    gF[nw + 2] = 0;
+                }
+                const u32 count = min(32u, rnwin - 32 * l);
+                // the shared-memory tier is the single-hash tier (bloom_words_for)
+                u32 hits = scan_chunk<!BLOOM_SMEM>(bloom, ix.n_bloom, km1, w0, w1, count);
+                c_verify += __popc(hits);
+                hits = verify_chunk(ix, w0, w1, hits);
+                a.H1[wb + l] = hits;
+                const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
+                if (fl) atomicOr(&S.flags[rd], fl);
+            }
+        }
+        __syncthreads();
+
+        // ---- per read: classify, hand on
+        if (tid < ST_MAX_R) {
+            const bool valid = tid < cnt;
+            const u32 r = r0 + tid;
+            const u32 fl = valid ? S.flags[tid] : 0u;
+            const bool slow = valid && (!fits || (fl & TS_FLAG_BAD));
+            const bool hit = (fl & TS_FLAG_HIT) != 0;
+            const bool pass_on = valid && !slow && (hit || (exhaustive && len == km1));
+            if (valid && !slow) {
+                a.info[r] = hit ? INFO_HIT1 : 0u;
+                c_windows += nwin;
+                c_reads += 1;
+                if (!pass_on) {
+                    bgr_result res;
+                    res.flags_len = no_hit_flags(exhaustive);
+                    res.path_off = 0;
+                    a.res[r] = res;
+                    c_nohit += 1;
+                }
+            }
+            const u32 mp = __ballot_sync(0xFFFFFFFFu, pass_on);
+            const u32 ms = __ballot_sync(0xFFFFFFFFu, slow);
+            u32 bp = 0, bs = 0;
+            if (lane == 0) {
+                if (mp) bp = atomicAdd(&a.scnt->list_n, (u32)__popc(mp));
+                if (ms) bs = atomicAdd(&a.scnt->slow_n, (u32)__popc(ms));
+            }
+            bp = __shfl_sync(0xFFFFFFFFu, bp, 0);
+            bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
+            const u32 lt = (1u << lane) - 1;
+            if (pass_on) a.list[bp + __popc(mp & lt)] = r;
+            if (slow) a.slow_list[bs + __popc(ms & lt)] = r;
+        }
+        my_off = next_off;
+        // the next iteration's first barrier orders these reads of S.flags / S.off before they are rewritten
+    }
+
+    // ---- counters: one atomic per warp and counter
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c_windows += __shfl_xor_sync(0xFFFFFFFFu, c_windows, d);
+        c_reads += __shfl_xor_sync(0xFFFFFFFFu, c_reads, d);
+        c_nohit += __shfl_xor_sync(0xFFFFFFFFu, c_nohit, d);
+        c_verify += __shfl_xor_sync(0xFFFFFFFFu, c_verify, d);
+    }
+    if (lane == 0) {
+        if (c_windows) atomicAdd(&a.scnt->c[BGR_C_WINDOWS], c_windows);
+        if (c_reads) atomicAdd(&a.scnt->c[BGR_C_READS], (unsigned long long)c_reads);
+        if (c_verify) atomicAdd(&a.scnt->c[BGR_C_VERIFIED], (unsigned long long)c_verify);
+        if (exhaustive) {
+            if (c_windows) atomicAdd(&a.scnt->c[BGR_C_OVERLAPS], c_windows);  // overlaps += listOverlap.size()
+            if (c_nohit) atomicAdd(&a.scnt->c[BGR_C_NOTALIGNED], (unsigned long long)c_nohit);
+        } else if (c_nohit) {
+            atomicAdd(&a.scnt->c[BGR_C_NOOVERLAP], (unsigned long long)c_nohit);
         }
     }
 }
@@ -884,8 +1250,6 @@ struct GreedyState {
         // ---- next seed (possibly switching to the reverse-complement pass)
         for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
             i32 p = tried < max_seeds ? it.next() : -1;
-            // the hit mask comes from the negative filter: settle the "maybe" exactly
-            while (p >= 0 && index_find(ix, seed_rep(ix, v.D, v.ND, v.hasN, v.pass, v.len, p)) < 0) p = it.next();
             if (p >= 0) {
                 ++tried;
                 seed_c = code = seed_code(ix, v, p);
@@ -1036,7 +1400,6 @@ BGR_HD u32 greedy_read_walkers(const DevIndex& ix, const BatchArgs& a, u32 r, Sc
         u32 tried = 0;
         while (tried < max_seeds) {
             i32 pos = it.next();
-            while (pos >= 0 && index_find(ix, seed_rep(ix, v.D, v.ND, v.hasN, v.pass, v.len, pos)) < 0) pos = it.next();
             if (pos < 0) break;
             ++tried;
             u64 code = seed_code(ix, v, pos);

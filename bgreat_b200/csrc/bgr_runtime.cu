@@ -18,6 +18,9 @@ namespace {
 
 thread_local std::string g_err;
 
+// bytes of one character buffer of the tile scan: 256 reads of 150 bases and their alignment slack
+const u32 TILE_CB = 40960;
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -40,6 +43,7 @@ struct Slot {
     ScanCounters* d_scnt = nullptr;
     ScanCounters* h_scnt = nullptr;  // pinned
     u32* d_list = nullptr;
+    u32* d_slow = nullptr;  // reads the tile scan hands to the general scan kernel
     unsigned long long* d_bsum = nullptr;  // per-1024-read path length sums (compaction)
     size_t cap_bsum = 0;
     // current batch
@@ -47,6 +51,7 @@ struct Slot {
     u64 chars = 0, words = 0;
     bgr_params params{};
     u32 scratch_ints = 0;
+    u32 tile_r = 0;  // reads per tile of the tile scan for this batch (0: general kernel only)
     bool uploaded = false, ran = false, timed = false, counted = false;
     bgr_result* h_res = nullptr;
     i32* h_pool = nullptr;
@@ -103,15 +108,18 @@ int grow(bgr_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack_num = 5, si
 int set_index_from_device_blob(bgr_ctx* ctx) {
     CK(cudaMemcpy(&ctx->hdr, ctx->d_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost));
     const BlobHeader& h = ctx->hdr;
-    if (h.magic != BLOB_MAGIC || h.version != 2) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
+    if (h.magic != BLOB_MAGIC || h.version != 3) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
     char* B = (char*)ctx->d_blob;
     ctx->ix.keys = (const u64*)(B + h.off_keys);
     ctx->ix.payload = (const Payload*)(B + h.off_payload);
     ctx->ix.meta = (const UnitigMeta*)(B + h.off_meta);
     ctx->ix.pool = (const u64*)(B + h.off_pool);
     ctx->ix.n_buckets = h.n_buckets;
-    ctx->ix.filter = (const u32*)(B + h.off_filter);
-    ctx->ix.n_fbuckets = (u32)h.n_fbuckets;
+    ctx->ix.bloom = (const u32*)(B + h.off_bloom);
+    ctx->ix.n_bloom = (u32)h.n_bloom;
+    ctx->ix.bloom_two_hashes = h.bloom_two_hashes;
+    if (!h.bloom_two_hashes && h.n_bloom > BLOOM_SMEM_WORDS)
+        return fail(ctx, BGR_ERR_FORMAT, "index blob: single-hash filter larger than the shared-memory tier");
     ctx->ix.k = h.k;
     ctx->has_index = true;
     return BGR_OK;
@@ -128,7 +136,7 @@ int install_host_blob(bgr_ctx* ctx, const void* blob, u64 bytes) {
     if (bytes < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index blob too small");
     BlobHeader h;
     memcpy(&h, blob, sizeof h);
-    if (h.magic != BLOB_MAGIC || h.version != 2 || h.total_bytes != bytes)
+    if (h.magic != BLOB_MAGIC || h.version != 3 || h.total_bytes != bytes)
         return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version/size");
     CK(cudaSetDevice(ctx->device));
     int rc = drop_index(ctx);
@@ -184,6 +192,9 @@ BatchArgs make_args(Slot& s) {
     a.cnt = s.d_cnt;
     a.scnt = s.d_scnt;
     a.list = s.d_list;
+    a.slow_list = s.d_slow;
+    a.tile_r = s.tile_r;
+    a.tile_cb = TILE_CB;
     a.errors = s.params.errors;
     a.effort = s.params.effort;
     a.mode = s.params.mode;
@@ -296,6 +307,7 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
         cudaFree(s.d_cnt);
         cudaFree(s.d_scnt);
         cudaFree(s.d_list);
+        cudaFree(s.d_slow);
         cudaFree(s.d_bsum);
         if (s.h_cnt) cudaFreeHost(s.h_cnt);
         if (s.h_scnt) cudaFreeHost(s.h_scnt);
@@ -424,12 +436,13 @@ int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* of
     int rc;
     if ((rc = grow(ctx, s.d_seq, s.cap_seq, (size_t)chars + 16))) return rc;
     if (n + 1 > s.cap_reads || !s.d_off) {
-        size_t cap = 0, c2 = 0, c3 = 0, c4 = 0;
-        if ((rc = grow(ctx, s.d_off, cap, (size_t)n + 1))) return rc;
+        size_t cap = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+        if ((rc = grow(ctx, s.d_off, cap, (size_t)n + 4))) return rc;
         if ((rc = grow(ctx, s.d_res, c2, (size_t)n + 1))) return rc;
         if ((rc = grow(ctx, s.d_info, c3, (size_t)n + 1))) return rc;
         if ((rc = grow(ctx, s.d_list, c4, (size_t)n + 1))) return rc;
-        s.cap_reads = std::min(std::min(cap, c4), std::min(c2, c3));
+        if ((rc = grow(ctx, s.d_slow, c5, (size_t)n + 1))) return rc;
+        s.cap_reads = std::min(std::min(std::min(cap, c4), c5), std::min(c2, c3)) - 3;
     }
     if (words > s.cap_words || !s.d_F) {
         size_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -463,7 +476,31 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     CK(cudaMemsetAsync(s.d_scnt, 0, sizeof(ScanCounters), s.stream));
     CK(cudaEventRecord(s.ev[0], s.stream));
     if (s.n) {
+        // reads per tile from the batch's mean read length: a tile's characters must fit one buffer
+        const u64 mean_len = (s.chars + s.n - 1) / s.n;
+        u64 tr = (TILE_CB - 32) / std::max<u64>(mean_len, 1);
+        if (tr > ST_MAX_R) tr = ST_MAX_R;
+        s.tile_r = (u32)(tr & ~1ull);
         BatchArgs a = make_args(s);
+        if (s.tile_r >= 2) {
+            // tile scan: one persistent CTA per SM; the Bloom filter rides in shared memory when it is small
+            const bool bloom_smem = !ctx->ix.bloom_two_hashes;
+            const size_t smem = tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
+            const u32 ntiles = (s.n + s.tile_r - 1) / s.tile_r;
+            const u32 blocks = std::min<u32>(ntiles, (u32)ctx->sm_count);
+            if (bloom_smem) {
+                CK(cudaFuncSetAttribute(k_scan_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_scan_tiles<true><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);
+            } else {
+                CK(cudaFuncSetAttribute(k_scan_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_scan_tiles<false><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);
+            }
+            ctx->launches++;
+            CK(cudaGetLastError());
+        } else {
+            a.slow_list = nullptr;  // reads too long for a tile: the general kernel takes the whole batch
+        }
+        // general scan for what the tile kernel handed over (usually nothing: the kernel then exits at once)
         u32 blocks = (s.n + PS_WARPS - 1) / PS_WARPS;
         u32 maxb = (u32)ctx->sm_count * ctx->scan_blocks_per_sm;
         if (blocks > maxb) blocks = maxb;

@@ -68,6 +68,7 @@ enum {
     BGR_C_NOOVERLAP = 3,  /* noOverlapRead */
     BGR_C_OVERLAPS = 4,   /* overlaps (exhaustive / paths modes: windows listed) */
     BGR_C_WINDOWS = 5,    /* instrumentation: (k-1)-mer windows probed by the seed-scan kernel */
+    BGR_C_VERIFIED = 6,   /* instrumentation: windows that passed the Bloom filter and were looked up in the key table */
     BGR_C_COUNT = 8
 };
 

@@ -34,8 +34,9 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     ix.pool = (const u64*)(B + h.off_pool);
     ix.n_buckets = h.n_buckets;
     ix.k = h.k;
-    ix.filter = (const u32*)(B + h.off_filter);
-    ix.n_fbuckets = (u32)h.n_fbuckets;
+    ix.bloom = (const u32*)(B + h.off_bloom);
+    ix.n_bloom = (u32)h.n_bloom;
+    ix.bloom_two_hashes = h.bloom_two_hashes;
 
     const u64 chars = off[n];
     const u64 words = batch_words(chars, n);
@@ -63,13 +64,19 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     a.cnt = &cnt;
     a.scnt = &scnt;
     a.list = list.data();
+    a.slow_list = nullptr;
+    a.tile_r = 0;
+    a.tile_cb = 0;
     a.errors = errors;
     a.effort = effort;
     a.mode = mode;
     const u32 km1 = k - 1;
     const bool exhaustive = mode != BGR_MODE_GREEDY;
 
-    // ---- k_pack_scan, one "warp" per read
+    // ---- k_scan_tiles: one "thread" per chunk of 32 windows (pack_span / scan_chunk / verify_chunk);
+    //      a read with a non-ACGT character goes to the general form below, like on the device
+    std::vector<unsigned char> padded(seqs, seqs + chars);
+    padded.resize(chars + 128, 'A');
     for (u32 r = 0; r < n; ++r) {
         const u64 o = off[r];
         const u32 len = (u32)(off[r + 1] - o);
@@ -77,6 +84,49 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         const u32 nw = (len + 31) >> 5;
         u64* gF = a.F + wb;
         u64* gN = a.NM + wb;
+        const u32 nwin_t = (len >= km1) ? len - km1 + 1 : 0;
+        const u32 chunks = (nwin_t + 31) >> 5;
+        bool tile_bad = false, tile_hit = false;
+        for (u32 l = 0; l < chunks; ++l) {
+            u64 w0, w1;
+            u32 bad;
+            // on the device the span may run into the next read's characters: only the part inside the
+            // read can flag it here, which is the exact rule (a spurious flag just takes the general path)
+            unsigned char span[64];
+            for (u32 j = 0; j < 64; ++j) span[j] = (32 * l + j < len) ? padded[o + 32 * l + j] : (unsigned char)'A';
+            pack_span(span, w0, w1, bad);
+            clip_span(len - 32 * l, w0, w1);
+            gF[1 + l] = w0;
+            if (l == 0) gF[0] = 0;
+            if (l + 1 == chunks) {
+                if (l + 1 < nw) gF[2 + l] = w1;
+                gF[nw + 1] = 0;
+                gF[nw + 2] = 0;
+            }
+            const u32 count = nwin_t - 32 * l < 32u ? nwin_t - 32 * l : 32u;
+            u32 hits = ix.bloom_two_hashes ? scan_chunk<true>(ix.bloom, ix.n_bloom, km1, w0, w1, count)
+                                           : scan_chunk<false>(ix.bloom, ix.n_bloom, km1, w0, w1, count);
+            scnt.c[BGR_C_VERIFIED] += (u64)__builtin_popcount(hits);
+            hits = verify_chunk(ix, w0, w1, hits);
+            a.H1[wb + l] = hits;
+            tile_bad |= bad != 0;
+            tile_hit |= hits != 0;
+        }
+        if (!tile_bad) {
+            a.info[r] = tile_hit ? INFO_HIT1 : 0u;
+            scnt.c[BGR_C_WINDOWS] += nwin_t;
+            scnt.c[BGR_C_READS] += 1;
+            if (exhaustive) scnt.c[BGR_C_OVERLAPS] += nwin_t;
+            if (tile_hit || (exhaustive && len == km1)) {
+                a.list[scnt.list_n++] = r;
+            } else {
+                res[r].flags_len = no_hit_flags(exhaustive);
+                res[r].path_off = 0;
+                scnt.c[exhaustive ? BGR_C_NOTALIGNED : BGR_C_NOOVERLAP] += 1;
+            }
+            continue;
+        }
+        // ---- k_pack_scan, one "warp" per read handed over
         gF[0] = gN[0] = 0;
         gF[nw + 1] = gN[nw + 1] = 0;
         gF[nw + 2] = gN[nw + 2] = 0;

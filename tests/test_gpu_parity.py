@@ -72,6 +72,43 @@ def _k31_case(seed, n_reads, read_len=150, genome=20000, sub=0.01, n_rate=0.0005
     return unitigs, reads
 
 
+def test_large_index_filter_tier(bg, monkeypatch):
+    """the two-hash Bloom filter read from global memory (what indexes beyond 131072 keys get)"""
+    monkeypatch.setenv("BGR_BLOOM", "global")
+    unitigs, reads = _k31_case(9, 4000)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(31, 2, 2, unitigs, reads, mode)
+        al = bg.Aligner(31, 2, 2)
+        al.index_unitigs(unitigs)
+        got = al.align_batch(reads, mode).as_tuples()
+        assert got == want
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        al.close()
+
+
+def test_many_tiles_and_mixed_lengths(bg):
+    """a batch spanning several tiles per CTA, with read lengths that leave tiles ragged"""
+    rng = random.Random(21)
+    unitigs, haps = S.make_graph(rng, 31, genome_len=30000, mean_unitig=70, n_variants=200)
+    reads = []
+    for ln in (150, 151, 100, 75, 250, 33, 30):
+        reads += S.make_reads(rng, haps, 3000, ln, sub_rate=0.01, n_rate=0.0002)
+    rng.shuffle(reads)
+    reads += S.make_reads(rng, haps, 40000, 150, sub_rate=0.01, n_rate=0.0)
+    want, wc = oracle_results(31, 2, 2, unitigs, reads, O.GREEDY)
+    al = bg.Aligner(31, 2, 2)
+    al.index_unitigs(unitigs)
+    got = al.align_batch(reads, O.GREEDY).as_tuples()
+    bad = [i for i in range(len(reads)) if got[i] != want[i]]
+    assert not bad, (len(bad), bad[:5], [(len(reads[i]), got[i], want[i]) for i in bad[:3]])
+    gc = al.counters()
+    for name in COUNTERS:
+        assert gc[name] == wc[name]
+    al.close()
+
+
 @pytest.mark.parametrize("m", [0, 1, 2, 5])
 def test_k31_reads_greedy_and_exhaustive(bg, m):
     unitigs, reads = _k31_case(7, 3000)
