@@ -40,6 +40,13 @@ EXHAUSTIVE = False
 WORKLOAD = "configs[1]: synthetic 5 Mbp diploid genome (SNP 1/150), k=31 unitigs, 150 bp reads at 1% substitutions, -m 2 -e 2, greedy"
 
 
+ROOFLINE_NOTE = ("achieved = SURVEY 8(d) algorithmic bytes (one 32-byte index sector per (k-1)-mer window the reference "
+                 "examines + 40 B of packed read) / measured kernel time. The kernel answers most windows from a Bloom "
+                 "filter (shared memory for small indexes, L2 for large ones) and only verifies survivors in the key "
+                 "table, so it moves far fewer DRAM bytes than that model (see traffic) and frac can exceed 1: it is "
+                 "issue bound, not HBM bound. Index blob: %.1f MB.")
+
+
 def configure(args):
     """The default run is BASELINE.json configs[1] (the configuration the metric is quoted on). The other
     configs (larger graphs, -m sweep, exhaustive mode) are selected with flags and named in `workload`."""
@@ -434,7 +441,10 @@ def run_b200_arm(args):
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("k_pack_scan_dram_bytes_per_launch")
+            # measured DRAM bytes of one 10 M-read launch of the scan kernel on a graph of this size
+            # (ncu --set full, tools/gpu_profile.sh), scaled to this run's reads per launch
+            t10 = json.load(open(prof)).get("k_scan_tiles@%d" % args.genome)
+            traffic = None if t10 is None else t10 * n_reads / 1e7
         except Exception:
             traffic = None
 
@@ -468,12 +478,11 @@ def run_b200_arm(args):
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": 1e3 * float(e2e_s.item()) / steps},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_pack_scan (pack + seed scan / index probe)", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": "k_scan_tiles (pack + seed scan / index probe)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                      "windows_per_read": w_per_read, "windows_source": w_src, "kernel_ms": scan_ms,
-                     "note": "index (%.1f MB) is L2-resident at this config: the kernel is L2/issue bound, the "
-                             "HBM fraction is reported as the contract asks" % (stats["device_bytes"] / 1e6)},
+                     "note": ROOFLINE_NOTE % (stats["device_bytes"] / 1e6)},
         "kernel_ms": {"pack_scan": scan_ms, "extend": dev_ms[1] / steps},
         "wall_ms_per_step_resident": 1e3 * (t_res1 - t_res0) / steps,
         "outcome": {"scope": "all ranks, per step", "reads": counters["reads"] // steps, "aligned": counters["aligned"] // steps,

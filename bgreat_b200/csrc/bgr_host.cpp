@@ -8,6 +8,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <deque>
+#include <thread>
 
 #include "../../include/bgreat_b200.h"
 
@@ -322,11 +324,29 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
 
 // ------------------------------------------------------------------------------ reads
 
-static inline bool acgtn_only(const std::string& r) {
-    for (char c : r)
-        if (c != 'A' && c != 'C' && c != 'T' && c != 'G' && c != 'N') return false;
-    return true;
+// Branch-free over 64-byte blocks so that the compiler vectorises the comparisons; the clones let one
+// binary use AVX2 where the host has it.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__CUDACC__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+bool acgtn_only(const char* p, size_t n) {
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        unsigned bad = 0;
+        for (size_t j = 0; j < 64; ++j) {
+            const char c = p[i + j];
+            bad |= (unsigned)!((c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'N'));
+        }
+        if (bad) return false;
+    }
+    unsigned bad = 0;
+    for (; i < n; ++i) {
+        const char c = p[i];
+        bad |= (unsigned)!((c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'N'));
+    }
+    return bad == 0;
 }
+static inline bool acgtn_only(const std::string& r) { return acgtn_only(r.data(), r.size()); }
 
 void ReadParser::next_chunk(uint32_t n, ReadBatch& out) {
     // The three strings are locals of getReads: fresh on every call (this is what makes the FASTQ
@@ -350,6 +370,7 @@ void ReadParser::next_chunk(uint32_t n, ReadBatch& out) {
                 if (c == '>') {
                     if (read.size() > 2 && acgtn_only(read) && read.size() > k_)
                         out.push(header.data(), header.size(), read.data(), read.size());
+                    read.clear();  // aligner.cpp:93: a following getline that fails must find it empty
                     break;
                 } else if (!s_.eof()) {
                     s_.getline(inter);
@@ -361,6 +382,259 @@ void ReadParser::next_chunk(uint32_t n, ReadBatch& out) {
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------ parallel reader
+
+void parallel_for(unsigned threads, const std::function<void(unsigned)>& fn) {
+    if (threads <= 1) {
+        fn(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(threads - 1);
+    for (unsigned t = 1; t < threads; ++t) th.emplace_back([&fn, t] { fn(t); });
+    fn(0);
+    for (auto& x : th) x.join();
+}
+
+namespace {
+
+struct Rec {
+    const char* h;
+    const char* s;
+    uint32_t hn, sn;
+};
+
+struct Shard {
+    std::vector<Rec> recs;
+    std::deque<std::string> joined;  // multi-line FASTA reads (stable addresses)
+    uint64_t chars = 0;
+};
+
+inline size_t line_end(const char* d, size_t pos, size_t end) {
+    const void* nl = memchr(d + pos, '\n', end - pos);
+    return nl ? (size_t)((const char*)nl - d) : end;
+}
+
+// the reference's FASTA loop (aligner.cpp:69-113) over [a, b): a is a record start, b a record start
+// or the end of the input
+void parse_fasta_range(const char* d, size_t a, size_t b, uint32_t k, Shard& out) {
+    size_t pos = a;
+    while (pos < b) {
+        const size_t h = pos;
+        size_t e = line_end(d, pos, b);
+        const size_t hn = e - h;
+        pos = e < b ? e + 1 : b;
+        if (pos >= b) break;  // header without a sequence line: the second getline fails, read stays empty
+        const size_t s = pos;
+        e = line_end(d, pos, b);
+        size_t sn = e - s;
+        pos = e < b ? e + 1 : b;
+        const char* sp = d + s;
+        if (pos < b && d[pos] != '>') {  // continuation lines: read += inter until peek() sees '>' or the end
+            out.joined.emplace_back(sp, sn);
+            std::string& j = out.joined.back();
+            while (pos < b && d[pos] != '>') {
+                e = line_end(d, pos, b);
+                j.append(d + pos, e - pos);
+                pos = e < b ? e + 1 : b;
+            }
+            sp = j.data();
+            sn = j.size();
+        }
+        if (sn > 2 && sn > k && sn <= 0xFFFFFFFFull && acgtn_only(sp, sn)) {
+            out.recs.push_back(Rec{d + h, sp, (uint32_t)hn, (uint32_t)sn});
+            out.chars += sn;
+        }
+    }
+}
+
+// whole 4-line FASTQ records in [a, b), every line newline-terminated (aligner.cpp:49-67 away from
+// the end of the stream)
+void parse_fastq_range(const char* d, size_t a, size_t b, Shard& out) {
+    size_t pos = a;
+    while (pos < b) {
+        const size_t h = pos;
+        size_t e = line_end(d, pos, b);
+        const size_t hn = e - h;
+        pos = e + 1;
+        const size_t s = pos;
+        e = line_end(d, pos, b);
+        const size_t sn = e - s;
+        pos = e + 1;
+        pos = line_end(d, pos, b) + 1;
+        pos = line_end(d, pos, b) + 1;
+        if (sn > 2 && sn <= 0xFFFFFFFFull && acgtn_only(d + s, sn)) {
+            out.recs.push_back(Rec{d + h, d + s, (uint32_t)hn, (uint32_t)sn});
+            out.chars += sn;
+        }
+    }
+}
+
+size_t count_newlines(const char* d, size_t a, size_t b) {
+    size_t c = 0;
+    for (size_t pos = a; pos < b;) {
+        const void* nl = memchr(d + pos, '\n', b - pos);
+        if (!nl) break;
+        ++c;
+        pos = (size_t)((const char*)nl - d) + 1;
+    }
+    return c;
+}
+
+// position right after the j-th newline (1-based) at or after a; j newlines must exist
+size_t after_newline(const char* d, size_t a, size_t j) {
+    size_t pos = a;
+    while (j--) pos = (size_t)((const char*)rawmemchr(d + pos, '\n') - d) + 1;
+    return pos;
+}
+
+// append the shards' records to the batch, in shard order, copying in parallel
+void gather(std::vector<Shard>& sh, unsigned threads, ParsedBatch& out) {
+    const size_t T = sh.size();
+    std::vector<size_t> r0(T + 1, 0), c0(T + 1, 0);
+    for (size_t t = 0; t < T; ++t) {
+        r0[t + 1] = r0[t] + sh[t].recs.size();
+        c0[t + 1] = c0[t] + sh[t].chars;
+    }
+    const size_t base_r = out.hdr.size(), base_c = out.seqs.n;
+    out.seqs.reserve(base_c + c0[T] + 64);
+    out.soff.reserve(base_r + r0[T] + 2);
+    out.hdr.resize(base_r + r0[T]);
+    parallel_for((unsigned)std::min<size_t>(threads, T), [&](unsigned w) {
+        for (size_t t = w; t < T; t += std::min<size_t>(threads, T)) {
+            size_t r = base_r + r0[t], c = base_c + c0[t];
+            for (const Rec& x : sh[t].recs) {
+                memcpy(out.seqs.p + c, x.s, x.sn);
+                c += x.sn;
+                out.soff.p[r + 1] = c;
+                out.hdr[r] = HdrView{x.h, x.hn};
+                ++r;
+            }
+        }
+    });
+    out.seqs.n = base_c + c0[T];
+    out.soff.n = base_r + r0[T] + 1;
+}
+
+}  // namespace
+
+ParallelReader::ParallelReader(const char* data, size_t n, uint32_t k, bool fastq, unsigned threads,
+                               size_t range_bytes, size_t min_slice)
+    : d_(data),
+      n_(n),
+      range_(range_bytes ? range_bytes : 1),
+      min_slice_(min_slice ? min_slice : 1),
+      k_(k),
+      fastq_(fastq),
+      threads_(threads ? threads : 1) {}
+
+// smallest unambiguous record start >= x (see the header), or n_
+size_t ParallelReader::fasta_boundary(size_t x) const {
+    if (x == 0) return 0;
+    size_t p = x - 1;
+    for (;;) {
+        if (p >= n_) return n_;
+        const void* nl = memchr(d_ + p, '\n', n_ - p);
+        if (!nl) return n_;
+        const size_t c = (size_t)((const char*)nl - d_) + 1;  // start of the line after that newline
+        if (c >= n_) return n_;
+        if (d_[c] == '>') {
+            // previous line = [ps, c-1)
+            const void* q = c >= 2 ? memrchr(d_, '\n', c - 1) : nullptr;
+            const size_t ps = q ? (size_t)((const char*)q - d_) + 1 : 0;
+            if (ps != 0 && d_[ps] != '>') return c;
+        }
+        p = c;
+    }
+}
+
+void ParallelReader::next(ParsedBatch& out) {
+    if (finished_) return;
+    if (fastq_) next_fastq(out);
+    else next_fasta(out);
+}
+
+void ParallelReader::next_fasta(ParsedBatch& out) {
+    const size_t a = pos_;
+    const size_t want = a + range_;
+    const size_t b = (want >= n_ || want < a) ? n_ : fasta_boundary(want);
+    const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, (b - a) / min_slice_ + 1));
+    std::vector<size_t> cut(T + 1);
+    cut[0] = a;
+    cut[T] = b;
+    parallel_for(T, [&](unsigned t) {
+        if (t) cut[t] = std::min(b, fasta_boundary(a + (size_t)((b - a) / T) * t));
+    });
+    std::vector<Shard> sh(T);
+    parallel_for(T, [&](unsigned t) {
+        if (cut[t] < cut[t + 1]) parse_fasta_range(d_, cut[t], cut[t + 1], k_, sh[t]);
+    });
+    gather(sh, T, out);
+    pos_ = b;
+    if (pos_ >= n_) finished_ = true;
+}
+
+void ParallelReader::next_fastq(ParsedBatch& out) {
+    const size_t a = pos_;
+    const size_t CH = 10000;  // reads per getReads call (alignerGreedy.cpp:376)
+    size_t win = range_;
+    for (;;) {
+        const bool final = a + win >= n_ || a + win < a;
+        const size_t b = final ? n_ : a + win;
+        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, (b - a) / min_slice_ + 1));
+        // newline counts per slice
+        std::vector<size_t> lo(T + 1), cnt(T + 1, 0);
+        for (unsigned t = 0; t <= T; ++t) lo[t] = a + (size_t)((b - a) / T) * t;
+        lo[T] = b;
+        parallel_for(T, [&](unsigned t) { cnt[t + 1] = count_newlines(d_, lo[t], lo[t + 1]); });
+        for (unsigned t = 0; t < T; ++t) cnt[t + 1] += cnt[t];  // cnt[t] = newlines before slice t
+        const size_t q = cnt[T] / 4;  // whole newline-terminated records in [a, b)
+        size_t P;                     // records parsed here by the workers
+        if (final) P = q ? ((q - 1) / CH) * CH : 0;  // the last <= 2*CH records go to the sequential parser
+        else P = (q / CH) * CH;
+        if (!final && P == 0) {  // not even one getReads chunk in the window: look further
+            win *= 2;
+            continue;
+        }
+        // start of record r = right after newline number 4r
+        auto record_start = [&](size_t r) -> size_t {
+            if (r == 0) return a;
+            const size_t j = 4 * r;  // 1-based newline number
+            unsigned t = (unsigned)(std::upper_bound(cnt.begin(), cnt.end(), j - 1) - cnt.begin()) - 1;  // cnt[t] < j <= cnt[t+1]
+            return after_newline(d_, lo[t], j - cnt[t]);
+        };
+        std::vector<size_t> cut(T + 1);
+        parallel_for(T, [&](unsigned t) { cut[t] = record_start(P / T * t); });
+        cut[T] = record_start(P);
+        std::vector<Shard> sh(T);
+        parallel_for(T, [&](unsigned t) {
+            if (cut[t] < cut[t + 1]) parse_fastq_range(d_, cut[t], cut[t + 1], sh[t]);
+        });
+        gather(sh, T, out);
+        pos_ = cut[T];
+        if (final) {
+            // the end of the stream, exactly as the reference sees it
+            ReadParser rp(d_ + pos_, n_ - pos_, k_, true);
+            ReadBatch tail;
+            while (!rp.done()) rp.next_chunk((uint32_t)CH, tail);
+            const size_t nt = tail.size();
+            out.arena.assign(tail.headers.p, tail.headers.p + tail.headers.n);
+            out.seqs.reserve(out.seqs.n + tail.seqs.n + 64);
+            out.soff.reserve(out.soff.n + nt + 1);
+            for (size_t i = 0; i < nt; ++i) {
+                const size_t sn = tail.soff.p[i + 1] - tail.soff.p[i];
+                memcpy(out.seqs.p + out.seqs.n, tail.seqs.p + tail.soff.p[i], sn);
+                out.seqs.n += sn;
+                out.soff.p[out.soff.n++] = out.seqs.n;
+                out.hdr.push_back(HdrView{out.arena.data() + tail.hoff.p[i], (uint32_t)(tail.hoff.p[i + 1] - tail.hoff.p[i])});
+            }
+            pos_ = n_;
+            finished_ = true;
+        }
+        return;
     }
 }
 

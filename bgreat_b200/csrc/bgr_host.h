@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -132,6 +133,74 @@ class ReadParser {
     LineStream s_;
     uint32_t k_;
     bool fastq_;
+};
+
+// ------------------------------------------------------------------------------ parallel reader
+//
+// Same records as ReadParser (= the reference's getReads driven in 10000-read chunks), produced by
+// `threads` workers over ranges of the input text. SURVEY 8(f) rank 1: the parser must keep up with
+// the GPU, which a single getline loop cannot.
+//
+//   FASTA  the reference's state machine (header line, first sequence line, continuation lines until
+//          a line that starts with '>') does not depend on the chunking of getReads, so the text is cut
+//          at record starts that are unambiguous -- a line starting with '>' whose previous line does not
+//          (and is not the first line of the file: every other header is reached through peek()=='>').
+//   FASTQ  records are 4 lines whatever their content: newlines are counted in parallel and the text is
+//          cut at line numbers that are multiples of 4 x 10000 (getReads boundaries). What depends on
+//          the stream state at the end of the file (partial last record, phantom duplicate of the last
+//          read after a trailing newline, aligner.cpp:52-53) is left to the sequential ReadParser,
+//          which runs over the last <= 20000 records only.
+struct HdrView {
+    const char* p;
+    uint32_t n;
+};
+
+struct ParsedBatch {
+    PodBuf<char> seqs;      // sequences, concatenated (allocator: pinned host memory in the CLI)
+    PodBuf<uint64_t> soff;  // n+1 offsets into seqs
+    std::vector<HdrView> hdr;  // header lines: views into the input text, or into `arena`
+    std::vector<char> arena;   // headers that do not live in the input text (sequential tail)
+    ParsedBatch() { clear(); }
+    void set_allocator(AllocFn a, FreeFn f) {
+        seqs.alloc = soff.alloc = a;
+        seqs.dealloc = soff.dealloc = f;
+    }
+    size_t size() const { return hdr.size(); }
+    void clear() {
+        seqs.n = soff.n = 0;
+        soff.push(0);
+        hdr.clear();
+        arena.clear();
+    }
+};
+
+// run fn(t) for t in [0, threads) on `threads` threads (the caller is one of them)
+void parallel_for(unsigned threads, const std::function<void(unsigned)>& fn);
+
+// every character one of A C G T N (aligner.cpp:55-60)
+bool acgtn_only(const char* p, size_t n);
+
+class ParallelReader {
+   public:
+    // range_bytes: text handed out per next() call (a batch); FASTQ ranges are rounded to whole
+    // getReads chunks and grow when a chunk does not fit
+    // min_slice: least text per worker (tests set it to 1 to cut tiny inputs everywhere)
+    ParallelReader(const char* data, size_t n, uint32_t k, bool fastq, unsigned threads, size_t range_bytes,
+                   size_t min_slice = 4096);
+    bool done() const { return finished_; }
+    // appends the records of the next range to `out` (which the caller has cleared)
+    void next(ParsedBatch& out);
+
+   private:
+    void next_fasta(ParsedBatch& out);
+    void next_fastq(ParsedBatch& out);
+    size_t fasta_boundary(size_t x) const;
+
+    const char* d_;
+    size_t n_, pos_ = 0, range_, min_slice_;
+    uint32_t k_;
+    bool fastq_, finished_ = false;
+    unsigned threads_;
 };
 
 }  // namespace bgr

@@ -276,6 +276,27 @@ extern "C" long emu_parse_reads(const char* path, uint32_t k, int fastq, uint32_
     return (long)rb.size();
 }
 
+// the parallel reader (bgr_host.cpp ParallelReader) over the whole file, range by range
+extern "C" long emu_parse_reads_parallel(const char* path, uint32_t k, int fastq, uint32_t threads, uint64_t range_bytes,
+                                         uint64_t min_slice, char** headers, uint64_t** hoff, char** seqs, uint64_t** soff) {
+    MappedFile mf;
+    if (!mf.open(path)) return -1;
+    ParallelReader pr(mf.data, mf.size, k, fastq != 0, threads, (size_t)range_bytes, (size_t)min_slice);
+    ReadBatch rb;
+    ParsedBatch pb;
+    do {
+        pb.clear();
+        pr.next(pb);
+        for (size_t i = 0; i < pb.size(); ++i)
+            rb.push(pb.hdr[i].p, pb.hdr[i].n, pb.seqs.p + pb.soff.p[i], pb.soff.p[i + 1] - pb.soff.p[i]);
+    } while (!pr.done());
+    *headers = dup_bytes(rb.headers.p, rb.headers.n);
+    *seqs = dup_bytes(rb.seqs.p, rb.seqs.n);
+    *hoff = dup_u64(rb.hoff.p, rb.hoff.n);
+    *soff = dup_u64(rb.soff.p, rb.soff.n);
+    return (long)rb.size();
+}
+
 extern "C" long emu_load_unitigs(const char* path, uint32_t k, char** seqs, uint64_t** off, int* opened) {
     std::string s;
     std::vector<uint64_t> o;

@@ -70,13 +70,19 @@ def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64):
     return out, dict(zip(names, [int(c) for c in counters[:6]])), flags, bool(ovf.value)
 
 
-def parse_reads(path, k, fastq=False, chunk=10000):
-    """The PRODUCT's read parser (bgr_host.cpp ReadParser) -> [(header, read)] or None."""
+def parse_reads(path, k, fastq=False, chunk=10000, threads=0, range_bytes=1 << 20, min_slice=4096):
+    """The PRODUCT's read parser -> [(header, read)] or None. threads == 0: the sequential ReadParser
+    (bgr_host.cpp) driven in `chunk`-read getReads calls; threads > 0: the ParallelReader the CLI uses."""
     L = lib()
     L.emu_parse_reads.restype = C.c_long
+    L.emu_parse_reads_parallel.restype = C.c_long
     ph, pho, ps, pso = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-    n = L.emu_parse_reads(os.fsencode(path), C.c_uint32(k), C.c_int(int(fastq)), C.c_uint32(chunk), C.byref(ph),
-                          C.byref(pho), C.byref(ps), C.byref(pso))
+    if threads:
+        n = L.emu_parse_reads_parallel(os.fsencode(path), C.c_uint32(k), C.c_int(int(fastq)), C.c_uint32(threads),
+                                       C.c_uint64(range_bytes), C.c_uint64(min_slice), C.byref(ph), C.byref(pho), C.byref(ps), C.byref(pso))
+    else:
+        n = L.emu_parse_reads(os.fsencode(path), C.c_uint32(k), C.c_int(int(fastq)), C.c_uint32(chunk), C.byref(ph),
+                              C.byref(pho), C.byref(ps), C.byref(pso))
     if n < 0:
         return None
     ho = C.cast(pho, C.POINTER(C.c_uint64))

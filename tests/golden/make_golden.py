@@ -170,9 +170,38 @@ def parse_cases():
     return cases
 
 
+def parse_fuzz_cases():
+    """Fuzzed small texts through the reference's getReads (chunk 10000, what the CLI uses)."""
+    import parse_gen as G
+    cases = []
+    for seed in range(150):
+        for fastq in (False, True):
+            cases.append(parse_case("fuzz_%s_%d" % ("fq" if fastq else "fa", seed), G.fuzz_text(seed, fastq), 4, fastq, 10000))
+    return cases
+
+
+def parse_big_cases():
+    """Many-chunk files: only a digest of the reference's records is stored (the text is regenerated)."""
+    import parse_gen as G
+    cases = []
+    for name in G.BIG_CASES:
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "reads")
+            with open(p, "w", newline="") as f:
+                f.write(G.big_text(name))
+            recs = O.ref_harness_parse(p, 4, name.startswith("fq"), 10000, d)
+        cases.append(dict(name=name, k=4, fastq=int(name.startswith("fq")), n_records=len(recs), sha256=G.digest(recs),
+                          last=[[h.decode("latin1"), r.decode("latin1")] for h, r in recs[-2:]]))
+    return cases
+
+
 def main():
     if not O.have_ref():
         O.build(with_ref=True)
+    if "--parse-extra" in sys.argv:  # only the parser fixtures added for the parallel reader
+        json.dump(parse_fuzz_cases(), open(os.path.join(HERE, "parse_fuzz_cases.json"), "w"), indent=0, separators=(",", ":"))
+        json.dump(parse_big_cases(), open(os.path.join(HERE, "parse_big_cases.json"), "w"), indent=0, separators=(",", ":"))
+        return
     hc = known_answer_cases()
     for seed in range(40):
         c = S.fuzz_case(seed)

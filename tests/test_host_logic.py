@@ -49,3 +49,54 @@ def test_unitig_loader_follows_the_reference_loop(content, k, want, tmp_path):
 def test_unitig_loader_missing_file():
     opened, got = E.load_unitigs("/nonexistent/u.fa", 4)
     assert not opened and got == []
+
+
+# ---- the parallel reader the CLI uses (bgr_host.cpp ParallelReader): same records as getReads driven in
+# 10000-read chunks, whatever the number of workers and wherever the text is cut
+
+import parse_gen as G
+
+FUZZ = json.load(open(os.path.join(GOLDEN, "parse_fuzz_cases.json")))
+BIG = json.load(open(os.path.join(GOLDEN, "parse_big_cases.json")))
+SPLITS = [(1, 1 << 20, 4096), (3, 7, 1), (4, 64, 1), (8, 1 << 20, 1), (2, 33, 5)]
+
+
+def _write(tmp_path, content):
+    p = tmp_path / "reads"
+    with open(p, "w", newline="") as f:
+        f.write(content)
+    return str(p)
+
+
+@pytest.mark.parametrize("case", [c for c in PARSE if c["chunk"] == 10000 or not c["fastq"]],
+                         ids=lambda c: c["name"])
+def test_parallel_reader_on_the_getReads_goldens(case, tmp_path):
+    p = _write(tmp_path, case["content"])
+    for threads, rng, ms in SPLITS:
+        got = E.parse_reads(p, case["k"], bool(case["fastq"]), threads=threads, range_bytes=rng, min_slice=ms)
+        assert [[h.decode("latin1"), r.decode("latin1")] for h, r in got] == case["records"], (threads, rng, ms)
+
+
+@pytest.mark.parametrize("case", FUZZ, ids=lambda c: c["name"])
+def test_parsers_on_fuzzed_texts(case, tmp_path):
+    """golden = the reference's getReads on the same text"""
+    p = _write(tmp_path, case["content"])
+    want = case["records"]
+    got = E.parse_reads(p, case["k"], bool(case["fastq"]))
+    assert [[h.decode("latin1"), r.decode("latin1")] for h, r in got] == want
+    for threads, rng, ms in SPLITS:
+        got = E.parse_reads(p, case["k"], bool(case["fastq"]), threads=threads, range_bytes=rng, min_slice=ms)
+        assert [[h.decode("latin1"), r.decode("latin1")] for h, r in got] == want, (threads, rng, ms)
+
+
+@pytest.mark.parametrize("case", BIG, ids=lambda c: c["name"])
+def test_parsers_on_many_chunk_files(case, tmp_path):
+    """> 10000 records: getReads chunk boundaries, the FASTQ tail rules; golden = digest of the reference's records"""
+    p = _write(tmp_path, G.big_text(case["name"]))
+    fastq = bool(case["fastq"])
+    for kw in (dict(), dict(threads=1, range_bytes=1 << 30), dict(threads=5, range_bytes=100_000, min_slice=1),
+               dict(threads=16, range_bytes=1 << 20), dict(threads=3, range_bytes=1000, min_slice=100)):
+        got = E.parse_reads(p, case["k"], fastq, **kw)
+        assert len(got) == case["n_records"], kw
+        assert [[h.decode("latin1"), r.decode("latin1")] for h, r in got[-2:]] == case["last"], kw
+        assert G.digest(got) == case["sha256"], kw

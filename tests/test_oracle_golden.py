@@ -10,7 +10,7 @@ from oracle import oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HARNESS = json.load(open(os.path.join(GOLDEN, "harness_cases.json")))
 CLI = json.load(open(os.path.join(GOLDEN, "cli_cases.json")))
-PARSE = json.load(open(os.path.join(GOLDEN, "parse_cases.json")))
+PARSE = json.load(open(os.path.join(GOLDEN, "parse_cases.json"))) + json.load(open(os.path.join(GOLDEN, "parse_fuzz_cases.json")))
 MODES = {"greedy": O.GREEDY, "exhaustive": O.EXHAUSTIVE, "greedy_path": O.GREEDY_PATH,
          "exhaustive_path": O.EXHAUSTIVE_PATH}
 
