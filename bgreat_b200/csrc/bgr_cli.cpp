@@ -2,25 +2,30 @@
 // with the mapping done on the GPU through the C ABI (include/bgreat_b200.h).
 //
 // Same getopt string, same defaults, same stdout lines, same `paths` / `notAligned.fa` record formats
-// (reference alignerGreedy.cpp:393-428, aligner.cpp:588-609). Host pipeline: one parser thread
-// (the reference's getReads semantics, exactly) -> GPU thread (double-buffered batch slots, pinned
-// staging) -> writer (formats on -t threads, writes in file order).
+// (reference alignerGreedy.cpp:393-428, aligner.cpp:588-609). Host
+// pipeline: reader (ParallelReader: -t workers cut and parse ranges of the memory-mapped input with the
+// reference's getReads semantics, exactly) -> GPU thread (double-buffered batch slots, pinned staging) ->
+// writer (-t workers format straight into the memory-mapped output files, in file order).
 //
 // Deliberate, documented differences (DESIGN.md "CLI"):
 //   * a read file that cannot be opened is an error (the reference spins forever);
 //   * -o FILE writes the reads without any overlap to FILE (the reference accepts -o and ignores it);
 //   * -b writes its paths and unmapped reads (the reference computes them and writes nothing);
 //   * -c / -G (and -i together with -b) are not part of this path and are refused.
+#include <fcntl.h>
 #include <getopt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <iostream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -44,14 +49,13 @@ static void* pinned_alloc(size_t bytes) {
 static void pinned_free(void* p) { bgr_host_free(p); }
 
 struct Batch {
-    ReadBatch rb;
+    ParsedBatch pb;
     PodBuf<bgr_result> res;
     PodBuf<int32_t> pool;
     uint64_t pool_used = 0;
     int slot = -1;
-    bool last_of_file = false;
     Batch() {
-        rb.set_allocator(pinned_alloc, pinned_free);
+        pb.set_allocator(pinned_alloc, pinned_free);
         res.alloc = pool.alloc = pinned_alloc;
         res.dealloc = pool.dealloc = pinned_free;
     }
@@ -98,48 +102,141 @@ static inline char* put_int(char* p, int32_t v) {
     return p;
 }
 
-struct Outputs {
-    FILE* paths = nullptr;
-    FILE* not_aligned = nullptr;
-    FILE* no_overlap = nullptr;
+static inline unsigned int_chars(int32_t v) {
+    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    unsigned n = v < 0 ? 2 : 1;
+    while (u >= 10) {
+        u /= 10;
+        ++n;
+    }
+    return n;
+}
+
+// One output file, written batch by batch. A regular file is extended and memory-mapped per batch so
+// that the workers format straight into the page cache in parallel (concurrent write()s to one file
+// serialise on the inode lock); anything else (pipe, /dev/null, BGR_OUT=write) gets plain write()s.
+struct OutFile {
+    int fd = -1;
+    bool mappable = false;
+    uint64_t pos = 0;
+    // current batch
+    char* map = nullptr;
+    size_t map_len = 0;
+    char* base = nullptr;  // where this batch's bytes start (inside map, or in `stage`)
+    std::vector<char> stage;
+
+    bool open(const std::string& path) {
+        bool rw = true;
+        fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);  // a shared mapping needs read access too
+        if (fd < 0) {
+            rw = false;
+            fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        }
+        if (fd < 0) return false;
+        struct stat st;
+        const char* e = getenv("BGR_OUT");
+        mappable = rw && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && !(e && !strcmp(e, "write"));
+        return true;
+    }
+    bool begin(size_t bytes) {
+        base = nullptr;
+        if (bytes == 0) return true;
+        if (fd >= 0 && mappable) {
+            const uint64_t page = 4096, lo = pos & ~(page - 1);
+            if (ftruncate(fd, (off_t)(pos + bytes)) == 0) {
+                map_len = (size_t)(pos + bytes - lo);
+                void* m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)lo);
+                if (m != MAP_FAILED) {
+                    map = (char*)m;
+                    base = map + (pos - lo);
+                    return true;
+                }
+            }
+            mappable = false;  // fall back to write() from here on
+            if (ftruncate(fd, (off_t)pos) != 0 || lseek(fd, (off_t)pos, SEEK_SET) < 0) return false;
+        }
+        stage.resize(bytes);  // also the sink when the file could not be opened
+        base = stage.data();
+        return true;
+    }
+    bool end(size_t bytes) {
+        if (fd < 0 || bytes == 0) return true;
+        bool ok = true;
+        if (map) {
+            munmap(map, map_len);
+            map = nullptr;
+        } else {
+            const char* p = stage.data();
+            size_t left = bytes;
+            while (left) {
+                ssize_t w = ::write(fd, p, left);
+                if (w <= 0) {
+                    ok = false;
+                    break;
+                }
+                p += w;
+                left -= (size_t)w;
+            }
+        }
+        pos += bytes;
+        return ok;
+    }
+    void close() {
+        if (fd >= 0) ::close(fd);
+        fd = -1;
+    }
 };
 
-// header\npath\n for mapped reads (printPath, aligner.cpp:600-609), header\nread\n otherwise
-static void format_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, std::string& paths,
-                         std::string& na, std::string& nov) {
+enum { OUT_PATHS = 0, OUT_NOT_ALIGNED = 1, OUT_NO_OVERLAP = 2 };
+
+// which file a read goes to (alignerGreedy.cpp:393-428; -o: see the header)
+static inline int out_of(uint32_t flags, bool split_no_overlap) {
+    if (flags & BGR_F_MAPPED) return OUT_PATHS;
+    return (split_no_overlap && !(flags & BGR_F_OVERLAP_FOUND)) ? OUT_NO_OVERLAP : OUT_NOT_ALIGNED;
+}
+
+// bytes reads [lo, hi) of the batch put into each of the three files
+static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, size_t sz[3]) {
+    sz[0] = sz[1] = sz[2] = 0;
     for (size_t i = lo; i < hi; ++i) {
-        const char* h = b.rb.headers.p + b.rb.hoff.p[i];
-        size_t hn = b.rb.hoff.p[i + 1] - b.rb.hoff.p[i];
         const bgr_result r = b.res.p[i];
-        uint32_t flags = BGR_RESULT_FLAGS(r), len = BGR_RESULT_LEN(r);
-        if (flags & BGR_F_MAPPED) {
-            size_t at = paths.size();
-            paths.resize(at + hn + 2 + 12 * (size_t)len);
-            char* p = &paths[at];
-            memcpy(p, h, hn);
-            p += hn;
-            *p++ = '\n';
+        const uint32_t flags = BGR_RESULT_FLAGS(r), len = BGR_RESULT_LEN(r);
+        const int o = out_of(flags, split_no_overlap);
+        size_t n = b.pb.hdr.p[i].n + 2;
+        if (o == OUT_PATHS) {
+            const int32_t* ids = b.pool.p + r.path_off;
+            for (uint32_t j = 0; j < len; ++j) n += int_chars(ids[j]) + 1;
+        } else {
+            n += b.pb.soff.p[i + 1] - b.pb.soff.p[i];
+        }
+        sz[o] += n;
+    }
+}
+
+// header\npath\n for mapped reads (printPath, aligner.cpp:600-609), header\nread\n otherwise
+static void format_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, char* dst[3]) {
+    for (size_t i = lo; i < hi; ++i) {
+        const bgr_result r = b.res.p[i];
+        const uint32_t flags = BGR_RESULT_FLAGS(r), len = BGR_RESULT_LEN(r);
+        const int o = out_of(flags, split_no_overlap);
+        char* p = dst[o];
+        memcpy(p, b.pb.hdr.p[i].p, b.pb.hdr.p[i].n);
+        p += b.pb.hdr.p[i].n;
+        *p++ = '\n';
+        if (o == OUT_PATHS) {
             const int32_t* ids = b.pool.p + r.path_off;
             for (uint32_t j = 0; j < len; ++j) {
                 p = put_int(p, ids[j]);
                 *p++ = '.';
             }
-            *p++ = '\n';
-            paths.resize((size_t)(p - paths.data()));
         } else {
-            std::string& o = (split_no_overlap && !(flags & BGR_F_OVERLAP_FOUND)) ? nov : na;
-            const char* s = b.rb.seqs.p + b.rb.soff.p[i];
-            size_t sn = b.rb.soff.p[i + 1] - b.rb.soff.p[i];
-            o.append(h, hn);
-            o.push_back('\n');
-            o.append(s, sn);
-            o.push_back('\n');
+            const size_t sn = b.pb.soff.p[i + 1] - b.pb.soff.p[i];
+            memcpy(p, b.pb.seqs.p + b.pb.soff.p[i], sn);
+            p += sn;
         }
+        *p++ = '\n';
+        dst[o] = p;
     }
-}
-
-static void write_all(FILE* f, const std::string& s) {
-    if (f && !s.empty()) fwrite(s.data(), 1, s.size(), f);
 }
 
 static void usage() {
@@ -197,6 +294,14 @@ int main(int argc, char** argv) {
     unsigned threads = (unsigned char)o.threads;
     if (threads == 0) threads = 1;
 
+    // BGR_VERBOSE=1: phase timings on stderr (not part of the reference's output)
+    const bool verbose = getenv("BGR_VERBOSE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (verbose)
+            fprintf(stderr, "[bgreat] %-28s t=%.3f s\n", what,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    };
     const int n_slots = 2;
     bgr_ctx* ctx = nullptr;
     if (bgr_ctx_create(0, n_slots, &ctx) != BGR_OK) {
@@ -204,11 +309,12 @@ int main(int argc, char** argv) {
         return 1;
     }
 
+    lap("context created");
     // Aligner ctor opens the outputs first (aligner.h:85-86)
-    Outputs out;
-    out.paths = fopen(o.path_file.c_str(), "wb");
-    out.not_aligned = fopen(o.not_aligned_file.c_str(), "wb");
-    if (o.have_o) out.no_overlap = fopen(o.no_overlap_file.c_str(), "wb");
+    OutFile out[3];
+    out[OUT_PATHS].open(o.path_file);
+    out[OUT_NOT_ALIGNED].open(o.not_aligned_file);
+    if (o.have_o) out[OUT_NO_OVERLAP].open(o.no_overlap_file);
 
     // ---- indexUnitigs (aligner.cpp:537-547)
     auto t0 = std::chrono::system_clock::now();
@@ -221,6 +327,7 @@ int main(int argc, char** argv) {
     std::cout << "Indexing in seconds : " << std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count()
               << std::endl;
 
+    lap("index built");
     // ---- alignAll (aligner.cpp:550-597)
     auto start = std::chrono::system_clock::now();
     bgr_params params;
@@ -233,8 +340,13 @@ int main(int argc, char** argv) {
     std::vector<Batch> batches(n_batches);
     Queue<Batch*> free_q, parsed_q, done_q;
     for (auto& b : batches) free_q.push(&b);
-    const size_t max_reads = 1u << 20, max_chars = 160u << 20;
+    // text per batch: about 400 k reads of 150 bases; BGR_RANGE_BYTES overrides (tests cut small files)
+    size_t range_bytes = 64u << 20;
+    if (const char* e = getenv("BGR_RANGE_BYTES")) range_bytes = std::max<size_t>(1, strtoull(e, nullptr, 10));
     bool io_error = false;
+    double parse_s = 0, gpu_wait_s = 0, write_s = 0;  // busy time per stage (BGR_VERBOSE)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(now() - t).count(); };
 
     // files of the comma separated list, in order (aligner.cpp:554-576)
     std::vector<std::string> files;
@@ -247,28 +359,28 @@ int main(int argc, char** argv) {
             }
         files.push_back(o.reads.substr(last));
     }
+    // the header lines of a batch are views into the mapped input: every file stays mapped until the end
+    std::vector<std::unique_ptr<MappedFile>> mapped;
 
     std::thread parser([&] {
         for (const std::string& file : files) {
-            MappedFile mf;
+            mapped.emplace_back(new MappedFile());
+            MappedFile& mf = *mapped.back();
             if (!mf.open(file.c_str())) {
                 fprintf(stderr, "bgreat: cannot open read file %s\n", file.c_str());
                 io_error = true;
                 continue;
             }
-            ReadParser rp(mf.data, mf.size, (uint32_t)o.k, o.fastq);
             // alignPartGreedy's loop (alignerGreedy.cpp:372-377): getReads(10000) until eof
-            Batch* b = free_q.pop();
-            b->rb.clear();
-            while (!rp.done()) {
-                rp.next_chunk(10000, b->rb);
-                if (b->rb.size() >= max_reads || b->rb.seqs.n >= max_chars) {
-                    parsed_q.push(b);
-                    b = free_q.pop();
-                    b->rb.clear();
-                }
-            }
-            parsed_q.push(b);  // possibly empty: still flows through so that order is kept
+            ParallelReader pr(mf.data, mf.size, (uint32_t)o.k, o.fastq, threads, range_bytes);
+            do {
+                Batch* b = free_q.pop();
+                const auto t = now();
+                b->pb.clear();
+                pr.next(b->pb);
+                parse_s += since(t);
+                parsed_q.push(b);  // possibly empty: still flows through so that order is kept
+            } while (!pr.done());
         }
         parsed_q.push(nullptr);
     });
@@ -279,6 +391,7 @@ int main(int argc, char** argv) {
         bool input_done = false;
         auto finish = [&](Batch* b) {
             uint64_t used = 0;
+            const auto t = now();
             int r = bgr_slot_wait(ctx, b->slot, &used);
             if (r == BGR_ERR_LIMIT) {  // pool buffer too small: come back with a bigger one
                 b->pool.reserve(used + 1024);
@@ -290,6 +403,7 @@ int main(int argc, char** argv) {
                 exit(1);
             }
             b->pool_used = used;
+            gpu_wait_s += since(t);
             done_q.push(b);
         };
         while (!input_done || !inflight.empty()) {
@@ -301,10 +415,10 @@ int main(int argc, char** argv) {
                 }
                 b->slot = next_slot;
                 next_slot = (next_slot + 1) % n_slots;
-                size_t n = b->rb.size();
+                size_t n = b->pb.size();
                 b->res.reserve(n + 1);
                 b->pool.reserve(n * 8 + 1024);
-                int r = bgr_slot_upload(ctx, b->slot, b->rb.seqs.p, b->rb.soff.p, (uint32_t)n);
+                int r = bgr_slot_upload(ctx, b->slot, b->pb.seqs.p, b->pb.soff.p, (uint32_t)n);
                 if (r == BGR_OK) r = bgr_slot_run(ctx, b->slot, &params);
                 if (r == BGR_OK) r = bgr_slot_download(ctx, b->slot, b->res.p, b->pool.p, b->pool.cap);
                 if (r != BGR_OK) {
@@ -321,34 +435,43 @@ int main(int argc, char** argv) {
         done_q.push(nullptr);
     });
 
-    // writer: this thread
+    // writer: this thread and its workers
+    bool write_error = false;
     {
-        std::vector<std::string> sp(threads), sn(threads), so(threads);
+        std::vector<size_t> sz(3 * (size_t)threads), at(3 * (size_t)threads);
+        WorkerPool pool(threads - 1);
         for (;;) {
             Batch* b = done_q.pop();
             if (!b) break;
-            size_t n = b->rb.size();
-            unsigned T = (unsigned)std::min<size_t>(threads, n / 4096 + 1);
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < T; ++t) {
-                sp[t].clear();
-                sn[t].clear();
-                so[t].clear();
-                size_t lo = n * t / T, hi = n * (t + 1) / T;
-                if (t + 1 == T) format_range(*b, lo, hi, o.have_o, sp[t], sn[t], so[t]);
-                else th.emplace_back([&, t, lo, hi] { format_range(*b, lo, hi, o.have_o, sp[t], sn[t], so[t]); });
-            }
-            for (auto& x : th) x.join();
-            for (unsigned t = 0; t < T; ++t) {
-                write_all(out.paths, sp[t]);
-                write_all(out.not_aligned, sn[t]);
-                write_all(out.no_overlap, so[t]);
-            }
+            const auto t0w = now();
+            const size_t n = b->pb.size();
+            const unsigned T = (unsigned)std::min<size_t>(threads, n / 4096 + 1);
+            pool.run(T, [&](unsigned t) { measure_range(*b, n * t / T, n * (t + 1) / T, o.have_o, &sz[3 * t]); });
+            size_t total[3] = {0, 0, 0};
+            for (unsigned t = 0; t < T; ++t)
+                for (int f = 0; f < 3; ++f) {
+                    at[3 * t + f] = total[f];
+                    total[f] += sz[3 * t + f];
+                }
+            for (int f = 0; f < 3; ++f)
+                if (!out[f].begin(total[f])) write_error = true;
+            pool.run(T, [&](unsigned t) {
+                char* dst[3];
+                for (int f = 0; f < 3; ++f) dst[f] = out[f].base ? out[f].base + at[3 * t + f] : nullptr;
+                format_range(*b, n * t / T, n * (t + 1) / T, o.have_o, dst);
+            });
+            for (int f = 0; f < 3; ++f)
+                if (!out[f].end(total[f])) write_error = true;
+            write_s += since(t0w);
             free_q.push(b);
         }
     }
     parser.join();
     gpu.join();
+    lap("mapping done");
+    if (verbose)
+        fprintf(stderr, "[bgreat] busy: reader %.3f s, waiting for the GPU %.3f s, writer %.3f s\n", parse_s, gpu_wait_s,
+                write_s);
     for (const std::string& file : files) std::cout << file << std::endl;
 
     uint64_t cnt[BGR_C_COUNT];
@@ -370,10 +493,12 @@ int main(int argc, char** argv) {
     std::cout << "Reads/seconds : " << readNumber / (secs + 1) << std::endl;
     std::cout << "Mapping in seconds : " << secs << std::endl;
 
-    if (out.paths) fclose(out.paths);
-    if (out.not_aligned) fclose(out.not_aligned);
-    if (out.no_overlap) fclose(out.no_overlap);
+    for (int f = 0; f < 3; ++f) out[f].close();
+    if (write_error) fprintf(stderr, "bgreat: error while writing the output files\n");
+    lap("outputs closed");
     batches.clear();
+    mapped.clear();
     bgr_ctx_destroy(ctx);
-    return io_error ? 1 : 0;
+    lap("context destroyed");
+    return (io_error || write_error) ? 1 : 0;
 }

@@ -7,8 +7,14 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include <algorithm>
+#include <condition_variable>
 #include <deque>
+#include <mutex>
 #include <thread>
 
 #include "../../include/bgreat_b200.h"
@@ -324,27 +330,66 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
 
 // ------------------------------------------------------------------------------ reads
 
-// Branch-free over 64-byte blocks so that the compiler vectorises the comparisons; the clones let one
-// binary use AVX2 where the host has it.
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__CUDACC__)
-__attribute__((target_clones("avx2", "default")))
-#endif
-bool acgtn_only(const char* p, size_t n) {
-    size_t i = 0;
-    for (; i + 64 <= n; i += 64) {
-        unsigned bad = 0;
-        for (size_t j = 0; j < 64; ++j) {
-            const char c = p[i + j];
-            bad |= (unsigned)!((c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'N'));
-        }
-        if (bad) return false;
+// Read validation touches every input byte once: 32 bytes per step with AVX2 where the host has it
+// (checked at run time: the binary is built on another machine), else a table walk.
+namespace {
+struct AcgtnTable {
+    unsigned char bad[256];
+    AcgtnTable() {
+        memset(bad, 1, sizeof bad);
+        bad[(unsigned char)'A'] = bad[(unsigned char)'C'] = bad[(unsigned char)'G'] = bad[(unsigned char)'T'] =
+            bad[(unsigned char)'N'] = 0;
     }
+};
+const AcgtnTable g_acgtn;
+
+bool acgtn_only_scalar(const char* p, size_t n) {
+    const unsigned char* u = (const unsigned char*)p;
     unsigned bad = 0;
-    for (; i < n; ++i) {
-        const char c = p[i];
-        bad |= (unsigned)!((c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'N'));
-    }
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        bad |= g_acgtn.bad[u[i]] | g_acgtn.bad[u[i + 1]] | g_acgtn.bad[u[i + 2]] | g_acgtn.bad[u[i + 3]] |
+               g_acgtn.bad[u[i + 4]] | g_acgtn.bad[u[i + 5]] | g_acgtn.bad[u[i + 6]] | g_acgtn.bad[u[i + 7]];
+    for (; i < n; ++i) bad |= g_acgtn.bad[u[i]];
     return bad == 0;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define BGR_HAVE_AVX2_PATH 1
+__attribute__((target("avx2"))) bool acgtn_only_avx2(const char* p, size_t n) {
+    const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'),
+                  cT = _mm256_set1_epi8('T'), cN = _mm256_set1_epi8('N');
+    __m256i all = _mm256_set1_epi8((char)0xFF);
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i x = _mm256_loadu_si256((const __m256i*)(p + i));
+        const __m256i ok = _mm256_or_si256(
+            _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cA), _mm256_cmpeq_epi8(x, cC)),
+                            _mm256_or_si256(_mm256_cmpeq_epi8(x, cG), _mm256_cmpeq_epi8(x, cT))),
+            _mm256_cmpeq_epi8(x, cN));
+        all = _mm256_and_si256(all, ok);
+    }
+    if (i < n && n >= 32) {  // the last, overlapping 32 bytes
+        const __m256i x = _mm256_loadu_si256((const __m256i*)(p + n - 32));
+        const __m256i ok = _mm256_or_si256(
+            _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cA), _mm256_cmpeq_epi8(x, cC)),
+                            _mm256_or_si256(_mm256_cmpeq_epi8(x, cG), _mm256_cmpeq_epi8(x, cT))),
+            _mm256_cmpeq_epi8(x, cN));
+        all = _mm256_and_si256(all, ok);
+        i = n;
+    }
+    if (_mm256_movemask_epi8(all) != -1) return false;
+    return acgtn_only_scalar(p + i, n - i);
+}
+#endif
+}  // namespace
+
+bool acgtn_only(const char* p, size_t n) {
+#ifdef BGR_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return acgtn_only_avx2(p, n);
+#endif
+    return acgtn_only_scalar(p, n);
 }
 static inline bool acgtn_only(const std::string& r) { return acgtn_only(r.data(), r.size()); }
 
@@ -387,16 +432,67 @@ void ReadParser::next_chunk(uint32_t n, ReadBatch& out) {
 
 // ------------------------------------------------------------------------------ parallel reader
 
-void parallel_for(unsigned threads, const std::function<void(unsigned)>& fn) {
-    if (threads <= 1) {
-        fn(0);
+struct WorkerPool::State {
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::vector<std::thread> th;
+    const std::function<void(unsigned)>* fn = nullptr;
+    unsigned T = 0, next = 0, pending = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+    void work(std::unique_lock<std::mutex>& l) {  // take indices until the job is used up
+        while (next < T) {
+            const unsigned t = next++;
+            const std::function<void(unsigned)>* f = fn;
+            l.unlock();
+            (*f)(t);
+            l.lock();
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+};
+
+WorkerPool::WorkerPool(unsigned workers) : st_(new State()) {
+    for (unsigned i = 0; i < workers; ++i)
+        st_->th.emplace_back([s = st_] {
+            std::unique_lock<std::mutex> l(s->m);
+            uint64_t seen = 0;
+            for (;;) {
+                s->cv_job.wait(l, [&] { return s->stop || s->epoch != seen; });
+                if (s->stop) return;
+                seen = s->epoch;
+                s->work(l);
+            }
+        });
+}
+
+WorkerPool::~WorkerPool() {
+    {
+        std::unique_lock<std::mutex> l(st_->m);
+        st_->stop = true;
+    }
+    st_->cv_job.notify_all();
+    for (auto& t : st_->th) t.join();
+    delete st_;
+}
+
+void WorkerPool::run(unsigned T, const std::function<void(unsigned)>& fn) {
+    if (T == 0) return;
+    if (T == 1 || st_->th.empty()) {
+        for (unsigned t = 0; t < T; ++t) fn(t);
         return;
     }
-    std::vector<std::thread> th;
-    th.reserve(threads - 1);
-    for (unsigned t = 1; t < threads; ++t) th.emplace_back([&fn, t] { fn(t); });
-    fn(0);
-    for (auto& x : th) x.join();
+    std::unique_lock<std::mutex> l(st_->m);
+    st_->fn = &fn;
+    st_->T = T;
+    st_->next = 0;
+    st_->pending = T;
+    ++st_->epoch;
+    st_->cv_job.notify_all();
+    st_->work(l);
+    st_->cv_done.wait(l, [&] { return st_->pending == 0; });
+    st_->fn = nullptr;
+    st_->T = st_->next = 0;
 }
 
 namespace {
@@ -411,6 +507,11 @@ struct Shard {
     std::vector<Rec> recs;
     std::deque<std::string> joined;  // multi-line FASTA reads (stable addresses)
     uint64_t chars = 0;
+    void clear() {
+        recs.clear();
+        joined.clear();
+        chars = 0;
+    }
 };
 
 inline size_t line_end(const char* d, size_t pos, size_t end) {
@@ -492,34 +593,42 @@ size_t after_newline(const char* d, size_t a, size_t j) {
 }
 
 // append the shards' records to the batch, in shard order, copying in parallel
-void gather(std::vector<Shard>& sh, unsigned threads, ParsedBatch& out) {
-    const size_t T = sh.size();
+void gather(std::vector<Shard>& sh, size_t T, WorkerPool& pool, ParsedBatch& out) {
     std::vector<size_t> r0(T + 1, 0), c0(T + 1, 0);
     for (size_t t = 0; t < T; ++t) {
         r0[t + 1] = r0[t] + sh[t].recs.size();
         c0[t + 1] = c0[t] + sh[t].chars;
     }
-    const size_t base_r = out.hdr.size(), base_c = out.seqs.n;
+    const size_t base_r = out.hdr.n, base_c = out.seqs.n;
     out.seqs.reserve(base_c + c0[T] + 64);
     out.soff.reserve(base_r + r0[T] + 2);
-    out.hdr.resize(base_r + r0[T]);
-    parallel_for((unsigned)std::min<size_t>(threads, T), [&](unsigned w) {
-        for (size_t t = w; t < T; t += std::min<size_t>(threads, T)) {
-            size_t r = base_r + r0[t], c = base_c + c0[t];
-            for (const Rec& x : sh[t].recs) {
-                memcpy(out.seqs.p + c, x.s, x.sn);
-                c += x.sn;
-                out.soff.p[r + 1] = c;
-                out.hdr[r] = HdrView{x.h, x.hn};
-                ++r;
-            }
+    out.hdr.reserve(base_r + r0[T] + 1);
+    pool.run((unsigned)T, [&](unsigned t) {
+        size_t r = base_r + r0[t], c = base_c + c0[t];
+        for (const Rec& x : sh[t].recs) {
+            memcpy(out.seqs.p + c, x.s, x.sn);
+            c += x.sn;
+            out.soff.p[r + 1] = c;
+            out.hdr.p[r] = HdrView{x.h, x.hn};
+            ++r;
         }
     });
     out.seqs.n = base_c + c0[T];
     out.soff.n = base_r + r0[T] + 1;
+    out.hdr.n = base_r + r0[T];
 }
 
 }  // namespace
+
+struct ParallelReader::Impl {
+    WorkerPool pool;
+    std::vector<Shard> sh;
+    explicit Impl(unsigned threads) : pool(threads - 1), sh(threads) {}
+    std::vector<Shard>& shards(unsigned T) {
+        for (unsigned t = 0; t < T; ++t) sh[t].clear();
+        return sh;
+    }
+};
 
 ParallelReader::ParallelReader(const char* data, size_t n, uint32_t k, bool fastq, unsigned threads,
                                size_t range_bytes, size_t min_slice)
@@ -529,7 +638,10 @@ ParallelReader::ParallelReader(const char* data, size_t n, uint32_t k, bool fast
       min_slice_(min_slice ? min_slice : 1),
       k_(k),
       fastq_(fastq),
-      threads_(threads ? threads : 1) {}
+      threads_(threads ? threads : 1),
+      impl_(new Impl(threads_)) {}
+
+ParallelReader::~ParallelReader() { delete impl_; }
 
 // smallest unambiguous record start >= x (see the header), or n_
 size_t ParallelReader::fasta_boundary(size_t x) const {
@@ -565,14 +677,15 @@ void ParallelReader::next_fasta(ParsedBatch& out) {
     std::vector<size_t> cut(T + 1);
     cut[0] = a;
     cut[T] = b;
-    parallel_for(T, [&](unsigned t) {
+    WorkerPool& pool = impl_->pool;
+    pool.run(T, [&](unsigned t) {
         if (t) cut[t] = std::min(b, fasta_boundary(a + (size_t)((b - a) / T) * t));
     });
-    std::vector<Shard> sh(T);
-    parallel_for(T, [&](unsigned t) {
+    std::vector<Shard>& sh = impl_->shards(T);
+    pool.run(T, [&](unsigned t) {
         if (cut[t] < cut[t + 1]) parse_fasta_range(d_, cut[t], cut[t + 1], k_, sh[t]);
     });
-    gather(sh, T, out);
+    gather(sh, T, pool, out);
     pos_ = b;
     if (pos_ >= n_) finished_ = true;
 }
@@ -589,7 +702,8 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
         std::vector<size_t> lo(T + 1), cnt(T + 1, 0);
         for (unsigned t = 0; t <= T; ++t) lo[t] = a + (size_t)((b - a) / T) * t;
         lo[T] = b;
-        parallel_for(T, [&](unsigned t) { cnt[t + 1] = count_newlines(d_, lo[t], lo[t + 1]); });
+        WorkerPool& pool = impl_->pool;
+        pool.run(T, [&](unsigned t) { cnt[t + 1] = count_newlines(d_, lo[t], lo[t + 1]); });
         for (unsigned t = 0; t < T; ++t) cnt[t + 1] += cnt[t];  // cnt[t] = newlines before slice t
         const size_t q = cnt[T] / 4;  // whole newline-terminated records in [a, b)
         size_t P;                     // records parsed here by the workers
@@ -607,13 +721,13 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
             return after_newline(d_, lo[t], j - cnt[t]);
         };
         std::vector<size_t> cut(T + 1);
-        parallel_for(T, [&](unsigned t) { cut[t] = record_start(P / T * t); });
+        pool.run(T, [&](unsigned t) { cut[t] = record_start(P / T * t); });
         cut[T] = record_start(P);
-        std::vector<Shard> sh(T);
-        parallel_for(T, [&](unsigned t) {
+        std::vector<Shard>& sh = impl_->shards(T);
+        pool.run(T, [&](unsigned t) {
             if (cut[t] < cut[t + 1]) parse_fastq_range(d_, cut[t], cut[t + 1], sh[t]);
         });
-        gather(sh, T, out);
+        gather(sh, T, pool, out);
         pos_ = cut[T];
         if (final) {
             // the end of the stream, exactly as the reference sees it
@@ -629,7 +743,7 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
                 memcpy(out.seqs.p + out.seqs.n, tail.seqs.p + tail.soff.p[i], sn);
                 out.seqs.n += sn;
                 out.soff.p[out.soff.n++] = out.seqs.n;
-                out.hdr.push_back(HdrView{out.arena.data() + tail.hoff.p[i], (uint32_t)(tail.hoff.p[i + 1] - tail.hoff.p[i])});
+                out.hdr.push(HdrView{out.arena.data() + tail.hoff.p[i], (uint32_t)(tail.hoff.p[i + 1] - tail.hoff.p[i])});
             }
             pos_ = n_;
             finished_ = true;

@@ -158,24 +158,36 @@ struct HdrView {
 struct ParsedBatch {
     PodBuf<char> seqs;      // sequences, concatenated (allocator: pinned host memory in the CLI)
     PodBuf<uint64_t> soff;  // n+1 offsets into seqs
-    std::vector<HdrView> hdr;  // header lines: views into the input text, or into `arena`
+    PodBuf<HdrView> hdr;    // header lines: views into the input text, or into `arena`
     std::vector<char> arena;   // headers that do not live in the input text (sequential tail)
     ParsedBatch() { clear(); }
     void set_allocator(AllocFn a, FreeFn f) {
         seqs.alloc = soff.alloc = a;
         seqs.dealloc = soff.dealloc = f;
     }
-    size_t size() const { return hdr.size(); }
+    size_t size() const { return hdr.n; }
     void clear() {
-        seqs.n = soff.n = 0;
+        seqs.n = soff.n = hdr.n = 0;
         soff.push(0);
-        hdr.clear();
         arena.clear();
     }
 };
 
-// run fn(t) for t in [0, threads) on `threads` threads (the caller is one of them)
-void parallel_for(unsigned threads, const std::function<void(unsigned)>& fn);
+// Persistent workers for the data-parallel phases of the reader and the writer: run(T, fn) calls
+// fn(t) for t in [0, T) on up to size()+1 threads (the caller is one of them) and returns when all are
+// done. One pool serves one caller at a time.
+class WorkerPool {
+   public:
+    explicit WorkerPool(unsigned workers);
+    ~WorkerPool();
+    WorkerPool(const WorkerPool&) = delete;
+    WorkerPool& operator=(const WorkerPool&) = delete;
+    void run(unsigned T, const std::function<void(unsigned)>& fn);
+
+   private:
+    struct State;
+    State* st_;
+};
 
 // every character one of A C G T N (aligner.cpp:55-60)
 bool acgtn_only(const char* p, size_t n);
@@ -187,6 +199,9 @@ class ParallelReader {
     // min_slice: least text per worker (tests set it to 1 to cut tiny inputs everywhere)
     ParallelReader(const char* data, size_t n, uint32_t k, bool fastq, unsigned threads, size_t range_bytes,
                    size_t min_slice = 4096);
+    ~ParallelReader();
+    ParallelReader(const ParallelReader&) = delete;
+    ParallelReader& operator=(const ParallelReader&) = delete;
     bool done() const { return finished_; }
     // appends the records of the next range to `out` (which the caller has cleared)
     void next(ParsedBatch& out);
@@ -195,12 +210,14 @@ class ParallelReader {
     void next_fasta(ParsedBatch& out);
     void next_fastq(ParsedBatch& out);
     size_t fasta_boundary(size_t x) const;
+    struct Impl;  // worker pool + per-worker record lists, reused from range to range
 
     const char* d_;
     size_t n_, pos_ = 0, range_, min_slice_;
     uint32_t k_;
     bool fastq_, finished_ = false;
     unsigned threads_;
+    Impl* impl_;
 };
 
 }  // namespace bgr

@@ -288,7 +288,7 @@ extern "C" long emu_parse_reads_parallel(const char* path, uint32_t k, int fastq
         pb.clear();
         pr.next(pb);
         for (size_t i = 0; i < pb.size(); ++i)
-            rb.push(pb.hdr[i].p, pb.hdr[i].n, pb.seqs.p + pb.soff.p[i], pb.soff.p[i + 1] - pb.soff.p[i]);
+            rb.push(pb.hdr.p[i].p, pb.hdr.p[i].n, pb.seqs.p + pb.soff.p[i], pb.soff.p[i + 1] - pb.soff.p[i]);
     } while (!pr.done());
     *headers = dup_bytes(rb.headers.p, rb.headers.n);
     *seqs = dup_bytes(rb.seqs.p, rb.seqs.n);
@@ -305,5 +305,7 @@ extern "C" long emu_load_unitigs(const char* path, uint32_t k, char** seqs, uint
     *off = dup_u64(o.data(), o.size());
     return (long)o.size() - 1;
 }
+
+extern "C" int emu_acgtn_only(const char* p, uint64_t n) { return acgtn_only(p, (size_t)n) ? 1 : 0; }
 
 extern "C" void emu_free(void* p) { free(p); }

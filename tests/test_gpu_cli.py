@@ -18,8 +18,10 @@ CLI = json.load(open(os.path.join(GOLDEN, "cli_cases.json")))
 TIMING = ("Indexing in seconds", "Reads/seconds", "Mapping in seconds")
 
 
-def run_cli(args, cwd):
-    p = subprocess.run([BGREAT] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=120)
+def run_cli(args, cwd, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([BGREAT] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=120, env=e)
     lines = [l for l in p.stdout.splitlines() if not l.startswith(TIMING)]
     return p.returncode, lines, p.stderr
 
@@ -53,6 +55,42 @@ def test_cli_matches_reference_binary(case, tmp_path):
         if with_o and fn.startswith("notAligned"):
             continue
         assert got == want, fn
+
+
+@pytest.mark.parametrize("env", [{"BGR_RANGE_BYTES": "40"}, {"BGR_RANGE_BYTES": "1000", "BGR_OUT": "write"},
+                                 {"BGR_OUT": "write"}], ids=["tiny_ranges", "ranges_write", "write"])
+@pytest.mark.parametrize("name", ["K1_two_files", "K4_fastq_trailing_nl", "K4_fastq_no_trailing_nl", "K5_fasta_edges_m1",
+                                  "random_k7_e2"])
+def test_cli_many_batches_and_plain_writes(name, env, tmp_path):
+    """The same golden runs with the input cut into many batches (several worker threads) and with the
+    write() output path instead of the memory-mapped one."""
+    case = next(c for c in CLI if c["name"] == name)
+    for fn, content in case["files"].items():
+        with open(tmp_path / fn, "w", newline="") as f:
+            f.write(content)
+    args = [a for a in case["args"]]
+    if "-t" in args:
+        args[args.index("-t") + 1] = "3"
+    else:
+        args += ["-t", "3"]
+    rc, lines, err = run_cli(args, str(tmp_path), env)
+    assert rc == 0, err
+    assert lines == case["stdout"]
+    for fn, want in case["outputs"].items():
+        if want is not None:
+            assert open(tmp_path / fn, newline="").read() == want, fn
+
+
+def test_cli_output_to_a_pipe(tmp_path):
+    """-f /dev/stdout style targets cannot be memory-mapped: plain writes."""
+    case = next(c for c in CLI if c["name"] == "K5_fasta_edges_m1")
+    for fn, content in case["files"].items():
+        with open(tmp_path / fn, "w", newline="") as f:
+            f.write(content)
+    p = subprocess.run("%s %s -f /dev/stderr > /dev/null" % (BGREAT, " ".join(case["args"])), shell=True, cwd=str(tmp_path),
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0
+    assert p.stderr == case["outputs"]["paths"]
 
 
 def test_cli_o_splits_no_overlap_reads(tmp_path):

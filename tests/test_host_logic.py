@@ -100,3 +100,18 @@ def test_parsers_on_many_chunk_files(case, tmp_path):
         assert len(got) == case["n_records"], kw
         assert [[h.decode("latin1"), r.decode("latin1")] for h, r in got[-2:]] == case["last"], kw
         assert G.digest(got) == case["sha256"], kw
+
+
+def test_read_validation_every_position():
+    """acgtn_only (vector body, overlapping tail, scalar rest): one bad byte anywhere must be seen"""
+    import ctypes as C
+    import random
+    L = E.lib()
+    rng = random.Random(5)
+    for n in list(range(0, 70)) + [95, 96, 97, 150, 151, 255, 256, 1000]:
+        good = bytes(rng.choice(b"ACGTN") for _ in range(n))
+        assert L.emu_acgtn_only(good, C.c_uint64(n)) == 1
+        for pos in range(n):
+            for badc in (b"a", b"X", b"\r", b"\x00", b"\xc1", b"B", b"@"):
+                bad = good[:pos] + badc + good[pos + 1:]
+                assert L.emu_acgtn_only(bad, C.c_uint64(n)) == 0, (n, pos, badc)

@@ -31,6 +31,8 @@ def run(exe, args, cwd):
     t0 = time.perf_counter()
     p = subprocess.run([exe] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True)
     dt = time.perf_counter() - t0
+    if os.environ.get("BGR_VERBOSE"):
+        sys.stderr.write(p.stderr)
     if p.returncode != 0:
         raise RuntimeError("%s failed rc=%d: %s" % (exe, p.returncode, p.stderr[-400:]))
     info = {}
