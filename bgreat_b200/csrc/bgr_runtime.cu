@@ -10,6 +10,7 @@
 
 #include "../../include/bgreat_b200.h"
 #include "bgr_host.h"
+#include "bgr_index_gpu.h"
 #include "bgr_kernels.cuh"
 
 using namespace bgr;
@@ -334,11 +335,26 @@ void bgr_host_free(void* p) {
 
 int bgr_index_build(bgr_ctx* ctx, const char* seqs, const uint64_t* off, uint32_t n_unitigs, uint32_t k) {
     if (!ctx || !off || (!seqs && n_unitigs)) return fail(ctx, BGR_ERR_ARG, "null argument");
-    std::vector<uint64_t> blob;
     std::string err;
-    int rc = build_index_blob(seqs, off, n_unitigs, k, blob, err);
+    const char* where = getenv("BGR_INDEX_BUILD");
+    if (where && !strcmp(where, "host")) {
+        // the original builder: table filled on the host, one upload (kept for comparison and debugging)
+        std::vector<uint64_t> blob;
+        int rc = build_index_blob(seqs, off, n_unitigs, k, blob, err);
+        if (rc) return fail(ctx, rc, err);
+        return install_host_blob(ctx, blob.data(), blob.size() * 8);
+    }
+    CK(cudaSetDevice(ctx->device));
+    void* d_blob = nullptr;
+    BlobHeader h;
+    int rc = build_index_on_device(seqs, off, n_unitigs, k, &d_blob, &h, &ctx->launches, err);
     if (rc) return fail(ctx, rc, err);
-    return install_host_blob(ctx, blob.data(), blob.size() * 8);
+    if ((rc = drop_index(ctx))) {
+        cudaFree(d_blob);
+        return rc;
+    }
+    ctx->d_blob = d_blob;
+    return set_index_from_device_blob(ctx);
 }
 
 int bgr_index_build_file(bgr_ctx* ctx, const char* unitig_fasta, uint32_t k) {

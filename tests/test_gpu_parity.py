@@ -244,3 +244,81 @@ def test_effort_and_mismatch_sweep_properties(bg):
         prev = c["aligned"]
         assert int((r.flags & 1).sum()) == c["aligned"]
         al.close()
+
+
+# ---- index built on the GPU (default) vs built on the host (BGR_INDEX_BUILD=host): same blob layout, same
+# content; only the slot a key occupies inside its probe sequence may differ
+
+def _blob_view(blob):
+    """-> (header dict, {key: payload bytes}, meta bytes, pool bytes, bloom bytes)"""
+    names = ["magic", "vk", "n_unitigs", "n_keys", "n_buckets", "pool_words", "off_keys", "off_payload", "off_meta",
+             "off_pool", "total_bytes", "n_bloom", "off_bloom", "two"]
+    h = dict(zip(names, np.frombuffer(blob[:8 * len(names)].tobytes(), dtype=np.uint64).tolist()))
+    nslots = h["n_buckets"] * 4
+    keys = np.frombuffer(blob[h["off_keys"]:h["off_keys"] + 8 * nslots].tobytes(), dtype=np.uint64)
+    pay = np.frombuffer(blob[h["off_payload"]:h["off_payload"] + 32 * nslots].tobytes(), dtype=np.uint8).reshape(nslots, 32)
+    table = {int(k): pay[i].tobytes() for i, k in enumerate(keys) if k != 0xFFFFFFFFFFFFFFFF}
+    empty_payload_ok = all(not pay[i].any() for i, k in enumerate(keys) if k == 0xFFFFFFFFFFFFFFFF)
+    meta = blob[h["off_meta"]:h["off_meta"] + 16 * (h["n_unitigs"] + 1)].tobytes()
+    pool = blob[h["off_pool"]:h["off_pool"] + 8 * h["pool_words"]].tobytes()
+    bloom = blob[h["off_bloom"]:h["off_bloom"] + 4 * h["n_bloom"]].tobytes()
+    # probe-sequence invariant: slots of a bucket fill in order
+    kb = keys.reshape(-1, 4) != 0xFFFFFFFFFFFFFFFF
+    in_order = bool((kb[:, :-1] >= kb[:, 1:]).all())
+    return h, table, meta, pool, bloom, empty_payload_ok and in_order
+
+
+def _build_both(bg, k, unitigs):
+    out = []
+    for where in ("gpu", "host"):
+        os.environ["BGR_INDEX_BUILD"] = where
+        try:
+            al = bg.Aligner(k, 2, 2)
+            al.index_unitigs(unitigs)
+        finally:
+            os.environ.pop("BGR_INDEX_BUILD", None)
+        out.append(al)
+    return out
+
+
+@pytest.mark.parametrize("case", [c for c in HARNESS if c["name"].startswith(("K", "fuzz_1", "fuzz_2", "k31"))],
+                         ids=lambda c: c["name"])
+def test_gpu_built_index_equals_host_built_index(bg, case):
+    g, h = _build_both(bg, case["k"], case["unitigs"])
+    assert g.index_stats() == h.index_stats()
+    hg, tg, mg, pg, bg_, okg = _blob_view(g.export_index_host())
+    hh, th, mh, ph, bh, okh = _blob_view(h.export_index_host())
+    assert hg == hh
+    assert okg and okh
+    assert tg == th          # every key, with its left/right slots (order, overflow, orientation flags)
+    assert mg == mh and pg == ph and bg_ == bh
+    g.close()
+    h.close()
+
+
+def test_gpu_built_index_maps_like_host_built_index(bg):
+    unitigs, reads = _k31_case(11, 4000, genome=60000)
+    for env in ({}, {"BGR_BLOOM": "global"}):
+        os.environ.update(env)
+        try:
+            g, h = _build_both(bg, 31, unitigs)
+        finally:
+            for k_ in env:
+                os.environ.pop(k_, None)
+        _, tg, mg, pg, blg, okg = _blob_view(g.export_index_host())
+        _, th, mh, ph, blh, okh = _blob_view(h.export_index_host())
+        assert okg and okh and tg == th and mg == mh and pg == ph and blg == blh
+        for mode in (O.GREEDY, O.EXHAUSTIVE):
+            assert g.align_batch(reads, mode).as_tuples() == h.align_batch(reads, mode).as_tuples()
+        g.close()
+        h.close()
+
+
+def test_gpu_index_build_reports_the_offending_unitig(bg):
+    al = bg.Aligner(5, 2, 2)
+    with pytest.raises(bg.BgrError) as e:
+        al.index_unitigs(["ACGTACGT", "ACGTTGCA", "ACGTNACGT", "ACGTAAAA"])
+    assert "unitig 3 " in str(e.value)
+    al.index_unitigs(["ACGTACGT", "ACG", "ACGTNACGT"])  # loading stops at the short one: the N is never seen
+    assert al.index_stats()["unitigs"] == 1
+    al.close()
