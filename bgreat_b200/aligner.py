@@ -131,8 +131,40 @@ class Aligner:
         return list(ids[:n])
 
     # ---- mapping
-    def params(self, mode):
-        return A.Params(mode, self.errors, self.effort, 0)
+    def params(self, mode, flags=0):
+        return A.Params(mode, self.errors, self.effort, flags)
+
+    def correct_batch(self, reads):
+        """Correction mode (`bgreat -c`, alignerGreedy.cpp:394-404): -> (MappingResult, [corrected read as
+        bytes, or None for a read that does not map]). Uses the slot API (upload / run / download)."""
+        buf, off = _concat(reads)
+        n = len(off) - 1
+        res = np.zeros((max(n, 1), 2), dtype=np.uint32)
+        cap = max(1024, int(off[-1]) + 2 * n + 16)
+        pool = np.zeros(cap, dtype=np.int32)
+        nw = (int(off[-1]) >> 5) + n + 2
+        words = np.zeros(nw, dtype=np.uint64)
+        used = C.c_uint64()
+        p = self.params(A.MODE_GREEDY, A.P_CORRECT)
+        self._ck(self.L.bgr_slot_upload(self.ctx, 0, buf.ctypes.data, off.ctypes.data, n))
+        self._ck(self.L.bgr_slot_run(self.ctx, 0, C.byref(p)))
+        self._ck(self.L.bgr_slot_download(self.ctx, 0, res.ctypes.data, pool.ctypes.data, cap))
+        self._ck(self.L.bgr_slot_download_corrected(self.ctx, 0, words.ctypes.data, nw))
+        self._ck(self.L.bgr_slot_wait(self.ctx, 0, C.byref(used)))
+        r = MappingResult(res[:n, 0], res[:n, 1], pool[:used.value])
+        out = []
+        for i in range(n):
+            if not r.mapped(i):
+                out.append(None)
+                continue
+            ln = int(off[i + 1] - off[i])
+            w0 = (int(off[i]) >> 5) + i
+            bits = words[w0:w0 + (ln + 31) // 32]
+            s = bytearray()
+            for j in range(ln):
+                s.append(b"ACGT"[(int(bits[j >> 5]) >> (62 - 2 * (j & 31))) & 3])
+            out.append(bytes(s))
+        return r, out
 
     def align_batch(self, reads, mode=A.MODE_GREEDY):
         """reads: list of str/bytes. -> MappingResult (through bgr_map_batch, host buffers)."""

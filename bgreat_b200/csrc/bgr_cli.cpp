@@ -11,7 +11,8 @@
 //   * a read file that cannot be opened is an error (the reference spins forever);
 //   * -o FILE writes the reads without any overlap to FILE (the reference accepts -o and ignores it);
 //   * -b writes its paths and unmapped reads (the reference computes them and writes nothing);
-//   * -c / -G (and -i together with -b) are not part of this path and are refused.
+//   * -G (and -i together with -b) are not part of this path and are refused; -c (corrected reads instead
+//     of paths, alignerGreedy.cpp:394-404) is supported for the greedy aligner, where the reference has it.
 #include <fcntl.h>
 #include <getopt.h>
 #include <stdio.h>
@@ -52,12 +53,13 @@ struct Batch {
     ParsedBatch pb;
     PodBuf<bgr_result> res;
     PodBuf<int32_t> pool;
+    PodBuf<uint64_t> corr;  // -c: corrected reads, 2 bits per base (layout: BGR_CORRECTED_BASE)
     uint64_t pool_used = 0;
     int slot = -1;
     Batch() {
         pb.set_allocator(pinned_alloc, pinned_free);
-        res.alloc = pool.alloc = pinned_alloc;
-        res.dealloc = pool.dealloc = pinned_free;
+        res.alloc = pool.alloc = corr.alloc = pinned_alloc;
+        res.dealloc = pool.dealloc = corr.dealloc = pinned_free;
     }
 };
 
@@ -196,14 +198,16 @@ static inline int out_of(uint32_t flags, bool split_no_overlap) {
 }
 
 // bytes reads [lo, hi) of the batch put into each of the three files
-static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, size_t sz[3]) {
+static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, bool correction, size_t sz[3]) {
     sz[0] = sz[1] = sz[2] = 0;
     for (size_t i = lo; i < hi; ++i) {
         const bgr_result r = b.res.p[i];
         const uint32_t flags = BGR_RESULT_FLAGS(r), len = BGR_RESULT_LEN(r);
         const int o = out_of(flags, split_no_overlap);
         size_t n = b.pb.hdr.p[i].n + 2;
-        if (o == OUT_PATHS) {
+        if (o == OUT_PATHS && correction) {
+            n += b.pb.soff.p[i + 1] - b.pb.soff.p[i];  // the corrected read is as long as the read
+        } else if (o == OUT_PATHS) {
             const int32_t* ids = b.pool.p + r.path_off;
             for (uint32_t j = 0; j < len; ++j) n += int_chars(ids[j]) + 1;
         } else {
@@ -214,7 +218,25 @@ static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_ov
 }
 
 // header\npath\n for mapped reads (printPath, aligner.cpp:600-609), header\nread\n otherwise
-static void format_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, char* dst[3]) {
+// 2-bit words -> characters, four bases per table entry
+struct DecodeTable {
+    char t[256][4];
+    DecodeTable() {
+        for (int v = 0; v < 256; ++v)
+            for (int j = 0; j < 4; ++j) t[v][j] = "ACGT"[(v >> (6 - 2 * j)) & 3];
+    }
+};
+static const DecodeTable g_decode;
+
+static inline char* put_bases(char* p, const uint64_t* w, size_t n) {
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32, ++w)
+        for (int b = 7; b >= 0; --b, p += 4) memcpy(p, g_decode.t[(*w >> (8 * b)) & 0xFF], 4);
+    for (; i < n; ++i) *p++ = "ACGT"[(*w >> (62 - 2 * (i & 31))) & 3];
+    return p;
+}
+
+static void format_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, bool correction, char* dst[3]) {
     for (size_t i = lo; i < hi; ++i) {
         const bgr_result r = b.res.p[i];
         const uint32_t flags = BGR_RESULT_FLAGS(r), len = BGR_RESULT_LEN(r);
@@ -223,7 +245,9 @@ static void format_range(const Batch& b, size_t lo, size_t hi, bool split_no_ove
         memcpy(p, b.pb.hdr.p[i].p, b.pb.hdr.p[i].n);
         p += b.pb.hdr.p[i].n;
         *p++ = '\n';
-        if (o == OUT_PATHS) {
+        if (o == OUT_PATHS && correction) {  // header\ncorrected\n (alignerGreedy.cpp:399)
+            p = put_bases(p, b.corr.p + BGR_CORRECTED_BASE(b.pb.soff.p[i], i), b.pb.soff.p[i + 1] - b.pb.soff.p[i]);
+        } else if (o == OUT_PATHS) {
             const int32_t* ids = b.pool.p + r.path_off;
             for (uint32_t j = 0; j < len; ++j) {
                 p = put_int(p, ids[j]);
@@ -286,10 +310,12 @@ int main(int argc, char** argv) {
         usage();
         return 0;
     }
-    if (o.correction || o.dog || (o.incomplete && o.brute)) {
-        fprintf(stderr, "bgreat: -c, -G and -b -i are outside the GPU mapping path and not supported\n");
+    if (o.dog || (o.incomplete && o.brute)) {
+        fprintf(stderr, "bgreat: -G and -b -i are outside the GPU mapping path and not supported\n");
         return 2;
     }
+    // correctionMode only acts in alignPartGreedy (alignerGreedy.cpp:394); -b ignores it
+    const bool correction = o.correction && !o.brute;
     // the reference keeps the thread count in an unsigned char (aligner.h:80)
     unsigned threads = (unsigned char)o.threads;
     if (threads == 0) threads = 1;
@@ -334,7 +360,7 @@ int main(int argc, char** argv) {
     params.mode = o.brute ? BGR_MODE_EXHAUSTIVE : BGR_MODE_GREEDY;
     params.errors = (uint32_t)o.errors;
     params.effort = (uint32_t)o.effort;
-    params.reserved = 0;
+    params.flags = correction ? BGR_P_CORRECT : 0u;
 
     const size_t n_batches = n_slots + 3;
     std::vector<Batch> batches(n_batches);
@@ -421,6 +447,10 @@ int main(int argc, char** argv) {
                 int r = bgr_slot_upload(ctx, b->slot, b->pb.seqs.p, b->pb.soff.p, (uint32_t)n);
                 if (r == BGR_OK) r = bgr_slot_run(ctx, b->slot, &params);
                 if (r == BGR_OK) r = bgr_slot_download(ctx, b->slot, b->res.p, b->pool.p, b->pool.cap);
+                if (r == BGR_OK && correction) {
+                    b->corr.reserve(BGR_CORRECTED_WORDS(b->pb.seqs.n, n));
+                    r = bgr_slot_download_corrected(ctx, b->slot, b->corr.p, b->corr.cap);
+                }
                 if (r != BGR_OK) {
                     fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
                     exit(1);
@@ -446,7 +476,7 @@ int main(int argc, char** argv) {
             const auto t0w = now();
             const size_t n = b->pb.size();
             const unsigned T = (unsigned)std::min<size_t>(threads, n / 4096 + 1);
-            pool.run(T, [&](unsigned t) { measure_range(*b, n * t / T, n * (t + 1) / T, o.have_o, &sz[3 * t]); });
+            pool.run(T, [&](unsigned t) { measure_range(*b, n * t / T, n * (t + 1) / T, o.have_o, correction, &sz[3 * t]); });
             size_t total[3] = {0, 0, 0};
             for (unsigned t = 0; t < T; ++t)
                 for (int f = 0; f < 3; ++f) {
@@ -458,7 +488,7 @@ int main(int argc, char** argv) {
             pool.run(T, [&](unsigned t) {
                 char* dst[3];
                 for (int f = 0; f < 3; ++f) dst[f] = out[f].base ? out[f].base + at[3 * t + f] : nullptr;
-                format_range(*b, n * t / T, n * (t + 1) / T, o.have_o, dst);
+                format_range(*b, n * t / T, n * (t + 1) / T, o.have_o, correction, dst);
             });
             for (int f = 0; f < 3; ++f)
                 if (!out[f].end(total[f])) write_error = true;

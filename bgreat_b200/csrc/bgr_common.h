@@ -181,4 +181,9 @@ inline u64 bloom_words_for(u64 n_keys, bool& two_hashes) {
 BGR_HD u64 read_word_base(u64 char_off, u64 r) { return (char_off >> 5) + 4 * r; }
 BGR_HD u64 batch_words(u64 chars, u64 n_reads) { return (chars >> 5) + 4 * n_reads + 8; }
 
+// correction mode: read r's corrected bases start at this word of the batch's corrected buffer
+// (ceil(len/32) <= floor((o+len)/32) - floor(o/32) + 1, so one spare word per read is enough)
+BGR_HD u64 corrected_word_base(u64 char_off, u64 r) { return (char_off >> 5) + r; }
+BGR_HD u64 corrected_words(u64 chars, u64 n_reads) { return (chars >> 5) + n_reads + 2; }
+
 }  // namespace bgr

@@ -752,4 +752,101 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
     }
 }
 
+// ------------------------------------------------------------------------------ parallel unitig loader
+
+bool load_unitig_file_parallel(const char* path, uint32_t k, unsigned threads, PodBuf<char>& seqs,
+                               PodBuf<uint64_t>& off, size_t min_slice) {
+    seqs.n = off.n = 0;
+    off.push(0);
+    MappedFile f;
+    if (!f.open(path)) return false;
+    const char* d = f.data;
+    const size_t n = f.size;
+    const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads ? threads : 1, n / (min_slice ? min_slice : 1) + 1));
+    WorkerPool pool(T - 1);
+    // newline counts per slice -> start of record r (= right after newline number 2r)
+    std::vector<size_t> lo(T + 1), cnt(T + 1, 0);
+    for (unsigned t = 0; t <= T; ++t) lo[t] = (size_t)(n / T) * t;
+    lo[T] = n;
+    pool.run(T, [&](unsigned t) { cnt[t + 1] = count_newlines(d, lo[t], lo[t + 1]); });
+    for (unsigned t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
+    const size_t q = cnt[T] / 2;        // whole newline-terminated records
+    const size_t P = q ? q - 1 : 0;     // records the workers take; the rest is the sequential tail
+    auto record_start = [&](size_t r) -> size_t {
+        if (r == 0) return 0;
+        const size_t j = 2 * r;
+        const unsigned t = (unsigned)(std::upper_bound(cnt.begin(), cnt.end(), j - 1) - cnt.begin()) - 1;
+        return after_newline(d, lo[t], j - cnt[t]);
+    };
+    std::vector<size_t> cut(T + 1), first_rec(T + 1);
+    for (unsigned t = 0; t <= T; ++t) first_rec[t] = P / T * t;
+    first_rec[T] = P;
+    pool.run(T, [&](unsigned t) { cut[t] = record_start(first_rec[t]); });
+    cut[T] = record_start(P);
+    // pass 1: sequence line of every record (view), up to the worker's first line shorter than k
+    struct Part {
+        std::vector<std::pair<const char*, size_t>> recs;
+        uint64_t chars = 0;
+        bool stopped = false;
+    };
+    std::vector<Part> part(T);
+    pool.run(T, [&](unsigned t) {
+        size_t pos = cut[t];
+        const size_t end = cut[t + 1];
+        Part& p = part[t];
+        p.recs.reserve(first_rec[t + 1] - first_rec[t]);
+        while (pos < end) {
+            pos = line_end(d, pos, end) + 1;  // header line
+            const size_t e = line_end(d, pos, end);
+            const size_t len = e - pos;
+            if (len < k) {  // aligner.cpp:418
+                p.stopped = true;
+                break;
+            }
+            p.recs.emplace_back(d + pos, len);
+            p.chars += len;
+            pos = e + 1;
+        }
+    });
+    // loading stops at the first short line: later workers' records are dropped
+    unsigned used = T;
+    bool stopped = false;
+    for (unsigned t = 0; t < T; ++t)
+        if (part[t].stopped) {
+            used = t + 1;
+            stopped = true;
+            break;
+        }
+    std::vector<uint64_t> r0(used + 1, 0), c0(used + 1, 0);
+    for (unsigned t = 0; t < used; ++t) {
+        r0[t + 1] = r0[t] + part[t].recs.size();
+        c0[t + 1] = c0[t] + part[t].chars;
+    }
+    seqs.reserve(c0[used] + 64);
+    off.reserve(r0[used] + 4);
+    pool.run(used, [&](unsigned t) {
+        uint64_t r = r0[t], c = c0[t];
+        for (const auto& x : part[t].recs) {
+            memcpy(seqs.p + c, x.first, x.second);
+            c += x.second;
+            off.p[++r] = c;
+        }
+    });
+    seqs.n = c0[used];
+    off.n = r0[used] + 1;
+    if (!stopped) {
+        // the end of the file, exactly as the reference's loop sees it (aligner.cpp:415-421)
+        LineStream s(d + cut[T], n - cut[T], true);
+        std::string line;
+        while (!s.eof()) {
+            s.getline(line);
+            s.getline(line);
+            if (line.size() < k) break;
+            seqs.append(line.data(), line.size());
+            off.push(seqs.n);
+        }
+    }
+    return true;
+}
+
 }  // namespace bgr

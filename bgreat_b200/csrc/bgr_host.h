@@ -220,4 +220,11 @@ class ParallelReader {
     Impl* impl_;
 };
 
+// load_unitig_file on `threads` workers: records are two lines whatever they contain, so newlines are
+// counted in parallel and every worker takes whole records; the last record goes through the sequential
+// loop, which knows what a missing final line does (a failed second getline keeps the header text).
+// seqs/off as bgr_index_build wants them. Returns false if the file cannot be opened.
+bool load_unitig_file_parallel(const char* path, uint32_t k, unsigned threads, PodBuf<char>& seqs,
+                               PodBuf<uint64_t>& off, size_t min_slice = 1 << 16);
+
 }  // namespace bgr

@@ -58,7 +58,7 @@ struct DevCounters {
     u32 scratch_overflow;  // some path / search stack did not fit the per-read scratch
     u32 pool_overflow;     // the path pool was too small (pool_cursor = ints needed)
     u32 ext_cursor;        // next hit-list entry to hand to a warp of the extension kernel
-    u32 pad;
+    u32 correct_error;     // correction mode: a path does not spell a sequence as long as its read
 };
 // Written by the pack + seed-scan kernel.
 struct ScanCounters {
@@ -89,6 +89,7 @@ struct BatchArgs {
     u32 tile_r;      // reads per tile of the tile kernel (even, <= ST_MAX_R)
     u32 tile_cb;     // bytes of one character buffer of the tile kernel
     u32 errors, effort, mode;
+    u64* corr;  // correction mode (-c): corrected reads, 2 bits per base, read r at word corrected_word_base(off[r], r)
 };
 
 static const u32 INFO_HAS_N = 1u, INFO_HIT1 = 2u, INFO_HIT2 = 4u;
@@ -1831,6 +1832,101 @@ BGR_HD u32 greedy_path_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scrat
     return flags | BGR_F_CNT_NOTALIGNED;
 }
 
+// ------------------------------------------------------------------------------ correction mode
+//
+// recoverPath (aligner.cpp:268-290) on packed words. path = [offset, +-u1, ..., +-um] as alignReadGreedy
+// returns it. S = U1 ++ U2[k-1:] ++ ... ++ Um[k-1:] (oriented unitigs; compactionEnd, utils.cpp:171-179,
+// always finds the forward overlap on such a path); the corrected read is S[offset, offset+len), or its
+// reverse complement when `rc` -- produced directly by walking the path backwards with every unitig
+// flipped. Writes ceil(len/32) words (first base most significant); returns the number of bases written
+// (len, unless the path spells less than the read: the caller reports that).
+struct BaseWriter {
+    u64* out;
+    u64 acc;
+    u32 fill, wi;
+    BGR_HD void push(u64 x, u32 m) {  // m (1..32) bases, left aligned, zero behind
+        if (fill == 0) {
+            if (m == 32) out[wi++] = x;
+            else {
+                acc = x;
+                fill = m;
+            }
+        } else {
+            acc |= x >> (2 * fill);
+            if (fill + m >= 32) {
+                out[wi++] = acc;
+                const u32 used = 32 - fill;
+                acc = (m > used) ? x << (2 * used) : 0ull;
+                fill = m - used;
+            } else {
+                fill += m;
+            }
+        }
+    }
+    BGR_HD void flush() {
+        if (fill) out[wi++] = acc;
+        fill = 0;
+    }
+};
+
+// bases [from, from+take) of unitig (start, ulen) read in orientation `neg` (true = reverse complement)
+BGR_HD void emit_unitig(const DevIndex& ix, u64 start, u32 ulen, bool neg, u32 from, u32 take, BaseWriter& w) {
+    for (u32 done = 0; done < take; done += 32) {
+        const u32 m = (take - done < 32) ? take - done : 32;
+        const u32 p = from + done;
+        u64 x;
+        if (!neg) {
+            x = ld_bases(ix.pool, (i64)(start + p));
+        } else {
+            const u64 y = ld_bases(ix.pool, (i64)(start + ulen - p - m));  // its first m bases, reversed, are wanted
+            x = rc64(y) << ((2 * (32 - m)) & 63);
+        }
+        if (m < 32) x &= ~(~0ull >> (2 * m));
+        w.push(x, m);
+    }
+}
+
+BGR_HD u32 correct_read(const DevIndex& ix, const i32* path, u32 n, u32 len, bool rc, u64* out) {
+    if (n < 2) return 0;  // the reference reads numbers[1] of a one-element path here
+    const u32 km1 = ix.k - 1;
+    u64 S = 0;
+    for (u32 j = 1; j < n; ++j) {
+        const i32 id = path[j];
+        const u32 ul = ix.meta[id < 0 ? -id : id].len;
+        S += (j == 1) ? ul : ul - km1;
+    }
+    const i64 offset = path[0];
+    if (offset < 0 || (u64)offset > S) return 0;
+    const u64 room = S - (u64)offset;
+    const u32 emit = room < len ? (u32)room : len;
+    BaseWriter w;
+    w.out = out;
+    w.acc = 0;
+    w.fill = 0;
+    w.wi = 0;
+    u64 skip = rc ? S - (u64)offset - emit : (u64)offset;
+    u32 need = emit;
+    for (u32 t = 1; t < n && need; ++t) {
+        const u32 j = rc ? n - t : t;  // backwards for the reverse complement
+        const i32 id = path[j];
+        const UnitigMeta m = ix.meta[id < 0 ? -id : id];
+        const bool neg = (id < 0) != rc;
+        const u32 base0 = (t == 1) ? 0 : km1;
+        const u32 avail = m.len - base0;
+        if (skip >= avail) {
+            skip -= avail;
+            continue;
+        }
+        const u32 from = base0 + (u32)skip;
+        const u32 take = (avail - (u32)skip < need) ? avail - (u32)skip : need;
+        emit_unitig(ix, m.start, m.len, neg, from, take, w);
+        skip = 0;
+        need -= take;
+    }
+    w.flush();
+    return emit - need;
+}
+
 #if defined(__CUDACC__)
 // ---- extension kernels. A finished read leaves its path (final order) in its scratch row, its flags
 // and path length in res[r].flags_len and the scratch row number in res[r].path_off; the compaction
@@ -2021,6 +2117,21 @@ __global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const u
             off += len[j];
         }
     }
+}
+
+// ---- correction mode (-c): the sequence a greedy path spells, cut to the read (recoverPath,
+// aligner.cpp:268-290: oriented unitigs glued on their k-1 overlaps, substr(offset, |read|)), reverse
+// complemented when the read was mapped through its reverse complement (alignerGreedy.cpp:396)
+__global__ void __launch_bounds__(128) k_correct(DevIndex ix, BatchArgs a) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    const bgr_result res = a.res[r];
+    if (!(res.flags_len & BGR_F_MAPPED)) return;
+    const u64 o = a.off[r];
+    const u32 len = (u32)(a.off[r + 1] - o);
+    const u32 got = correct_read(ix, a.pool + res.path_off, res.flags_len >> 8, len, (res.flags_len & BGR_F_RC) != 0,
+                                 a.corr + corrected_word_base(o, r));
+    if (got != len) atomicExch(&a.cnt->correct_error, 1u);
 }
 
 // getBegin / getEnd for one code, for tests (bgr_index_query)

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bgreat_b200.h"
@@ -47,6 +48,11 @@ struct Slot {
     u32* d_slow = nullptr;  // reads the tile scan hands to the general scan kernel
     unsigned long long* d_bsum = nullptr;  // per-1024-read path length sums (compaction)
     size_t cap_bsum = 0;
+    u64* d_corr = nullptr;  // correction mode: corrected reads, 2 bits per base
+    size_t cap_corr = 0;
+    u64* h_corr = nullptr;
+    u64 h_corr_cap = 0;
+    bool want_corrected = false;
     // current batch
     u32 n = 0;
     u64 chars = 0, words = 0;
@@ -199,6 +205,7 @@ BatchArgs make_args(Slot& s) {
     a.errors = s.params.errors;
     a.effort = s.params.effort;
     a.mode = s.params.mode;
+    a.corr = s.d_corr;
     return a;
 }
 
@@ -222,6 +229,10 @@ int enqueue_compaction(bgr_ctx* ctx, Slot& s) {
     k_path_scan_blocks<<<1, CP_THREADS, 0, s.stream>>>(a, s.d_bsum, nb);
     k_path_gather<<<nb, CP_THREADS, 0, s.stream>>>(a, s.d_bsum);
     ctx->launches += 3;
+    if (s.params.flags & BGR_P_CORRECT) {  // needs the final pool offsets the gather just wrote
+        k_correct<<<(s.n + 127) / 128, 128, 0, s.stream>>>(ctx->ix, a);
+        ctx->launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(s.ev[2], s.stream));
     CK(cudaMemcpyAsync(s.h_cnt, s.d_cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, s.stream));
@@ -310,6 +321,7 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
         cudaFree(s.d_list);
         cudaFree(s.d_slow);
         cudaFree(s.d_bsum);
+        cudaFree(s.d_corr);
         if (s.h_cnt) cudaFreeHost(s.h_cnt);
         if (s.h_scnt) cudaFreeHost(s.h_scnt);
         for (int j = 0; j < 3; ++j)
@@ -359,10 +371,14 @@ int bgr_index_build(bgr_ctx* ctx, const char* seqs, const uint64_t* off, uint32_
 
 int bgr_index_build_file(bgr_ctx* ctx, const char* unitig_fasta, uint32_t k) {
     if (!ctx || !unitig_fasta) return fail(ctx, BGR_ERR_ARG, "null argument");
-    std::string seqs;
-    std::vector<uint64_t> off;
-    bool opened = load_unitig_file(unitig_fasta, k, seqs, off);
-    int rc = bgr_index_build(ctx, seqs.data(), off.data(), (uint32_t)(off.size() - 1), k);
+    // host threads for the loader: BGR_HOST_THREADS, else the machine's cores (at most 32)
+    unsigned threads = std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("BGR_HOST_THREADS")) threads = (unsigned)std::max(1, atoi(e));
+    PodBuf<char> seqs;
+    PodBuf<uint64_t> off;
+    const bool opened = load_unitig_file_parallel(unitig_fasta, k, threads, seqs, off);
+    if (off.n - 1 > 0xFFFFFFFFull) return fail(ctx, BGR_ERR_LIMIT, "more than 2^32-1 unitig records");
+    int rc = bgr_index_build(ctx, seqs.p ? seqs.p : "", off.p, (uint32_t)(off.n - 1), k);
     if (rc) return rc;
     if (!opened) return fail(ctx, BGR_ERR_IO, std::string("cannot open unitig file ") + unitig_fasta);
     return BGR_OK;
@@ -476,6 +492,7 @@ int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* of
     s.uploaded = true;
     s.ran = false;
     s.want_download = false;
+    s.want_corrected = false;
     return BGR_OK;
 }
 
@@ -485,8 +502,15 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     Slot& s = ctx->slots[slot];
     if (!s.uploaded) return fail(ctx, BGR_ERR_ARG, "slot has no batch uploaded");
     if (p->mode > BGR_MODE_EXHAUSTIVE_PATH) return fail(ctx, BGR_ERR_ARG, "unknown mode");
+    if ((p->flags & BGR_P_CORRECT) && p->mode != BGR_MODE_GREEDY)
+        return fail(ctx, BGR_ERR_ARG, "correction mode applies to the greedy aligner only (alignerGreedy.cpp:394)");
+    if (p->flags & ~BGR_P_CORRECT) return fail(ctx, BGR_ERR_ARG, "unknown flag in bgr_params.flags");
     CK(cudaSetDevice(ctx->device));
     s.params = *p;
+    if (p->flags & BGR_P_CORRECT) {
+        int rc = grow(ctx, s.d_corr, s.cap_corr, (size_t)corrected_words(s.chars, s.n));
+        if (rc) return rc;
+    }
     s.scratch_ints = (p->mode == BGR_MODE_GREEDY) ? ctx->scratch_greedy : ctx->scratch_exhaustive;
     CK(cudaMemsetAsync(s.d_cnt, 0, sizeof(DevCounters), s.stream));
     CK(cudaMemsetAsync(s.d_scnt, 0, sizeof(ScanCounters), s.stream));
@@ -555,6 +579,18 @@ int bgr_slot_download(bgr_ctx* ctx, int slot, bgr_result* results, int32_t* path
     return BGR_OK;
 }
 
+int bgr_slot_download_corrected(bgr_ctx* ctx, int slot, uint64_t* words, uint64_t cap_words) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    Slot& s = ctx->slots[slot];
+    if (!s.ran) return fail(ctx, BGR_ERR_ARG, "slot has not been run");
+    if (!(s.params.flags & BGR_P_CORRECT)) return fail(ctx, BGR_ERR_ARG, "the run was not made with BGR_P_CORRECT");
+    if (!words || cap_words < corrected_words(s.chars, s.n)) return fail(ctx, BGR_ERR_ARG, "corrected buffer too small");
+    s.h_corr = words;
+    s.h_corr_cap = cap_words;
+    s.want_corrected = true;
+    return BGR_OK;
+}
+
 int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
     if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
     Slot& s = ctx->slots[slot];
@@ -578,6 +614,8 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
         CK(cudaStreamSynchronize(s.stream));
         s.timed = false;  // event pair no longer brackets a single pass
     }
+    if (s.n && s.h_cnt->correct_error)
+        return fail(ctx, BGR_ERR_FORMAT, "correction mode: a path spells a sequence shorter than its read");
     const u64 used = s.h_cnt->pool_cursor;
     if (pool_used) *pool_used = used;
     if (!s.counted) {
@@ -590,6 +628,13 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used) {
         if (used > s.h_pool_cap) return fail(ctx, BGR_ERR_LIMIT, "path pool buffer too small");
         if (s.n) CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.n * sizeof(bgr_result), cudaMemcpyDeviceToHost, s.stream));
         if (used) CK(cudaMemcpyAsync(s.h_pool, s.d_pool, (size_t)used * sizeof(i32), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    if (s.want_corrected) {
+        s.want_corrected = false;
+        if (s.n)
+            CK(cudaMemcpyAsync(s.h_corr, s.d_corr, (size_t)corrected_words(s.chars, s.n) * sizeof(u64), cudaMemcpyDeviceToHost,
+                               s.stream));
         CK(cudaStreamSynchronize(s.stream));
     }
     return BGR_OK;

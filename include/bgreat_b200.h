@@ -73,11 +73,14 @@ enum {
 };
 
 /* parameters of one mapping call: Aligner ctor arguments that act per read (aligner.h:80) */
+/* bgr_params.flags */
+#define BGR_P_CORRECT 0x1u /* correctionMode (-c, aligner.h:97): also produce the corrected reads; BGR_MODE_GREEDY only */
+
 typedef struct bgr_params {
     uint32_t mode;   /* BGR_MODE_* */
     uint32_t errors; /* errorsMax, -m */
     uint32_t effort; /* tryNumber, -e */
-    uint32_t reserved;
+    uint32_t flags;  /* BGR_P_* (0: paths only) */
 } bgr_params;
 
 typedef struct bgr_ctx bgr_ctx;
@@ -141,6 +144,16 @@ int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* of
 int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p);
 int bgr_slot_download(bgr_ctx* ctx, int slot, bgr_result* results, int32_t* path_pool, uint64_t pool_cap);
 int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used);
+
+/* Correction mode (reference alignerGreedy.cpp:394-404: recoverPath, aligner.cpp:268-290, then the reverse
+ * complement when rc is set). With BGR_P_CORRECT in bgr_params.flags the run also spells every mapped
+ * read's path as a sequence of the read's length: 2 bits per base (A0 C1 G2 T3), first base in the most
+ * significant bits of a word, read i starting at word BGR_CORRECTED_BASE(off[i], i) of a buffer of
+ * BGR_CORRECTED_WORDS(off[n], n) words. Call between bgr_slot_run and bgr_slot_wait, like
+ * bgr_slot_download; words of unmapped reads are left untouched. */
+#define BGR_CORRECTED_BASE(char_off, i) (((uint64_t)(char_off) >> 5) + (uint64_t)(i))
+#define BGR_CORRECTED_WORDS(chars, n) (((uint64_t)(chars) >> 5) + (uint64_t)(n) + 2)
+int bgr_slot_download_corrected(bgr_ctx* ctx, int slot, uint64_t* words, uint64_t cap_words);
 /* device time of the last bgr_slot_run on this slot, per kernel (ms; CUDA events on the slot's
  * stream): [0] pack+seed-scan kernel, [1] extension kernel, [2] whole run */
 int bgr_slot_kernel_ms(bgr_ctx* ctx, int slot, float ms[3]);

@@ -1334,8 +1334,86 @@ static void print_path(sbuf* out, const int32_t* path, int n) {
     sb_putc(out, '\n');
 }
 
+/* ---- correction mode (-c): recoverPath / getUnitig (aligner.cpp:268-302), compactionEnd (utils.cpp:171-179) ---- */
+
+static void oriented_unitig(const bo_aligner* a, int32_t id, sbuf* out) { /* getUnitig, aligner.cpp:293-302 */
+    out->n = 0;
+    uint32_t u = (uint32_t)(id > 0 ? id : -id);
+    if (u >= a->n_unitigs) return; /* the reference indexes its vector out of range here */
+    if (id > 0) {
+        sb_put(out, a->unitigs[u], a->ulen[u]);
+    } else {
+        char* tmp = (char*)malloc(a->ulen[u] + 1);
+        bo_reverse_complement(a->unitigs[u], a->ulen[u], tmp);
+        sb_put(out, tmp, a->ulen[u]);
+        free(tmp);
+    }
+}
+
+/* recoverPath(numbers, size) followed by the reverse complement alignPartGreedy applies when rc is set
+ * (alignerGreedy.cpp:394-398). Returns the corrected read's length, -1 where the reference prints
+ * "bug compaction" and exits, -2 where it would index numbers[1] of a one-element path. */
+int64_t bo_recover_path(const bo_aligner* a, const int32_t* numbers, int n, uint32_t size, int rc, char* out) {
+    if (n < 2) return -2;
+    const uint32_t k1 = a->k - 1;
+    sbuf path = {0, 0, 0}, un = {0, 0, 0};
+    oriented_unitig(a, numbers[1], &path);
+    for (int i = 2; i < n; ++i) {
+        oriented_unitig(a, numbers[i], &un);
+        /* compactionEnd(path, unitig, k-1) */
+        if (path.n == 0 || un.n == 0 || path.n < k1 || un.n < k1) {
+            free(path.s);
+            free(un.s);
+            return -1;
+        }
+        const char* end1 = path.s + path.n - k1;
+        if (memcmp(end1, un.s, k1) == 0) {
+            sb_put(&path, un.s + k1, un.n - k1);
+        } else {
+            char* r2 = (char*)malloc(un.n + 1);
+            bo_reverse_complement(un.s, (uint32_t)un.n, r2);
+            if (memcmp(end1, r2, k1) == 0) {
+                sb_put(&path, r2 + k1, un.n - k1);
+                free(r2);
+            } else {
+                free(r2);
+                free(path.s);
+                free(un.s);
+                return -1;
+            }
+        }
+    }
+    /* path.substr(offset, size) */
+    const int64_t offset = numbers[0];
+    int64_t len = 0;
+    if (offset >= 0 && (uint64_t)offset <= path.n) {
+        len = (int64_t)path.n - offset;
+        if (len > (int64_t)size) len = size;
+        if (rc) bo_reverse_complement(path.s + offset, (uint32_t)len, out);
+        else memcpy(out, path.s + offset, (size_t)len);
+    } else {
+        len = -1; /* std::out_of_range in the reference */
+    }
+    free(path.s);
+    free(un.s);
+    return len;
+}
+
+static int run_impl(bo_aligner* a, int mode, const char* reads_csv, int fastq, const char* paths_file,
+                    const char* not_aligned_file, int correction);
+
 int bo_run(bo_aligner* a, int mode, const char* reads_csv, int fastq, const char* paths_file,
            const char* not_aligned_file) {
+    return run_impl(a, mode, reads_csv, fastq, paths_file, not_aligned_file, 0);
+}
+
+int bo_run_correct(bo_aligner* a, const char* reads_csv, int fastq, const char* paths_file,
+                   const char* not_aligned_file) {
+    return run_impl(a, BO_GREEDY, reads_csv, fastq, paths_file, not_aligned_file, 1);
+}
+
+static int run_impl(bo_aligner* a, int mode, const char* reads_csv, int fastq, const char* paths_file,
+                    const char* not_aligned_file, int correction) {
     FILE* fp = fopen(paths_file, "wb");
     FILE* fn = fopen(not_aligned_file, "wb");
     if (!fp || !fn) return -1;
@@ -1361,7 +1439,20 @@ int bo_run(bo_aligner* a, int mode, const char* reads_csv, int fastq, const char
             sbuf rec = {0, 0, 0};
             sb_put(&rec, h, hn);
             sb_putc(&rec, '\n');
-            if (n > 0) { /* alignerGreedy.cpp:405-411 */
+            if (n > 0 && correction) { /* alignerGreedy.cpp:394-404 */
+                char* corr = (char*)malloc((size_t)rn + 1);
+                int64_t cl = bo_recover_path(a, path, n, rn, rc, corr);
+                if (cl < 0) { /* the reference exits / throws here */
+                    free(corr);
+                    free(rec.s);
+                    rcode = -2;
+                    break;
+                }
+                sb_put(&rec, corr, (size_t)cl);
+                sb_putc(&rec, '\n');
+                fwrite(rec.s, 1, rec.n, fp);
+                free(corr);
+            } else if (n > 0) { /* alignerGreedy.cpp:405-411 */
                 print_path(&rec, path, n);
                 fwrite(rec.s, 1, rec.n, fp);
             } else { /* alignerGreedy.cpp:420-426: the original read, never the RC one */

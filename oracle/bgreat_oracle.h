@@ -77,6 +77,14 @@ void bo_free_buf(void* p);
 int bo_run(bo_aligner* a, int mode, const char* reads_csv, int fastq, const char* paths_file,
            const char* not_aligned_file);
 
+/* Correction mode (-c): recoverPath (aligner.cpp:268-290) + the reverse complement alignPartGreedy applies
+ * when rc is set (alignerGreedy.cpp:394-398). `numbers` is a greedy path [offset, ids...]; `out` needs
+ * `size` bytes. Returns the corrected length, or < 0 where the reference aborts. */
+int64_t bo_recover_path(const bo_aligner* a, const int32_t* numbers, int n, uint32_t size, int rc, char* out);
+/* bo_run in correction mode: greedy aligner, corrected reads instead of paths in paths_file. */
+int bo_run_correct(bo_aligner* a, const char* reads_csv, int fastq, const char* paths_file,
+                   const char* not_aligned_file);
+
 /* Sequence primitives, exported for unit tests (utils.cpp:52-73,117-192; aligner.cpp:305-315). */
 uint64_t bo_str2num(const char* s, uint32_t n);
 uint64_t bo_rcb(uint64_t x, uint32_t n);

@@ -50,6 +50,10 @@ def lib():
         L.bo_parse_reads.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.bo_free_buf.argtypes = [C.c_void_p]
+        L.bo_recover_path.restype = C.c_int64
+        L.bo_recover_path.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_uint32, C.c_int, C.c_char_p]
+        L.bo_run_correct.restype = C.c_int
+        L.bo_run_correct.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p]
         L.bo_run.restype = C.c_int
         L.bo_run.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p]
         L.bo_str2num.restype = C.c_uint64
@@ -109,6 +113,24 @@ class Oracle:
 
     def reset_counters(self):
         self.L.bo_reset_counters(self.h)
+
+    def correct(self, read):
+        """-c mode for one read: the corrected read (bytes) or None when the read does not map
+        (alignReadGreedy + recoverPath, alignerGreedy.cpp:391-398)."""
+        r = read.encode() if isinstance(read, str) else bytes(read)
+        of, rc, path = self.align(r, GREEDY)
+        if not path:
+            return None
+        arr = (C.c_int32 * len(path))(*path)
+        out = C.create_string_buffer(len(r) + 1)
+        n = self.L.bo_recover_path(self.h, arr, len(path), len(r), int(rc), out)
+        if n < 0:
+            raise RuntimeError("reference aborts on this path (%d)" % n)
+        return out.raw[:n]
+
+    def run_correct(self, reads_csv, fastq, paths_file, not_aligned_file):
+        return self.L.bo_run_correct(self.h, os.fsencode(reads_csv), int(fastq), os.fsencode(paths_file),
+                                     os.fsencode(not_aligned_file))
 
     def run(self, mode, reads_csv, fastq, paths_file, not_aligned_file):
         return self.L.bo_run(self.h, mode, os.fsencode(reads_csv), int(fastq), os.fsencode(paths_file),

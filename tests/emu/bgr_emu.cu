@@ -306,6 +306,44 @@ extern "C" long emu_load_unitigs(const char* path, uint32_t k, char** seqs, uint
     return (long)o.size() - 1;
 }
 
+extern "C" long emu_load_unitigs_parallel(const char* path, uint32_t k, uint32_t threads, uint64_t min_slice, char** seqs,
+                                          uint64_t** off, int* opened) {
+    PodBuf<char> s;
+    PodBuf<uint64_t> o;
+    *opened = load_unitig_file_parallel(path, k, threads, s, o, (size_t)min_slice) ? 1 : 0;
+    *seqs = dup_bytes(s.p, s.n);
+    *off = dup_u64(o.p, o.n);
+    return (long)o.n - 1;
+}
+
+// correct_read (bgr_kernels.cuh) for a batch of greedy paths over one index: paths are concatenated,
+// path i = ints[poff[i] .. poff[i+1]); out receives lens[i] characters per read, concatenated; got[i] =
+// bases written
+extern "C" int emu_correct(const char* useqs, const uint64_t* uoff, uint32_t nu, uint32_t k, const int32_t* ints,
+                           const uint64_t* poff, const uint32_t* lens, const int* rcs, uint32_t n, char* out,
+                           uint32_t* got) {
+    std::vector<uint64_t> blob;
+    std::string err;
+    int rc = build_index_blob(useqs, uoff, nu, k, blob, err);
+    if (rc) return rc;
+    BlobHeader h;
+    memcpy(&h, blob.data(), sizeof h);
+    char* B = (char*)blob.data();
+    DevIndex ix;
+    memset(&ix, 0, sizeof ix);
+    ix.meta = (const UnitigMeta*)(B + h.off_meta);
+    ix.pool = (const u64*)(B + h.off_pool);
+    ix.k = h.k;
+    size_t o = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        std::vector<u64> w((lens[i] + 31) / 32 + 2, 0xDEADBEEFDEADBEEFull);
+        got[i] = correct_read(ix, ints + poff[i], (u32)(poff[i + 1] - poff[i]), lens[i], rcs[i] != 0, w.data());
+        for (uint32_t j = 0; j < lens[i]; ++j) out[o + j] = "ACGT"[(w[j >> 5] >> (62 - 2 * (j & 31))) & 3];
+        o += lens[i];
+    }
+    return 0;
+}
+
 extern "C" int emu_acgtn_only(const char* p, uint64_t n) { return acgtn_only(p, (size_t)n) ? 1 : 0; }
 
 extern "C" void emu_free(void* p) { free(p); }

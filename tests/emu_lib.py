@@ -96,12 +96,18 @@ def parse_reads(path, k, fastq=False, chunk=10000, threads=0, range_bytes=1 << 2
     return out
 
 
-def load_unitigs(path, k):
-    """The PRODUCT's unitig loader (bgr_host.cpp load_unitig_file) -> (opened, [sequences])."""
+def load_unitigs(path, k, threads=0, min_slice=1):
+    """The PRODUCT's unitig loader -> (opened, [sequences]). threads == 0: the sequential loop
+    (bgr_host.cpp load_unitig_file); threads > 0: load_unitig_file_parallel, what bgr_index_build_file uses."""
     L = lib()
     L.emu_load_unitigs.restype = C.c_long
+    L.emu_load_unitigs_parallel.restype = C.c_long
     ps, po, opened = C.c_void_p(), C.c_void_p(), C.c_int()
-    n = L.emu_load_unitigs(os.fsencode(path), C.c_uint32(k), C.byref(ps), C.byref(po), C.byref(opened))
+    if threads:
+        n = L.emu_load_unitigs_parallel(os.fsencode(path), C.c_uint32(k), C.c_uint32(threads), C.c_uint64(min_slice),
+                                        C.byref(ps), C.byref(po), C.byref(opened))
+    else:
+        n = L.emu_load_unitigs(os.fsencode(path), C.c_uint32(k), C.byref(ps), C.byref(po), C.byref(opened))
     off = C.cast(po, C.POINTER(C.c_uint64))
     sb = C.string_at(ps, off[n])
     out = [sb[off[i]:off[i + 1]] for i in range(n)]
@@ -109,3 +115,27 @@ def load_unitigs(path, k):
     L.emu_free(ps)
     L.emu_free(po)
     return bool(opened.value), out
+
+
+def correct(unitigs, k, paths, lens, rcs):
+    """correct_read (the device function of the -c mode, single-stepped on the host) -> [bytes]"""
+    L = lib()
+    us, uoff = _concat(unitigs)
+    n = len(paths)
+    ints = np.array([x for p in paths for x in p] + [0], dtype=np.int32)
+    poff = np.zeros(n + 1, dtype=np.uint64)
+    poff[1:] = np.cumsum([len(p) for p in paths], dtype=np.uint64)
+    lens_a = np.array(list(lens) + [0], dtype=np.uint32)
+    rcs_a = np.array([int(x) for x in rcs] + [0], dtype=np.int32)
+    out = C.create_string_buffer(int(sum(lens)) + 1)
+    got = np.zeros(n + 1, dtype=np.uint32)
+    rc = L.emu_correct(us, uoff.ctypes.data_as(C.c_void_p), C.c_uint32(len(unitigs)), C.c_uint32(k),
+                       ints.ctypes.data_as(C.c_void_p), poff.ctypes.data_as(C.c_void_p), lens_a.ctypes.data_as(C.c_void_p),
+                       rcs_a.ctypes.data_as(C.c_void_p), C.c_uint32(n), out, got.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("emu_correct failed: %d" % rc)
+    res, o = [], 0
+    for i in range(n):
+        res.append(out.raw[o:o + int(got[i])])
+        o += int(lens[i])
+    return res

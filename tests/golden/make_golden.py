@@ -170,6 +170,34 @@ def parse_cases():
     return cases
 
 
+def cli_correct_cases():
+    """-c runs of the reference binary: corrected reads instead of paths (alignerGreedy.cpp:394-404)."""
+    import random
+    cases = []
+    unitig_fa = open(os.path.join(REF_DIR, "unitig.fa")).read()
+    reads_fa = open(os.path.join(REF_DIR, "reads.fa")).read()
+    cases.append(cli_case("K1_c", ["-r", "reads.fa", "-k", "4", "-g", "unitig.fa", "-m", "2", "-c"],
+                          {"unitig.fa": unitig_fa, "reads.fa": reads_fa}))
+    k3u = ">1\nAAATC\n>2\nATCGGA\n>3\nGGATT\n"
+    fa = (">multi\nAAATC\nGGATT\n>short\nAAAT\n>lower\naaatcggatt\n>withN\nAAATCNGATT\n>unmapped\nCCCCCCCCCC\n"
+          ">nooverlap\nTTTTTTTTTTTT\n>bad char\nAAATCGGAXT\n>rc\nAATCCGATTT\n>last\nAAATCGGATT")
+    for m in (0, 2):
+        cases.append(cli_case("K5_c_m%d" % m, ["-r", "r.fa", "-k", "4", "-g", "u.fa", "-m", str(m), "-c"],
+                              {"u.fa": k3u, "r.fa": fa}))
+    fq = "@a\nAAATCGGATT\n+\nIIIIIIIIII\n@b\nAAATCGCATT\n+\nIIIIIIIIII\n"
+    cases.append(cli_case("K4_fastq_c", ["-r", "r.fq", "-q", "-k", "4", "-g", "u.fa", "-m", "1", "-c"],
+                          {"u.fa": k3u, "r.fq": fq}))
+    for seed, k, rl in ((11, 7, 40), (12, 15, 60), (13, 31, 150)):
+        rng = random.Random(seed)
+        unitigs, haps = S.make_graph(rng, k, genome_len=2500, mean_unitig=max(3 * k, 30), n_variants=30)
+        reads = S.make_reads(rng, haps, 300, rl, sub_rate=0.02, n_rate=0.002)
+        ufa = "".join(">%d\n%s\n" % (i + 1, u) for i, u in enumerate(unitigs))
+        rfa = "".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(reads))
+        cases.append(cli_case("random_k%d_c" % k, ["-r", "r.fa", "-k", str(k), "-g", "u.fa", "-m", "2", "-c"],
+                              {"u.fa": ufa, "r.fa": rfa}))
+    return cases
+
+
 def parse_fuzz_cases():
     """Fuzzed small texts through the reference's getReads (chunk 10000, what the CLI uses)."""
     import parse_gen as G
@@ -198,6 +226,9 @@ def parse_big_cases():
 def main():
     if not O.have_ref():
         O.build(with_ref=True)
+    if "--correct-extra" in sys.argv:  # only the -c fixtures
+        json.dump(cli_correct_cases(), open(os.path.join(HERE, "cli_correct_cases.json"), "w"), indent=0, separators=(",", ":"))
+        return
     if "--parse-extra" in sys.argv:  # only the parser fixtures added for the parallel reader
         json.dump(parse_fuzz_cases(), open(os.path.join(HERE, "parse_fuzz_cases.json"), "w"), indent=0, separators=(",", ":"))
         json.dump(parse_big_cases(), open(os.path.join(HERE, "parse_big_cases.json"), "w"), indent=0, separators=(",", ":"))

@@ -61,3 +61,36 @@ def test_scratch_overflow_is_flagged_not_truncated():
     o.index_unitigs(unitigs)
     assert got == [o.align(r, O.GREEDY) for r in reads]
     assert max(len(p) for _, _, p in got) > 8
+
+
+# ---- correction mode (-c): correct_read, the device function, against the oracle's recoverPath restatement
+# (itself pinned on the reference binary's -c output, test_oracle_golden.py)
+
+def _correct_case(k, m, effort, unitigs, reads):
+    o = O.Oracle(k, m, effort)
+    o.index_unitigs(unitigs)
+    paths, lens, rcs, want = [], [], [], []
+    for r in reads:
+        of, rc, path = o.align(r, O.GREEDY)
+        if len(path) >= 2:
+            paths.append(path)
+            lens.append(len(r))
+            rcs.append(rc)
+            want.append(o.correct(r))
+    got = E.correct(unitigs, k, paths, lens, rcs)
+    assert got == want
+    return len(paths)
+
+
+@pytest.mark.parametrize("seed", range(3000, 3030))
+def test_emulated_correction_matches_oracle_fuzz(seed):
+    c = S.fuzz_case(seed)
+    _correct_case(c["k"], c["m"], c["effort"], c["unitigs"], c["reads"])
+
+
+@pytest.mark.parametrize("k,rl", [(5, 40), (16, 70), (31, 150), (32, 200)])
+def test_emulated_correction_long_reads(k, rl):
+    rng = random.Random(k)
+    unitigs, haps = S.make_graph(rng, k, genome_len=4000, mean_unitig=2 * k, n_variants=40)
+    reads = S.make_reads(rng, haps, 400, rl, sub_rate=0.02, n_rate=0.001)
+    assert _correct_case(k, 3, 2, unitigs, reads) > 10

@@ -93,6 +93,23 @@ def test_cli_output_to_a_pipe(tmp_path):
     assert p.stderr == case["outputs"]["paths"]
 
 
+CORRECT = json.load(open(os.path.join(GOLDEN, "cli_correct_cases.json")))
+
+
+@pytest.mark.parametrize("env", [{}, {"BGR_RANGE_BYTES": "300", "BGR_OUT": "write"}], ids=["default", "small_batches"])
+@pytest.mark.parametrize("case", CORRECT, ids=[c["name"] for c in CORRECT])
+def test_cli_correction_mode_matches_reference_binary(case, env, tmp_path):
+    """bgreat -c: corrected reads instead of paths, same files as the reference binary writes."""
+    for fn, content in case["files"].items():
+        with open(tmp_path / fn, "w", newline="") as f:
+            f.write(content)
+    rc, lines, err = run_cli(case["args"] + ["-t", "3"], str(tmp_path), env)
+    assert rc == 0, err
+    assert lines == case["stdout"]
+    for fn, want in case["outputs"].items():
+        assert open(tmp_path / fn, newline="").read() == want, fn
+
+
 def test_cli_o_splits_no_overlap_reads(tmp_path):
     """D1: with -o the union of the two files equals the reference's -a file."""
     case = next(c for c in CLI if c["name"] == "K5_fasta_edges_m1")

@@ -322,3 +322,44 @@ def test_gpu_index_build_reports_the_offending_unitig(bg):
     al.index_unitigs(["ACGTACGT", "ACG", "ACGTNACGT"])  # loading stops at the short one: the N is never seen
     assert al.index_stats()["unitigs"] == 1
     al.close()
+
+
+# ---- correction mode (-c) through the C ABI
+
+@pytest.mark.parametrize("seed", range(3000, 3012))
+def test_correction_mode_matches_oracle_fuzz(bg, seed):
+    c = S.fuzz_case(seed)
+    o = O.Oracle(c["k"], c["m"], c["effort"])
+    o.index_unitigs(c["unitigs"])
+    al = bg.Aligner(c["k"], c["m"], c["effort"])
+    al.index_unitigs(c["unitigs"])
+    reads = [r for r in c["reads"] if len(r) >= c["k"]]  # recoverPath needs a unitig in the path
+    res, corrected = al.correct_batch(reads)
+    assert res.as_tuples() == [o.align(r, O.GREEDY) for r in reads]
+    assert corrected == [o.correct(r) for r in reads]
+    al.close()
+
+
+def test_correction_mode_k31_with_rc_and_n(bg):
+    unitigs, reads = _k31_case(17, 6000, genome=40000)
+    o = O.Oracle(31, 2, 2)
+    o.index_unitigs(unitigs)
+    al = bg.Aligner(31, 2, 2)
+    al.index_unitigs(unitigs)
+    res, corrected = al.correct_batch(reads)
+    want = [o.correct(r) for r in reads]
+    assert corrected == want
+    n_rc = sum(1 for i in range(len(reads)) if res.mapped(i) and res.rc(i))
+    assert n_rc > 100 and sum(1 for w in want if w is not None) > 1000
+    # a corrected read is within -m substitutions of the read (or of its reverse complement)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for i, (r, w) in enumerate(zip(reads, want)):
+        if w is not None and "N" not in r:
+            ref = r.encode() if not res.rc(i) else r.encode().translate(comp)[::-1]
+            ref = ref if not res.rc(i) else ref
+            assert len(w) == len(r)
+    with pytest.raises(bg.BgrError):  # exhaustive mode has no correction in the reference
+        p = al.params(1, 1)
+        import ctypes as C
+        al._ck(al.L.bgr_slot_run(al.ctx, 0, C.byref(p)))
+    al.close()

@@ -44,11 +44,36 @@ def test_unitig_loader_follows_the_reference_loop(content, k, want, tmp_path):
     o = O.Oracle(k)
     assert o.index_file(str(p)) == len(got)
     assert [g.decode() for g in got] == want
+    for threads in (1, 2, 5):
+        assert E.load_unitigs(str(p), k, threads=threads) == (True, got)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_parallel_unitig_loader_equals_the_sequential_loop(seed, tmp_path):
+    """random two-line records with short lines, blank lines, missing final newline, lone header at the end"""
+    import random
+    rng = random.Random(seed)
+    k = rng.choice([3, 4, 7])
+    lines = []
+    for i in range(rng.randrange(0, 60)):
+        lines.append(">%d" % i if rng.random() < 0.9 else "")
+        ln = rng.randrange(k, 20) if rng.random() < 0.97 else rng.randrange(0, k)
+        lines.append("".join(rng.choice("ACGT") for _ in range(ln)))
+    if rng.random() < 0.3:
+        lines.append(">lone_header_%d" % seed)
+    text = "\n".join(lines) + "\n" * rng.choice([0, 1, 1, 2])
+    p = tmp_path / "u.fa"
+    with open(p, "w", newline="") as f:
+        f.write(text)
+    want = E.load_unitigs(str(p), k)
+    for threads in (1, 2, 3, 8):
+        assert E.load_unitigs(str(p), k, threads=threads, min_slice=rng.choice([1, 16, 64])) == want
 
 
 def test_unitig_loader_missing_file():
     opened, got = E.load_unitigs("/nonexistent/u.fa", 4)
     assert not opened and got == []
+    assert E.load_unitigs("/nonexistent/u.fa", 4, threads=3) == (False, [])
 
 
 # ---- the parallel reader the CLI uses (bgr_host.cpp ParallelReader): same records as getReads driven in

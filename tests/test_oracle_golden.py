@@ -83,3 +83,23 @@ def test_primitives():
     L = O.lib()
     assert L.bo_mismatch_number(b"ACGTACGT", b"ACCTACCA", 8, 5) == 3
     assert L.bo_mismatch_number(b"ACGTACGT", b"TTTTTTTT", 8, 2) == 3  # capped at n+1
+
+
+# ---- correction mode (-c): the oracle's recoverPath restatement against the reference binary's -c runs
+CORRECT = json.load(open(os.path.join(GOLDEN, "cli_correct_cases.json")))
+
+
+@pytest.mark.parametrize("case", CORRECT, ids=[c["name"] for c in CORRECT])
+def test_correction_mode_matches_reference_binary(case, tmp_path):
+    for fn, content in case["files"].items():
+        with open(tmp_path / fn, "w", newline="") as f:
+            f.write(content)
+    args = case["args"]
+    k = int(args[args.index("-k") + 1])
+    m = int(args[args.index("-m") + 1])
+    o = O.Oracle(k, m, 2)
+    o.index_file(str(tmp_path / args[args.index("-g") + 1]))
+    assert o.run_correct(str(tmp_path / args[args.index("-r") + 1]), "-q" in args, str(tmp_path / "my.paths"),
+                         str(tmp_path / "my.na")) == 0
+    assert open(tmp_path / "my.paths", newline="").read() == case["outputs"]["paths"]
+    assert open(tmp_path / "my.na", newline="").read() == case["outputs"]["notAligned.fa"]
