@@ -24,6 +24,7 @@
 //                                     significant bits (same digit order as str2num, utils.cpp:117)
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #if defined(__CUDACC__)
 #define BGR_HD __host__ __device__ __forceinline__
@@ -166,12 +167,21 @@ inline u64 bloom_words_for(u64 n_keys, bool& two_hashes) {
         if (w > BLOOM_SMEM_WORDS) w = BLOOM_SMEM_WORDS;
         return w;
     }
-    // global tier: 16 bytes per key while that stays within 64 MB (L2-resident), never below 2 bytes per key
+    // global tier: 16 bytes per key while that stays within the cap, never below 2/3 byte per key (about 8 %
+    // false positives). The cap is what stays L2-resident next to the read stream: the B200's 126 MB L2
+    // is two partitions that each hold their own copy of read-shared lines, so a 64 MB filter already
+    // misses 40 % of its probes (profiles/r01_ncu_k_scan_tiles_v5_1Gbp.txt) while 32 MB does not.
     two_hashes = true;
+    u64 cap_mb = 32;  // BGR_BLOOM_MB: experiment hook
+    if (n_keys > (20ull << 20)) cap_mb = 64;  // beyond ~20 M keys the false positives cost more than the misses (3 Gbp: 64 MB wins)
+    if (const char* e = getenv("BGR_BLOOM_MB")) {
+        const long v = atol(e);
+        if (v > 0) cap_mb = (u64)v;
+    }
     u64 w = 4 * n_keys;
-    const u64 l2_words = 16ull << 20;
-    if (w > l2_words) w = l2_words;
-    if (w < n_keys / 2) w = n_keys / 2;
+    const u64 cap_words = cap_mb << 18;
+    if (w > cap_words) w = cap_words;
+    if (w < n_keys / 6) w = n_keys / 6;
     return w;
 }
 

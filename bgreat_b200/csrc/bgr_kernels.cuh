@@ -510,21 +510,22 @@ BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, u32 km1, u64 w0, u64 w1, u3
     u64 rc = rcb(num, km1);
     u64 inc = (w0 << (2 * km1)) | (w1 >> sh);  // the bases that follow the first window
     u32 hits = 0;
+    // All 32 window slots are tested, the slots past `count` are dropped at the end: no branch per
+    // window, so the filter loads of several windows are in flight together (a slot past the end reads
+    // some valid filter word: the index is always < n_bloom).
 #pragma unroll
     for (u32 j = 0; j < 32; ++j) {
-        if (j < count) {
-            const u64 rep = num < rc ? num : rc;
-            const u32 h1 = bloom_h1(rep);
-            const u32 m = bloom_mask(TWO ? (bloom_h2(rep) >> 17) : h1);
-            const u32 w = bloom[bloom_word_of(h1, n_bloom)];
-            if ((w & m) == m) hits |= 1u << j;
-        }
+        const u64 rep = num < rc ? num : rc;
+        const u32 h1 = bloom_h1(rep);
+        const u32 m = bloom_mask(TWO ? (bloom_h2(rep) >> 17) : h1);
+        const u32 w = bloom[bloom_word_of(h1, n_bloom)];
+        hits |= ((w & m) == m ? 1u : 0u) << j;
         const u64 nb = inc >> 62;
         inc <<= 2;
         num = ((num << 2) | nb) & mask;
         rc = (rc >> 2) | ((3 - nb) << top);
     }
-    return hits;
+    return count >= 32 ? hits : hits & ((1u << count) - 1);
 }
 
 // The windows that passed the filter, checked against the key table: the returned mask is exact.
