@@ -89,10 +89,15 @@ struct BatchArgs {
     u32 tile_r;      // reads per tile of the tile kernel (even, <= ST_MAX_R)
     u32 tile_cb;     // bytes of one character buffer of the tile kernel
     u32 errors, effort, mode;
+    u32 ext_lazy;  // greedy extension: lanes that must wait before hand-in / refill / seed selection run
     u64* corr;  // correction mode (-c): corrected reads, 2 bits per base, read r at word corrected_word_base(off[r], r)
 };
 
 static const u32 INFO_HAS_N = 1u, INFO_HIT1 = 2u, INFO_HIT2 = 4u;
+// internal bit of bgr_result.flags_len between the greedy kernel and the path compaction: the first
+// entries of the scratch row are pathBegin in walk order (count in the row's last entry) and must be
+// reversed on the way into the pool. Never leaves the device.
+static const u32 RES_REV_HEAD = 0x08u;
 
 // ------------------------------------------------------------------------------ helpers
 
@@ -1243,13 +1248,11 @@ struct GreedyState {
         pos = seed_pos;
     }
 
-    // One turn of the loop = one level of a walk: (pick a seed if needed) -> query the index ->
-    // compare the <= 4 candidates -> settle. Every lane of a warp runs these same stages every turn.
-    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+    // Seed selection, possibly switching to the reverse-complement pass: needed once per seed, i.e. rarely
+    // compared with the levels of a walk, so the kernel runs it for several lanes at once (see k_extend_greedy).
+    BGR_HD void pick_seed(const DevIndex& ix, const BatchArgs& a) {
         ReadView& v = s.v;
-        const i64 km1 = ix.k - 1;
         const u32 max_seeds = a.effort ? a.effort : 1;
-        // ---- next seed (possibly switching to the reverse-complement pass)
         for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
             i32 p = tried < max_seeds ? it.next() : -1;
             if (p >= 0) {
@@ -1275,6 +1278,18 @@ struct GreedyState {
                 phase = GP_DONE;
             }
         }
+    }
+
+    // One turn of the loop = one level of a walk: query the index -> compare the <= 4 candidates ->
+    // settle. Every lane of a warp that holds a seed runs these same stages every turn.
+    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+        if (phase == GP_SEED) pick_seed(ix, a);
+        if (phase != GP_SEED && phase != GP_DONE) step_level(ix, a);
+    }
+
+    BGR_HD void step_level(const DevIndex& ix, const BatchArgs& a) {
+        ReadView& v = s.v;
+        const i64 km1 = ix.k - 1;
         // ---- ends of walks that need no index query
         if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
             sc.set(n++, 0);
@@ -1369,6 +1384,18 @@ struct GreedyState {
             sc.set(i, y);
             sc.set(j, x);
         }
+        return n;
+    }
+    // Kernel form: pathBegin stays in walk order; its length goes into the last scratch entry and
+    // k_path_gather reverses it while copying the path into the pool (the in-place loop above runs with
+    // a few lanes of a warp active). The caller sets RES_REV_HEAD in the result's flags.
+    BGR_HD u32 finish_deferred() {
+        if (!(flags & BGR_F_MAPPED) || sc.overflow) return 0;
+        if (n + 1 > sc.cap) {
+            sc.overflow = true;
+            return 0;
+        }
+        sc.set(sc.cap - 1, (i32)nl);
         return n;
     }
 };
@@ -1967,45 +1994,54 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
     bool dry = false;                    // the list has no more chunks
     u32 n_al = 0, n_na = 0, n_no = 0;
     bool any_overflow = false;
+    // Hand-in, refill and seed selection are needed once or twice per read while a walk has several
+    // levels: run per lane as soon as it is due, every turn pays for them with a handful of lanes
+    // active (profiles/r01_ncu_k_extend_greedy_v5_5Mbp.txt: 8 of 32 threads per instruction). They are
+    // therefore serviced together, once `lazy` lanes wait for them (or nobody can walk).
+    const u32 lazy = a.ext_lazy ? a.ext_lazy : 1;
     for (;;) {
-        const bool fin = have && g.done();
-        if (fin) {  // hand in
-            const u32 plen = g.finish();
-            any_overflow |= g.sc.overflow;
-            bgr_result res;
-            res.flags_len = (g.flags & 0xFFu) | (plen << 8);
-            res.path_off = t;
-            a.res[r] = res;
-            n_al += (g.flags & BGR_F_CNT_ALIGNED) != 0;
-            n_na += (g.flags & BGR_F_CNT_NOTALIGNED) != 0;
-            n_no += (g.flags & BGR_F_CNT_NOOVERLAP) != 0;
-            have = false;
-        }
-        const u32 want = __ballot_sync(0xFFFFFFFFu, !have);
-        if (want) {
-            if (chunk_left == 0 && !dry) {
-                u32 base = 0;
-                if (lane == 0) base = atomicAdd(&a.cnt->ext_cursor, 32u);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (base >= list_n) dry = true;
-                else {
-                    chunk_base = base;
-                    chunk_left = min(32u, list_n - base);
+        const bool walking = have && g.phase != GP_DONE && g.phase != GP_SEED;
+        const u32 waiting = __ballot_sync(0xFFFFFFFFu, !walking);
+        if ((u32)__popc(waiting) >= lazy || waiting == 0xFFFFFFFFu) {
+            if (have && g.done()) {  // hand in
+                const u32 plen = g.finish_deferred();
+                any_overflow |= g.sc.overflow;
+                bgr_result res;
+                res.flags_len = (g.flags & 0xFFu) | (plen ? RES_REV_HEAD : 0u) | (plen << 8);
+                res.path_off = t;
+                a.res[r] = res;
+                n_al += (g.flags & BGR_F_CNT_ALIGNED) != 0;
+                n_na += (g.flags & BGR_F_CNT_NOTALIGNED) != 0;
+                n_no += (g.flags & BGR_F_CNT_NOOVERLAP) != 0;
+                have = false;
+            }
+            const u32 want = __ballot_sync(0xFFFFFFFFu, !have);
+            if (want) {
+                if (chunk_left == 0 && !dry) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&a.cnt->ext_cursor, 32u);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= list_n) dry = true;
+                    else {
+                        chunk_base = base;
+                        chunk_left = min(32u, list_n - base);
+                    }
                 }
+                const u32 rank = __popc(want & ((1u << lane) - 1));
+                if (!have && rank < chunk_left) {
+                    t = chunk_base + rank;
+                    r = a.list[t];
+                    g.start(ix, a, r, a.scratch + t);
+                    have = true;
+                }
+                const u32 taken = min((u32)__popc(want), chunk_left);
+                chunk_base += taken;
+                chunk_left -= taken;
+                if (dry && want == 0xFFFFFFFFu) break;  // nobody holds a read and nothing is left
             }
-            const u32 rank = __popc(want & ((1u << lane) - 1));
-            if (!have && rank < chunk_left) {
-                t = chunk_base + rank;
-                r = a.list[t];
-                g.start(ix, a, r, a.scratch + t);
-                have = true;
-            }
-            const u32 taken = min((u32)__popc(want), chunk_left);
-            chunk_base += taken;
-            chunk_left -= taken;
-            if (dry && want == 0xFFFFFFFFu) break;  // nobody holds a read and nothing is left
+            if (have && g.phase == GP_SEED) g.pick_seed(ix, a);
         }
-        if (have && !g.done()) g.step(ix, a);
+        if (have && g.phase != GP_DONE && g.phase != GP_SEED) g.step_level(ix, a);
     }
     if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
     count_classes(a, n_al, n_na, n_no);
@@ -2101,7 +2137,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const u
     u32 len[CP_PER_THREAD], v = 0;
 #pragma unroll
     for (int j = 0; j < CP_PER_THREAD; ++j) {
-        len[j] = (r0 + j < a.n) ? a.res[r0 + j].flags_len >> 8 : 0;
+        len[j] = (r0 + j < a.n) ? (a.res[r0 + j].flags_len & ~RES_REV_HEAD) >> 8 : 0;
         v += len[j];
     }
     u32 total;
@@ -2110,11 +2146,15 @@ __global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const u
     for (int j = 0; j < CP_PER_THREAD; ++j) {
         if (len[j]) {
             const u32 r = r0 + j;
-            const u32 t = a.res[r].path_off;  // scratch row
-            const i32* src = a.scratch + t;
+            bgr_result res = a.res[r];
+            const i32* src = a.scratch + res.path_off;  // scratch row
             i32* dst = a.pool + off;
-            for (u32 q = 0; q < len[j]; ++q) dst[q] = src[(size_t)q * a.n];
-            a.res[r].path_off = (u32)off;
+            // pathBegin was pushed walking away from the seed: reverse(pathBegin) (alignerGreedy.cpp:48)
+            const u32 nl = (res.flags_len & RES_REV_HEAD) ? (u32)src[(size_t)(a.scratch_ints - 1) * a.n] : 0u;
+            for (u32 q = 0; q < len[j]; ++q) dst[q] = src[(size_t)(q < nl ? nl - 1 - q : q) * a.n];
+            res.flags_len &= ~RES_REV_HEAD;
+            res.path_off = (u32)off;
+            a.res[r] = res;
             off += len[j];
         }
     }

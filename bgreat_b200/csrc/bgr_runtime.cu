@@ -205,6 +205,8 @@ BatchArgs make_args(Slot& s) {
     a.errors = s.params.errors;
     a.effort = s.params.effort;
     a.mode = s.params.mode;
+    a.ext_lazy = 8;
+    if (const char* e = getenv("BGR_EXT_LAZY")) a.ext_lazy = (u32)std::max(1, std::min(32, atoi(e)));
     a.corr = s.d_corr;
     return a;
 }
