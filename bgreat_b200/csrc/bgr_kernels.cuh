@@ -1621,6 +1621,212 @@ BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratc
     return flags | BGR_F_CNT_NOTALIGNED;
 }
 
+// ---- the same search as a resumable state machine: one turn = one node of the depth-first search
+// (index query -> candidate compares until one is worth descending into -> descend or return). This is
+// what the persistent kernel runs: lanes of a warp are at different nodes of different searches but
+// execute the same body every turn. exhaustive_read above is the loop-shaped statement of the same
+// procedure; tests/emu runs both and compares.
+enum { XP_SEED = 0, XP_LEFT = 1, XP_RIGHT = 2, XP_DONE = 3 };
+
+struct ExhaustiveState {
+    ReadSetup s;
+    Scratch sc;
+    SeedIter it;
+    DfsLayout lay;
+    u32 flags, phase, n;
+    // current seed
+    u64 seed_c;
+    i32 seed_pos;
+    u32 w, eb;  // ints of the final path written so far; mismatches spent on the left side
+    // current search (one side)
+    u32 budget, best_total, best_n;
+    i32 term, depth;
+    // top frame, kept in registers; the frames below it live in the scratch row
+    u64 f_code;
+    i32 f_pos;
+    u32 f_acc, f_next;
+
+    BGR_HD bool done() const { return phase == XP_DONE; }
+
+    BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
+        s = setup_read(ix, a, r);
+        sc.base = scratch_row;
+        sc.stride = a.n;
+        sc.cap = a.scratch_ints;
+        sc.overflow = false;
+        lay.init(a.scratch_ints);
+        flags = BGR_F_OVERLAP_FOUND;
+        n = 0;
+        w = eb = 0;
+        phase = XP_SEED;
+        seed_c = 0;
+        seed_pos = 0;
+        budget = best_total = best_n = 0;
+        term = -1;
+        depth = -1;
+        f_code = 0;
+        f_pos = 0;
+        f_acc = f_next = 0;
+        const u32 km1 = ix.k - 1;
+        it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, s.nwin);
+        if (s.nwin == 0) {  // shorter than k-1: see DESIGN.md
+            flags |= BGR_F_CNT_NOTALIGNED;
+            phase = XP_DONE;
+        } else if ((u32)s.v.len == km1) {  // single window, nothing on either side: [0, 0]
+            sc.set(0, 0);
+            sc.set(1, 0);
+            n = 2;
+            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+            phase = XP_DONE;
+        }
+    }
+
+    BGR_HD void begin_side(bool right, u32 budget_) {
+        phase = right ? XP_RIGHT : XP_LEFT;
+        budget = budget_;
+        best_total = budget_ + 1;
+        best_n = 0;
+        term = -1;
+        depth = 0;
+        f_code = seed_c;
+        f_pos = seed_pos;
+        f_acc = 0;
+        f_next = 0;
+    }
+
+    // alignReadExhaustive's loop header (alignerExhaustive.cpp:41): the next window that can be a seed
+    BGR_HD void pick_seed(const DevIndex& ix, const BatchArgs& a) {
+        if (phase != XP_SEED) return;
+        const i32 p = it.next();
+        if (p < 0) {
+            n = 0;
+            flags |= BGR_F_CNT_NOTALIGNED;
+            phase = XP_DONE;
+            return;
+        }
+        seed_pos = p;
+        seed_c = seed_code(ix, s.v, p);
+        w = 0;
+        eb = 0;
+        if (p == 0) {
+            sc.set(w++, 0);  // checkBeginExhaustive:159
+            begin_side(true, a.errors);
+        } else {
+            begin_side(false, a.errors);
+        }
+    }
+
+    BGR_HD void pop_frame() {
+        --depth;
+        if (depth >= 0) {
+            const u32 b = lay.fr0 + 5 * (u32)depth;
+            f_code = (u64)(u32)sc.get(b) | ((u64)(u32)sc.get(b + 1) << 32);
+            f_pos = sc.get(b + 2);
+            f_acc = (u32)sc.get(b + 3);
+            f_next = (u32)sc.get(b + 4);
+        }
+    }
+
+    // the side's search is over: left -> store its part of the path and search the right side;
+    // right -> the read is mapped. A side without a walk within the budget fails the seed.
+    BGR_HD void side_finished(const BatchArgs& a) {
+        const bool ok = best_total <= budget;
+        if (!ok || sc.overflow) {
+            if (sc.overflow) {  // the host re-runs the batch with a larger scratch
+                n = 0;
+                flags |= BGR_F_CNT_NOTALIGNED;
+                phase = XP_DONE;
+            } else {
+                phase = XP_SEED;
+            }
+            return;
+        }
+        if (phase == XP_LEFT) {
+            // left part in output order: [offset] then the ids from the far end to the anchor
+            if (term >= 0) sc.set(w++, term);
+            for (u32 j = 0; j < best_n; ++j) sc.set(w++, sc.get(lay.best0 + best_n - 1 - j));
+            eb = best_total;
+            begin_side(true, a.errors - eb);
+        } else {
+            for (u32 j = 0; j < best_n; ++j) sc.set(w++, sc.get(lay.best0 + j));
+            sc.set(w++, term);
+            n = w;
+            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+            phase = XP_DONE;
+        }
+    }
+
+    // one node of the search (the body of exhaustive_side's while loop)
+    BGR_HD void step_node(const DevIndex& ix, const BatchArgs& a) {
+        const ReadView& v = s.v;
+        const i64 km1 = ix.k - 1;
+        const bool right = phase == XP_RIGHT;
+        const i32 rl = right ? v.len - (f_pos + (i32)km1) : f_pos;
+        if (rl == 0) {
+            if (f_acc < best_total) {
+                best_total = f_acc;
+                best_n = (u32)depth;
+                term = right ? 0 : -1;
+                for (u32 j = 0; j < best_n; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+            }
+            pop_frame();
+        } else {
+            const Cands c = index_query(ix, f_code, !right);
+            bool descended = false;
+            for (u32 i = f_next; i < (u32)c.n; ++i) {
+                if (f_acc >= best_total) break;  // nothing below can be strictly better
+                const Oriented u = orient(ix, c, (int)i);
+                const i64 L = u.len - km1;
+                const u32 cap = best_total - 1 - f_acc;
+                if (L >= rl) {
+                    const u32 miss = right ? mismatches(ix, v, u, km1, f_pos + (i32)km1, rl, cap)
+                                           : mismatches(ix, v, u, L - rl, 0, rl, cap);
+                    if (miss <= cap) {
+                        best_total = f_acc + miss;
+                        best_n = (u32)depth + 1;
+                        term = right ? rl + (i32)km1 : (i32)(L - rl);
+                        for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+                        sc.set(lay.best0 + (u32)depth, u.sid);
+                    }
+                } else {
+                    const u32 miss = right ? mismatches(ix, v, u, km1, f_pos + (i32)km1, (i32)L, cap)
+                                           : mismatches(ix, v, u, 0, rl - (i32)L, (i32)L, cap);
+                    if (miss <= cap) {
+                        if ((u32)depth + 1 >= lay.D) {  // search stack too small: give up, the host grows the scratch
+                            sc.overflow = true;
+                            depth = -1;
+                            side_finished(a);
+                            return;
+                        }
+                        // park this frame (resume with candidate i+1), make the child the top frame
+                        const u32 b = lay.fr0 + 5 * (u32)depth;
+                        sc.set(b, (i32)(u32)f_code);
+                        sc.set(b + 1, (i32)(u32)(f_code >> 32));
+                        sc.set(b + 2, f_pos);
+                        sc.set(b + 3, (i32)f_acc);
+                        sc.set(b + 4, (i32)(i + 1));
+                        sc.set(lay.cur0 + (u32)depth, u.sid);
+                        f_code = right ? last_code(ix, u) : first_code(ix, u);
+                        f_pos = right ? f_pos + (i32)L : f_pos - (i32)L;
+                        f_acc += miss;
+                        f_next = 0;
+                        ++depth;
+                        descended = true;
+                        break;
+                    }
+                }
+            }
+            if (!descended) pop_frame();
+        }
+        if (depth < 0) side_finished(a);
+    }
+
+    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+        if (phase == XP_SEED) pick_seed(ix, a);
+        if (phase == XP_LEFT || phase == XP_RIGHT) step_node(ix, a);
+    }
+};
+
 // ------------------------------------------------------------------------------ greedy "paths" aligner
 //
 // alignReadGreedyPath and its helpers (alignerPaths.cpp:35-63 driver, :91-124 coverGreedyPath,
@@ -2045,6 +2251,69 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
     }
     if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
     count_classes(a, n_al, n_na, n_no);
+}
+
+// alignReadExhaustive / alignReadExhaustivePath as persistent warps (same life cycle as k_extend_greedy):
+// every lane runs one node of its read's search per turn.
+template <int MINB>
+__global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_exhaustive_nodes(DevIndex ix, BatchArgs a) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 list_n = a.scnt->list_n;
+    ExhaustiveState g;
+    g.phase = XP_DONE;
+    g.sc.overflow = false;
+    bool have = false;
+    u32 r = 0, t = 0;
+    u32 chunk_base = 0, chunk_left = 0;
+    bool dry = false;
+    u32 n_al = 0, n_na = 0;
+    bool any_overflow = false;
+    const u32 lazy = a.ext_lazy ? a.ext_lazy : 1;
+    for (;;) {
+        const bool searching = have && (g.phase == XP_LEFT || g.phase == XP_RIGHT);
+        const u32 waiting = __ballot_sync(0xFFFFFFFFu, !searching);
+        if ((u32)__popc(waiting) >= lazy || waiting == 0xFFFFFFFFu) {
+            if (have && g.done()) {  // hand in
+                any_overflow |= g.sc.overflow;
+                const u32 plen = ((g.flags & BGR_F_MAPPED) && !g.sc.overflow) ? g.n : 0;
+                bgr_result res;
+                res.flags_len = (g.flags & 0xFFu) | (plen << 8);
+                res.path_off = t;
+                a.res[r] = res;
+                n_al += (g.flags & BGR_F_CNT_ALIGNED) != 0;
+                n_na += (g.flags & BGR_F_CNT_NOTALIGNED) != 0;
+                have = false;
+            }
+            const u32 want = __ballot_sync(0xFFFFFFFFu, !have);
+            if (want) {
+                if (chunk_left == 0 && !dry) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&a.cnt->ext_cursor, 32u);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= list_n) dry = true;
+                    else {
+                        chunk_base = base;
+                        chunk_left = min(32u, list_n - base);
+                    }
+                }
+                const u32 rank = __popc(want & ((1u << lane) - 1));
+                if (!have && rank < chunk_left) {
+                    t = chunk_base + rank;
+                    r = a.list[t];
+                    g.start(ix, a, r, a.scratch + t);
+                    have = true;
+                }
+                const u32 taken = min((u32)__popc(want), chunk_left);
+                chunk_base += taken;
+                chunk_left -= taken;
+                if (dry && want == 0xFFFFFFFFu) break;
+            }
+            if (have && g.phase == XP_SEED) g.pick_seed(ix, a);
+        }
+        if (have && (g.phase == XP_LEFT || g.phase == XP_RIGHT)) g.step_node(ix, a);
+    }
+    if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
+    count_classes(a, n_al, n_na, 0);
 }
 
 __global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, BatchArgs a) {

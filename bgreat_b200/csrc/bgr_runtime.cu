@@ -168,8 +168,15 @@ int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
             break;
         }
         case BGR_MODE_EXHAUSTIVE:
-        case BGR_MODE_GREEDY_PATH:
         case BGR_MODE_EXHAUSTIVE_PATH: {
+            // persistent warps, one node of the depth-first search per lane and turn
+            u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
+            const u32 maxb = (u32)ctx->sm_count * 5;
+            if (blocks > maxb) blocks = maxb;
+            k_extend_exhaustive_nodes<5><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
+            break;
+        }
+        case BGR_MODE_GREEDY_PATH: {
             const u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
             k_extend_exhaustive<<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
             break;

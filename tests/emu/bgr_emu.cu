@@ -222,7 +222,28 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
                 for (u32 j = 0; j < np; ++j) same = same && sc.get(j) == (j < nl2 ? sc2.get(nl2 - 1 - j) : sc2.get(j));
             if (!same && !sc.overflow && !sc2.overflow) return 1000;  // the two formulations disagree
         } else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH) {
-            flags = exhaustive_read(ix, a, r, sc, np, overlaps);
+            // the persistent kernel's per-lane life cycle: start, one search node per step until done
+            ExhaustiveState x;
+            x.start(ix, a, r, sc.base);
+            while (!x.done()) x.step(ix, a);
+            flags = x.flags;
+            np = x.n;
+            sc.overflow = x.sc.overflow;
+            // cross-check against the loop-shaped statement of the same search
+            std::vector<i32> tmp((size_t)scratch_ints + 1, 0);
+            Scratch sc2 = sc;
+            sc2.base = tmp.data();
+            sc2.stride = 1;
+            sc2.overflow = false;
+            u32 np2 = 0;
+            const u32 flags2 = exhaustive_read(ix, a, r, sc2, np2, overlaps);
+            if (!sc.overflow && !sc2.overflow) {
+                bool same = flags2 == flags && np2 == np;
+                for (u32 j = 0; same && j < np; ++j) same = sc.get(j) == sc2.get(j);
+                if (!same) return 1001;  // the two formulations disagree
+            } else if (sc.overflow != sc2.overflow) {
+                return 1002;
+            }
         } else if (mode == BGR_MODE_GREEDY_PATH) {
             flags = greedy_path_read(ix, a, r, sc, np);
         } else {
