@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1 << 20, help="reads per batch on the end-to-end leg")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the command-line leg (files in /dev/shm)")
+    ap.add_argument("--cli-reads", type=int, default=10_000_000, help="reads of the command-line leg")
     ap.add_argument("--errors", type=int, default=2, help="-m")
     ap.add_argument("--effort", type=int, default=2, help="-e")
     ap.add_argument("--sub-rate", type=float, default=0.01, help="substitution error rate of the reads")
@@ -241,6 +243,46 @@ class CpuReference:
 
     def cleanup(self):
         shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def cli_leg(graph, n_reads):
+    """the drop-in `bgreat` command line end to end on page-cached files (/dev/shm): FASTA in,
+    paths + notAligned.fa out, all host cores. Bounded sample; returns None if anything is missing."""
+    from tools import synth
+    exe = os.path.join(ROOT, "bgreat_b200", "bin", "bgreat")
+    if not os.access(exe, os.X_OK):
+        return None
+    d = scratch_dir()
+    try:
+        graph.write_unitigs(os.path.join(d, "unitigs.fa"))
+        seqs, off = graph.make_reads(n_reads, READ_LEN, SUB_RATE)
+        synth.write_reads(os.path.join(d, "reads.fa"), seqs, off, n_reads)
+        del seqs, off
+        cores = min(host_cores(), 255)
+        env = dict(os.environ, BGR_VERBOSE="1")
+        t0 = time.perf_counter()
+        p = subprocess.run([exe, "-r", "reads.fa", "-g", "unitigs.fa", "-k", str(K), "-m", str(ERRORS), "-e", str(EFFORT),
+                            "-t", str(cores), "-f", "paths", "-a", "notAligned.fa"] + (["-b"] if EXHAUSTIVE else []),
+                           cwd=d, capture_output=True, text=True, env=env, timeout=900)
+        wall = time.perf_counter() - t0
+        if p.returncode != 0:
+            return None
+        marks = {}
+        for l in p.stderr.splitlines():  # "[bgreat] index built   t=0.698 s"
+            if l.startswith("[bgreat]") and " t=" in l:
+                marks[l[9:l.index(" t=")].strip()] = float(l.split(" t=")[1].split()[0])
+        mapping = marks.get("mapping done", wall) - marks.get("index built", 0.0)
+        out_bytes = sum(os.path.getsize(os.path.join(d, f)) for f in ("paths", "notAligned.fa"))
+        return {"reads": n_reads, "threads": cores, "wall_s": wall, "mapping_s": mapping,
+                "reads_per_s_mapping": n_reads / max(mapping, 1e-9), "reads_per_s_wall": n_reads / wall,
+                "input_bytes": os.path.getsize(os.path.join(d, "reads.fa")), "output_bytes": out_bytes,
+                "what": "bgreat_b200/bin/bgreat on FASTA in /dev/shm -> paths + notAligned.fa; mapping_s excludes "
+                        "CUDA context creation and index build, like the reference's 'Mapping in seconds'"}
+    except Exception as e:  # never let the optional leg break the bench line
+        sys.stderr.write("bench: cli leg skipped (%s)\n" % e)
+        return None
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def auto_cpu_sample(args):
@@ -492,6 +534,9 @@ def run_b200_arm(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_cli:
+        al.close()  # the command line creates its own context
+        line["cli"] = cli_leg(graph, min(n_reads, args.cli_reads))
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -865,26 +865,48 @@ struct Cands {
     u32 fwd_bit;
 };
 
-// getBegin / getEnd (aligner.cpp:147-267)
+// getBegin / getEnd (aligner.cpp:147-267). The key's bucket and the payloads of that bucket's four slots
+// (one 128-byte line) are requested together: a key sits in its home bucket nearly always, and the walk
+// is a chain of dependent round trips, so the extra sectors are cheaper than a second trip.
 BGR_HD Cands index_query(const DevIndex& ix, u64 bin, bool want_end) {
     Cands c;
     c.n = 0;
     c.fwd_bit = 0;
     u64 rc = rcb(bin, ix.k - 1);
     bool canon = bin <= rc;
-    i64 slot = index_find(ix, canon ? bin : rc);
-    if (slot < 0) return c;
+    const u64 key = canon ? bin : rc;
     // getEnd: canonical -> right table, else left; getBegin: canonical -> left, else right
     bool right = (want_end == canon);
-    const u32* p = right ? ix.payload[slot].right : ix.payload[slot].left;
+    const u64 b0 = bucket_of(key, ix.n_buckets);
+    const u64x4 v = ld_bucket(ix.keys + b0 * 4);
+    const u32* line = right ? ix.payload[b0 * 4].right : ix.payload[b0 * 4].left;
+    i64 slot;
 #if defined(__CUDA_ARCH__)
-    uint4 v = __ldg((const uint4*)p);
-    c.raw[0] = v.x;
-    c.raw[1] = v.y;
-    c.raw[2] = v.z;
-    c.raw[3] = v.w;
+    const uint4 p0 = __ldg((const uint4*)line), p1 = __ldg((const uint4*)(line + 8)), p2 = __ldg((const uint4*)(line + 16)),
+                p3 = __ldg((const uint4*)(line + 24));
+    uint4 p;
+    if (v.a == key) p = p0, slot = 0;
+    else if (v.b == key) p = p1, slot = 1;
+    else if (v.c == key) p = p2, slot = 2;
+    else if (v.d == key) p = p3, slot = 3;
+    else if (v.d == EMPTY_KEY) return c;
+    else {
+        slot = index_find(ix, key);  // overflowed into a later bucket
+        if (slot < 0) return c;
+        const u32* q = right ? ix.payload[slot].right : ix.payload[slot].left;
+        p = __ldg((const uint4*)q);
+    }
+    c.raw[0] = p.x;
+    c.raw[1] = p.y;
+    c.raw[2] = p.z;
+    c.raw[3] = p.w;
 #else
-    for (int j = 0; j < 4; ++j) c.raw[j] = p[j];
+    (void)v;
+    (void)line;
+    slot = index_find(ix, key);
+    if (slot < 0) return c;
+    const u32* q = right ? ix.payload[slot].right : ix.payload[slot].left;
+    for (int j = 0; j < 4; ++j) c.raw[j] = q[j];
 #endif
     c.fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
     // slots are scanned in order up to the first empty one (aligner.cpp:172-203)
@@ -1306,10 +1328,15 @@ struct GreedyState {
         i64 next_L = 0;
         u64 next_code = 0;
         bool ended = false, accepted = false;
+        // the candidates' (start, length) are fetched together, before the compares that depend on each other
+        Oriented us[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < c.n) us[i] = orient(ix, c, i);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (i < c.n && !accepted) {
-                const Oriented u = orient(ix, c, i);
+                const Oriented u = us[i];
                 const i64 L = u.len - km1;
                 bool ends_here;
                 i64 upos;
