@@ -1328,15 +1328,10 @@ struct GreedyState {
         i64 next_L = 0;
         u64 next_code = 0;
         bool ended = false, accepted = false;
-        // the candidates' (start, length) are fetched together, before the compares that depend on each other
-        Oriented us[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i < c.n) us[i] = orient(ix, c, i);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (i < c.n && !accepted) {
-                const Oriented u = us[i];
+                const Oriented u = orient(ix, c, i);
                 const i64 L = u.len - km1;
                 bool ends_here;
                 i64 upos;
