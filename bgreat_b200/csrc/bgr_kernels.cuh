@@ -2426,18 +2426,22 @@ __global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const u
     if (a.cnt->pool_overflow) return;  // the host grows the pool and runs the compaction again
     const u32 r0 = blockIdx.x * CP_BLOCK + threadIdx.x * CP_PER_THREAD;
     u32 len[CP_PER_THREAD], v = 0;
+    bgr_result rs[CP_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < CP_PER_THREAD; ++j) {
-        len[j] = (r0 + j < a.n) ? (a.res[r0 + j].flags_len & ~RES_REV_HEAD) >> 8 : 0;
+        rs[j].flags_len = 0;
+        rs[j].path_off = 0;
+        if (r0 + j < a.n) rs[j] = a.res[r0 + j];
+        len[j] = rs[j].flags_len >> 8;
         v += len[j];
     }
     u32 total;
     unsigned long long off = bsum[blockIdx.x] + block_exclusive_scan(v, &total);
 #pragma unroll
     for (int j = 0; j < CP_PER_THREAD; ++j) {
+        const u32 r = r0 + j;
         if (len[j]) {
-            const u32 r = r0 + j;
-            bgr_result res = a.res[r];
+            bgr_result res = rs[j];
             const i32* src = a.scratch + res.path_off;  // scratch row
             i32* dst = a.pool + off;
             // pathBegin was pushed walking away from the seed: reverse(pathBegin) (alignerGreedy.cpp:48)
@@ -2447,6 +2451,10 @@ __global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const u
             res.path_off = (u32)off;
             a.res[r] = res;
             off += len[j];
+        } else if (rs[j].path_off != 0) {
+            // an unmapped read that went through the extension kernel still carries its scratch row
+            // number (which depends on the order of the hit list): results are deterministic without it
+            a.res[r].path_off = 0;
         }
     }
 }
