@@ -327,6 +327,34 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------ B200 arm
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and therefore allocate its pinned staging buffers, first touch) on the NUMA node its
+    GPU hangs off: with 8 ranks streaming 50 GB/s each out of host memory, buffers on the wrong socket
+    halve the end-to-end rate. Returns a description for the bench line; does nothing when the topology
+    cannot be read. BGR_BENCH_NUMA=0 disables it."""
+    if os.environ.get("BGR_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        dom, rest = out.split(":", 1)
+        dev = "%s:%s" % (dom[-4:], rest)  # sysfs uses a 4-digit domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % dev).read())
+        if node < 0:
+            return "no numa information"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "node %d has no usable cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:
+        return "unavailable (%s)" % type(e).__name__
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -340,6 +368,7 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the mapping path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -514,7 +543,8 @@ def run_b200_arm(args):
                    "read_len": READ_LEN, "reads_per_gpu_per_step": n_reads, "unitigs": stats["unitigs"],
                    "border_keys": stats["keys"], "index_bytes": stats["device_bytes"],
                    "l2": "inputs (1.5 GB of read characters per step) exceed L2; no flush needed",
-                   "e2e_batch_reads": B, "parallelism": "reads sharded across GPUs, index replicated"},
+                   "e2e_batch_reads": B, "parallelism": "reads sharded across GPUs, index replicated",
+                   "rank0_numa_binding": numa},
         "bases_per_s": value * READ_LEN,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
@@ -542,9 +572,20 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def quiet_stdout():
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1; the contract is ONE JSON line on
+    stdout. Everything else is sent to stderr; the returned file object is the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse_args()
     configure(args)
+    out = quiet_stdout()
+    sys.stdout = out
     if args.impl == "reference":
         run_reference_arm(args)
     else:
