@@ -31,6 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+E2E_DEPTH = 4  # batches in flight on the end-to-end leg (slots 1..E2E_DEPTH; slot 0 holds the resident leg)
 K = 31
 ERRORS = 2
 EFFORT = 2
@@ -78,6 +79,7 @@ def parse_args():
     ap.add_argument("--effort", type=int, default=2, help="-e")
     ap.add_argument("--sub-rate", type=float, default=0.01, help="substitution error rate of the reads")
     ap.add_argument("--mode", default="greedy", choices=["greedy", "exhaustive"])
+    ap.add_argument("--mix", type=float, default=0.5, help="end-to-end leg 'mixed': fraction of batches the host packs")
     ap.add_argument("--label", default="", help="name of the BASELINE.json config this run stands for")
     return ap.parse_args()
 
@@ -382,7 +384,7 @@ def run_b200_arm(args):
 
     # ---- graph + index: built once on rank 0, replicated by one NCCL broadcast of the flat blob
     graph = synth.Graph(args.genome, K, seed=1)
-    al = bgreat_b200.Aligner(K, ERRORS, EFFORT, device=local, n_slots=3)
+    al = bgreat_b200.Aligner(K, ERRORS, EFFORT, device=local, n_slots=1 + E2E_DEPTH)
     from bgreat_b200 import shard
     t0 = time.perf_counter()
 
@@ -447,7 +449,7 @@ def run_b200_arm(args):
     n_batches = (n_reads + B - 1) // B
     res_t = torch.empty((n_reads, 2), dtype=torch.int32, pin_memory=True)
     pool_cap = B * 16
-    pool_t = [torch.empty(pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    pool_t = [torch.empty(pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(E2E_DEPTH)]
     boff = [np.ascontiguousarray(off[b * B:min(n_reads, (b + 1) * B) + 1] - off[b * B]) for b in range(n_batches)]
     boff_t = []
     for a in boff:  # per-batch offsets (each batch starts at 0) also pinned
@@ -456,21 +458,43 @@ def run_b200_arm(args):
         boff_t.append(t)
     res_np = res_t.numpy()
     d2h = [0]
+    # packed upload: the host packs every batch to 2 bits per base inside the timed region (bgr_pack_reads on
+    # all host cores of this rank), the 2-bit stream is what crosses PCIe
+    pack_threads = max(1, min(host_cores() // max(1, world), 64))
+    pk_t = [torch.empty(B * READ_LEN // 32 + 16, dtype=torch.int64, pin_memory=True) for _ in range(E2E_DEPTH)]
+    bad_t = [torch.empty(B // 32 + 2, dtype=torch.int32, pin_memory=True) for _ in range(E2E_DEPTH)]
+    h2d_packed = [0]
 
-    def e2e_step():
+    def e2e_step(form="characters"):
+        """form: 'characters' | 'packed' | 'mixed' (a fraction args.mix of the batches is packed by the host
+        cores while the others cross PCIe as characters: the two forms draw on different resources)"""
+        frac = {"characters": 0.0, "packed": 1.0, "mixed": args.mix}[form]
         used = C.c_uint64()
+        n_bad = C.c_uint32()
         inflight = []
         d2h[0] = 0
+        h2d_packed[0] = 0
         for b in range(n_batches + 1):
             if b < n_batches:
-                slot = 1 + (b & 1)
+                slot = 1 + (b % E2E_DEPTH)
+                q = b % E2E_DEPTH
+                packed = int((b + 1) * frac) > int(b * frac)
                 lo = b * B
                 n = min(n_reads, lo + B) - lo
-                ck(L.bgr_slot_upload(ctx, slot, seqs.ctypes.data + int(off[lo]), boff_t[b].data_ptr(), n))
+                src = seqs.ctypes.data + int(off[lo])
+                if packed:
+                    ck(L.bgr_pack_reads(src, boff_t[b].data_ptr(), n, pack_threads, pk_t[q].data_ptr(),
+                                        bad_t[q].data_ptr(), C.byref(n_bad)))
+                    ck(L.bgr_slot_upload_packed(ctx, slot, pk_t[q].data_ptr(), boff_t[b].data_ptr(), n,
+                                                bad_t[q].data_ptr(), n_bad.value, src))
+                    h2d_packed[0] += ((int(boff[b][-1]) + 31) // 32) * 8 + (n + 1) * 8 + ((n + 31) // 32) * 4
+                else:
+                    ck(L.bgr_slot_upload(ctx, slot, src, boff_t[b].data_ptr(), n))
+                    h2d_packed[0] += int(boff[b][-1]) + (n + 1) * 8
                 ck(L.bgr_slot_run(ctx, slot, C.byref(params)))
-                ck(L.bgr_slot_download(ctx, slot, res_np.ctypes.data + lo * 8, pool_t[b & 1].data_ptr(), pool_cap))
+                ck(L.bgr_slot_download(ctx, slot, res_np.ctypes.data + lo * 8, pool_t[q].data_ptr(), pool_cap))
                 inflight.append((slot, n))
-            if len(inflight) == 2 or (b == n_batches and inflight):
+            if len(inflight) == E2E_DEPTH or (b == n_batches and inflight):
                 slot, n = inflight.pop(0)
                 ck(L.bgr_slot_wait(ctx, slot, C.byref(used)))
                 d2h[0] += n * 8 + used.value * 4
@@ -479,23 +503,43 @@ def run_b200_arm(args):
             ck(L.bgr_slot_wait(ctx, slot, C.byref(used)))
             d2h[0] += n * 8 + used.value * 4
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    t_e0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    t_e1 = time.perf_counter()
-    e2e_s = torch.tensor([t_e1 - t_e0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_reads * steps / float(e2e_s.item())
-    h2d = n_reads * READ_LEN + (n_reads + n_batches) * 8
+    def time_e2e(form):
+        for _ in range(max(3, args.warmup)):
+            e2e_step(form)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step(form)
+        barrier()
+        t1 = time.perf_counter()
+        sec = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return float(sec.item()), t1, int((res_np[:, 0] & 1).sum()), d2h[0], h2d_packed[0]
+
+    # both upload forms of the public API are timed; the headline is the faster one, the other is reported beside it
+    what = {"characters": "bgr_slot_upload: read characters + offsets cross PCIe (8 bits per base)",
+            "packed": "bgr_pack_reads (host cores, inside the timed region) + bgr_slot_upload_packed: 2 bits per base "
+                      "+ offsets + flag bitmap cross PCIe",
+            "mixed": "a fraction %g of the batches is packed by the host cores (as in 'packed') while the others "
+                     "cross PCIe as characters: the two forms load different resources" % args.mix}
+    e2e_forms, t_e1, mapped = {}, 0.0, set()
+    for form in ("characters", "packed", "mixed"):
+        sec, t_e1, m, d2h_f, h2d_f = time_e2e(form)
+        mapped.add(m)
+        e2e_forms[form] = {"value": world * n_reads * steps / sec, "unit": "reads/s", "ms_per_step": 1e3 * sec / steps,
+                           "h2d_bytes_per_step": int(h2d_f), "d2h_bytes_per_step": int(d2h_f), "what": what[form]}
+        if form != "characters":
+            e2e_forms[form]["host_pack_threads"] = pack_threads
+    e2e_best = max(e2e_forms, key=lambda f: e2e_forms[f]["value"])
+    e2e_s_best = e2e_forms[e2e_best]["ms_per_step"] * steps / 1e3
+    e2e_value = e2e_forms[e2e_best]["value"]
     clocks.stop()
     clk = clocks.summary(t_res0, t_e1)
-    # sanity: the end-to-end leg reproduces the resident leg's outcome
-    mapped_e2e = int((res_np[:, 0] & 1).sum())
+    # sanity: every end-to-end leg reproduces the same outcome
+    mapped_e2e = mapped.pop()
+    if mapped:
+        raise SystemExit("bench.py: the upload forms disagree on the number of mapped reads")
 
     if rank != 0:
         if world > 1:
@@ -547,8 +591,9 @@ def run_b200_arm(args):
                    "rank0_numa_binding": numa},
         "bases_per_s": value * READ_LEN,
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": 1e3 * float(e2e_s.item()) / steps},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": e2e_forms[e2e_best]["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": e2e_forms[e2e_best]["d2h_bytes_per_step"], "ms_per_step": 1e3 * e2e_s_best / steps,
+                "upload": e2e_best, "forms": e2e_forms},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_scan_tiles (pack + seed scan / index probe)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -21,7 +21,8 @@ SYMBOLS = ["bgr_abi_version", "bgr_ctx_create", "bgr_ctx_destroy", "bgr_last_err
            "bgr_host_free", "bgr_index_build", "bgr_index_build_file", "bgr_index_stats", "bgr_index_blob_size",
            "bgr_index_export_device", "bgr_index_import_device", "bgr_index_export_host", "bgr_index_import_host",
            "bgr_index_query", "bgr_map_batch", "bgr_slot_upload", "bgr_slot_run", "bgr_slot_download",
-           "bgr_slot_wait", "bgr_slot_download_corrected", "bgr_slot_kernel_ms", "bgr_counters", "bgr_counters_reset", "bgr_launch_count"]
+           "bgr_slot_wait", "bgr_slot_download_corrected", "bgr_slot_kernel_ms", "bgr_counters", "bgr_counters_reset", "bgr_launch_count",
+           "bgr_pack_reads", "bgr_slot_upload_packed"]
 
 
 P_CORRECT = 1  # bgr_params.flags: correction mode (-c)
@@ -70,6 +71,8 @@ def lib():
     L.bgr_map_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint64, u64p]
     L.bgr_slot_upload.argtypes = [vp, C.c_int, vp, vp, C.c_uint32]
     L.bgr_slot_run.argtypes = [vp, C.c_int, C.POINTER(Params)]
+    L.bgr_pack_reads.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
+    L.bgr_slot_upload_packed.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, vp, C.c_uint32, vp]
     L.bgr_slot_download.argtypes = [vp, C.c_int, vp, vp, C.c_uint64]
     L.bgr_slot_wait.argtypes = [vp, C.c_int, u64p]
     L.bgr_slot_download_corrected.argtypes = [vp, C.c_int, vp, C.c_uint64]
@@ -81,7 +84,7 @@ def lib():
     for name in ("bgr_ctx_create", "bgr_host_alloc", "bgr_index_build", "bgr_index_build_file", "bgr_index_stats",
                  "bgr_index_blob_size", "bgr_index_export_device", "bgr_index_import_device",
                  "bgr_index_export_host", "bgr_index_import_host", "bgr_index_query", "bgr_map_batch",
-                 "bgr_slot_upload", "bgr_slot_run", "bgr_slot_download", "bgr_slot_wait", "bgr_slot_download_corrected", "bgr_slot_kernel_ms",
+                 "bgr_slot_upload", "bgr_pack_reads", "bgr_slot_upload_packed", "bgr_slot_run", "bgr_slot_download", "bgr_slot_wait", "bgr_slot_download_corrected", "bgr_slot_kernel_ms",
                  "bgr_counters", "bgr_counters_reset"):
         getattr(L, name).restype = C.c_int
     _lib = L

@@ -171,6 +171,34 @@ class Aligner:
         buf, off = _concat(reads)
         return self.align_packed(buf, off, mode)
 
+    def pack_reads(self, buf, off, threads=1):
+        """bgr_pack_reads: the batch at 2 bits per base -> (words uint64, bad bitmap uint32, flagged reads)."""
+        n = len(off) - 1
+        words = np.zeros(max(1, (int(off[-1]) + 31) >> 5), dtype=np.uint64)
+        bad = np.zeros(max(1, (n + 31) >> 5), dtype=np.uint32)
+        n_bad = C.c_uint32()
+        self._ck(self.L.bgr_pack_reads(buf.ctypes.data, off.ctypes.data, n, threads, words.ctypes.data, bad.ctypes.data,
+                                       C.byref(n_bad)))
+        return words, bad, n_bad.value
+
+    def align_batch_packed(self, reads, mode=A.MODE_GREEDY, threads=1):
+        """The same batch call with the reads travelling as a 2-bit stream (bgr_pack_reads on the host,
+        bgr_slot_upload_packed); results are identical to align_batch's."""
+        buf, off = _concat(reads)
+        n = len(off) - 1
+        words, bad, n_bad = self.pack_reads(buf, off, threads)
+        res = np.zeros((max(n, 1), 2), dtype=np.uint32)
+        cap = max(1024, int(off[-1]) + 2 * n + 16)
+        pool = np.zeros(cap, dtype=np.int32)
+        used = C.c_uint64()
+        p = self.params(mode)
+        self._ck(self.L.bgr_slot_upload_packed(self.ctx, 0, words.ctypes.data, off.ctypes.data, n, bad.ctypes.data, n_bad,
+                                               buf.ctypes.data))
+        self._ck(self.L.bgr_slot_run(self.ctx, 0, C.byref(p)))
+        self._ck(self.L.bgr_slot_download(self.ctx, 0, res.ctypes.data, pool.ctypes.data, cap))
+        self._ck(self.L.bgr_slot_wait(self.ctx, 0, C.byref(used)))
+        return MappingResult(res[:n, 0], res[:n, 1], pool[:used.value])
+
     def align_packed(self, buf, off, mode=A.MODE_GREEDY):
         n = len(off) - 1
         res = np.zeros((max(n, 1), 2), dtype=np.uint32)

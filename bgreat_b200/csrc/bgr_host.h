@@ -192,6 +192,13 @@ class WorkerPool {
 // every character one of A C G T N (aligner.cpp:55-60)
 bool acgtn_only(const char* p, size_t n);
 
+// 2-bit packing of a batch on `threads` host threads (bgr_pack.cpp): words[w] = characters [32w, 32w+32) of
+// the batch's character stream, first character most significant, A0 C1 G2 T3; (off[n]+31)/32 words are
+// written. bad_bits: bitmap over the reads ((n+31)/32 words), bit set = the read holds a character outside
+// ACGT (its 2-bit codes are then meaningless). Returns the number of such reads.
+uint32_t pack_reads_2bit(const char* seqs, const uint64_t* off, uint32_t n, unsigned threads, uint64_t* words,
+                         uint32_t* bad_bits);
+
 class ParallelReader {
    public:
     // range_bytes: text handed out per next() call (a batch); FASTQ ranges are rounded to whole

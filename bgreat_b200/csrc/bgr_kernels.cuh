@@ -69,9 +69,19 @@ struct ScanCounters {
 };
 
 struct BatchArgs {
-    const char* seq;  // concatenated read characters
+    const char* seq;  // concatenated read characters (null when the batch was uploaded packed)
     const u64* off;   // n+1 character offsets
     u32 n;
+    // batch uploaded as a 2-bit stream (bgr_slot_upload_packed): word w = characters [32w, 32w+32) of the
+    // concatenation, first character most significant. Reads holding a character outside ACGT are flagged in
+    // `bad` (bit r%32 of word r/32) and come as characters on the side: exception j is read exc_idx[j], its
+    // characters are exc_seq[exc_off[j] .. exc_off[j+1]).
+    const u64* pk;
+    const u32* bad;
+    const u32* exc_idx;
+    const u64* exc_off;
+    const char* exc_seq;
+    u32 n_exc;
     u64* F;     // 2-bit words, per read: [pad][ceil(len/32) data words][pad], see read_word_base
     u64* NM;    // N mask in the same layout (0b11 per non-ACGT base); written only for reads with N
     u32* H1;    // hit mask of the forward scan, bit i of word (i/32): window i is a border
@@ -260,8 +270,11 @@ BGR_HD u32 transpose_hits(const u32 ballot[PS_WPL], u32 w) {
 #if defined(__CUDACC__)
 // Pack one read into F/N (shared or global words, one call site each so that the address space is
 // known at compile time), then scan its windows. Returns (any hit in H1, any in H2, has N).
-__device__ __forceinline__ u32 pack_and_scan(const DevIndex& ix, const BatchArgs& a, u64* F, u64* N, const u64 o,
-                                             const u32 len, const u64 wb, const bool exhaustive, const u32 lane) {
+// src: the read's characters, or null = take the bases from the batch's 2-bit stream at base o (such a
+// read has no N: the host flags those and sends them as characters).
+__device__ __forceinline__ u32 pack_and_scan(const DevIndex& ix, const BatchArgs& a, u64* F, u64* N,
+                                             const unsigned char* src, const u64 o, const u32 len, const u64 wb,
+                                             const bool exhaustive, const u32 lane) {
     const u32 km1 = ix.k - 1;
     const u32 nw = (len + 31) >> 5;
     if (lane == 0) {  // pad words: one in front, two behind (the rolling scan looks one word ahead)
@@ -269,10 +282,17 @@ __device__ __forceinline__ u32 pack_and_scan(const DevIndex& ix, const BatchArgs
         F[nw + 1] = 0;
         F[nw + 2] = 0;
     }
+    if (!src) {  // packed upload: realign the read's words out of the stream
+        for (u32 j = lane; j < nw; j += 32) {
+            u64 w = ld_bases(a.pk, (i64)(o + 32ull * j));
+            const u32 rem = len - 32 * j;
+            if (rem < 32) w &= ~(~0ull >> (2 * rem));
+            F[1 + j] = w;
+        }
+    }
     // ---- pack: 256 characters per pass, 8 per lane (a 150-base read takes one pass on 19 lanes)
-    const unsigned char* src = (const unsigned char*)a.seq + o;
     bool anyN = false;
-    for (u32 base = 0; base < nw * 32; base += 256) {
+    for (u32 base = 0; src && base < nw * 32; base += 256) {
         const u32 c0 = base + 8 * lane;
         if (c0 < nw * 32) {
             u32 x0 = 0x41414141u, x1 = 0x41414141u;
@@ -378,10 +398,21 @@ __global__ void __launch_bounds__(PS_WARPS * 32, MINB) k_pack_scan(DevIndex ix, 
     unsigned long long windows = 0, n_reads = 0, n_nohit = 0;
     u32 n_list = 0;  // reads buffered in s_list[warp]
 
-    // the reads the tile kernel handed over (slow_list), or every read of the batch (no list)
-    const u32 n_items = a.slow_list ? a.scnt->slow_n : a.n;
+    // the reads the tile kernel handed over (slow_list), or every read of the batch (no list); after a
+    // packed upload also the exception reads, whose characters came on the side
+    const u32 n_slow = a.slow_list ? a.scnt->slow_n : a.n;
+    const u32 n_items = n_slow + a.n_exc;
     for (u32 it = blockIdx.x * PS_WARPS + warp; it < n_items; it += nwarps) {
-        const u32 r = a.slow_list ? a.slow_list[it] : it;
+        u32 r;
+        const unsigned char* src;
+        if (it < n_slow) {
+            r = a.slow_list ? a.slow_list[it] : it;
+            if (a.pk && (a.bad[r >> 5] >> (r & 31) & 1u)) continue;  // an exception read: see below
+            src = a.pk ? nullptr : (const unsigned char*)a.seq + a.off[r];
+        } else {
+            r = a.exc_idx[it - n_slow];
+            src = (const unsigned char*)a.exc_seq + a.exc_off[it - n_slow];
+        }
         const u64 o = a.off[r];
         const u32 len = (u32)(a.off[r + 1] - o);
         const u64 wb = read_word_base(o, r);
@@ -392,7 +423,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, MINB) k_pack_scan(DevIndex ix, 
         u32 info;
         __syncwarp();  // the previous read's shared words are no longer in use
         if (nw + 3 <= (u32)PS_SWORDS) {
-            info = pack_and_scan(ix, a, sF[warp], sN[warp], o, len, wb, exhaustive, lane);
+            info = pack_and_scan(ix, a, sF[warp], sN[warp], src, o, len, wb, exhaustive, lane);
             // keep the packed words for the extension kernel
             const bool hasN = (info & INFO_HAS_N) != 0;
             const bool needed = (info & (INFO_HIT1 | INFO_HIT2)) != 0;
@@ -403,7 +434,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, MINB) k_pack_scan(DevIndex ix, 
                 }
         } else {
             // long read: the words live in HBM; the warp reads back what it wrote
-            info = pack_and_scan(ix, a, gF, gN, o, len, wb, exhaustive, lane);
+            info = pack_and_scan(ix, a, gF, gN, src, o, len, wb, exhaustive, lane);
         }
         const bool pass_on = (info & INFO_HIT1) || (exhaustive && len == km1);
         if (lane == 0) {
@@ -504,6 +535,16 @@ BGR_HD void clip_span(u32 rem, u64& w0, u64& w1) {
     }
 }
 
+// 64 bases starting at base p of a 2-bit stream W (first base most significant): the packed-upload
+// counterpart of pack_span. W[p/32 + 2] must be readable.
+BGR_HD void packed_span(const u64* W, u64 p, u64& w0, u64& w1) {
+    const u64 i = p >> 5;
+    const u32 s = (u32)(p & 31) * 2;
+    const u64 a = W[i], b = W[i + 1], c = W[i + 2];
+    w0 = (a << s) | ((b >> 1) >> (63 - s));
+    w1 = (b << s) | ((c >> 1) >> (63 - s));
+}
+
 // Bloom test of the chunk's windows: bit j = window 32l+j may be a border. The first window is taken
 // from w0, the following ones roll the forward and the reverse-complement code like update / updateRC
 // (aligner.cpp:305-315). TWO: word index and bit positions come from two hashes (large filters).
@@ -601,7 +642,10 @@ __host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 t
     return b + 128;
 }
 
-template <bool BLOOM_SMEM>
+// PACKED: the batch came as a 2-bit stream (bgr_slot_upload_packed); a tile is then the stream's words under
+// its reads, a chunk's two words are cut out of them with funnel shifts (packed_span) instead of being packed
+// from characters, and the reads the host flagged as holding a non-ACGT character are left to k_pack_scan.
+template <bool BLOOM_SMEM, bool PACKED>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, BatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem S;
@@ -644,8 +688,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
     }
     __syncthreads();
 
-    // bytes the tile [lo, hi) of the character stream occupies in a buffer (16-byte granules)
-    auto tile_bytes = [](u64 lo, u64 hi) -> u64 { return ((hi + 15) & ~15ull) - (lo & ~15ull); };
+    // bytes the tile [lo, hi) of the character stream occupies in a buffer (16-byte granules); first
+    // character of the buffer
+    auto tile_start = [](u64 lo) -> u64 { return PACKED ? ((lo >> 5) & ~1ull) << 5 : (lo & ~15ull); };
+    auto tile_bytes = [](u64 lo, u64 hi) -> u64 {
+        if (PACKED) return (((((hi + 31) >> 5) + 1) & ~1ull) - ((lo >> 5) & ~1ull)) * 8;
+        return ((hi + 15) & ~15ull) - (lo & ~15ull);
+    };
     auto load_bounds = [&](u32 t, u64& lo, u64& hi) {
         lo = hi = 0;
         if (t < ntiles) {
@@ -658,7 +707,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
         const u64 bytes = tile_bytes(lo, hi);
         if (bytes != 0 && bytes <= a.tile_cb) {
             mbar_expect_tx(&S.mbar[buf], (u32)bytes);
-            bulk_g2s(S.chars[buf], a.seq + (lo & ~15ull), (u32)bytes, &S.mbar[buf], policy);
+            const void* src = PACKED ? (const void*)(a.pk + (tile_start(lo) >> 5)) : (const void*)(a.seq + tile_start(lo));
+            bulk_g2s(S.chars[buf], src, (u32)bytes, &S.mbar[buf], policy);
         }
     };
 
@@ -703,7 +753,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
             len = (u32)(S.off[tid + 1] - o);
             nwin = (len >= km1) ? len - km1 + 1 : 0;
             chunks = (nwin + 31) >> 5;
-            S.flags[tid] = 0;
+            const u32 r = r0 + tid;
+            S.flags[tid] = (PACKED && (a.bad[r >> 5] >> (r & 31) & 1u)) ? TS_FLAG_BAD : 0u;
         }
         if (tid < ST_MAX_R) {
             u32 incl = chunks;
@@ -736,7 +787,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
             }
             const u32 T = S.prefix[cnt];
             const unsigned char* cb = S.chars[buf];
-            const u64 gs = t_lo & ~15ull;
+            const u64 gs = tile_start(t_lo);
             for (u32 j = tid; j < T; j += ST_THREADS) {
                 // the read this chunk belongs to: last rd with prefix[rd] <= j
                 u32 rd = 0;
@@ -753,8 +804,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
                 const u32 r = r0 + rd;
                 const u64 wb = read_word_base(ro, r);
                 u64 w0, w1;
-                u32 bad;
-                pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
+                u32 bad = 0;
+                if (PACKED) packed_span((const u64*)cb, ro - gs + 32 * l, w0, w1);
+                else pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
                 clip_span(rlen - 32 * l, w0, w1);
                 // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
                 u64* gF = a.F + wb;
@@ -799,7 +851,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
                 }
             }
             const u32 mp = __ballot_sync(0xFFFFFFFFu, pass_on);
-            const u32 ms = __ballot_sync(0xFFFFFFFFu, slow);
+            // reads for the general kernel's list; flagged reads of a packed batch reach it as exceptions
+            const bool to_slow = PACKED ? (slow && !(fl & TS_FLAG_BAD)) : slow;
+            const u32 ms = __ballot_sync(0xFFFFFFFFu, to_slow);
             u32 bp = 0, bs = 0;
             if (lane == 0) {
                 if (mp) bp = atomicAdd(&a.scnt->list_n, (u32)__popc(mp));
@@ -809,7 +863,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
             bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
             const u32 lt = (1u << lane) - 1;
             if (pass_on) a.list[bp + __popc(mp & lt)] = r;
-            if (slow) a.slow_list[bs + __popc(ms & lt)] = r;
+            if (to_slow) a.slow_list[bs + __popc(ms & lt)] = r;
         }
         my_off = next_off;
         // the next iteration's first barrier orders these reads of S.flags / S.off before they are rewritten

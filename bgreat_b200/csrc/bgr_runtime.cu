@@ -29,6 +29,21 @@ struct Slot {
     // device buffers and their capacities
     char* d_seq = nullptr;
     size_t cap_seq = 0;
+    // packed upload (bgr_slot_upload_packed): 2-bit stream, flag bitmap, exception reads as characters
+    u64* d_pk = nullptr;
+    size_t cap_pk = 0;
+    u32* d_bad = nullptr;
+    size_t cap_bad = 0;
+    u32* d_exc_idx = nullptr;
+    size_t cap_exc_idx = 0;
+    u64* d_exc_off = nullptr;
+    size_t cap_exc_off = 0;
+    char* d_exc_seq = nullptr;
+    size_t cap_exc_seq = 0;
+    char* h_exc = nullptr;  // pinned staging: [exc_off u64 x (n_exc+1)][exc_idx u32 x n_exc][characters]
+    size_t cap_h_exc = 0;
+    bool packed = false;
+    u32 n_exc = 0;
     u64* d_off = nullptr;
     bgr_result* d_res = nullptr;
     u32* d_info = nullptr;
@@ -190,7 +205,13 @@ int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
 
 BatchArgs make_args(Slot& s) {
     BatchArgs a;
-    a.seq = s.d_seq;
+    a.seq = s.packed ? nullptr : s.d_seq;
+    a.pk = s.packed ? s.d_pk : nullptr;
+    a.bad = s.packed ? s.d_bad : nullptr;
+    a.exc_idx = s.d_exc_idx;
+    a.exc_off = s.d_exc_off;
+    a.exc_seq = s.d_exc_seq;
+    a.n_exc = s.packed ? s.n_exc : 0;
     a.off = s.d_off;
     a.n = s.n;
     a.F = s.d_F;
@@ -316,6 +337,12 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
         Slot& s = ctx->slots[i];
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_seq);
+        cudaFree(s.d_pk);
+        cudaFree(s.d_bad);
+        cudaFree(s.d_exc_idx);
+        cudaFree(s.d_exc_off);
+        cudaFree(s.d_exc_seq);
+        if (s.h_exc) cudaFreeHost(s.h_exc);
         cudaFree(s.d_off);
         cudaFree(s.d_res);
         cudaFree(s.d_info);
@@ -466,16 +493,12 @@ int bgr_index_query(const bgr_ctx* cctx, uint64_t kmer_code, int want_end, int32
 
 // ---------------------------------------------------------------------------------- mapping
 
-int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* off, uint32_t n) {
-    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
-    if (!off || (!seqs && n)) return fail(ctx, BGR_ERR_ARG, "null argument");
-    if (off[0] != 0) return fail(ctx, BGR_ERR_ARG, "off[0] must be 0");
-    Slot& s = ctx->slots[slot];
-    CK(cudaSetDevice(ctx->device));
+namespace {
+// per-read and per-word device buffers every upload form needs; the offsets go up with it
+int upload_common(bgr_ctx* ctx, Slot& s, const uint64_t* off, uint32_t n) {
     const u64 chars = off[n];
     const u64 words = batch_words(chars, n);
     int rc;
-    if ((rc = grow(ctx, s.d_seq, s.cap_seq, (size_t)chars + 16))) return rc;
     if (n + 1 > s.cap_reads || !s.d_off) {
         size_t cap = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
         if ((rc = grow(ctx, s.d_off, cap, (size_t)n + 4))) return rc;
@@ -493,7 +516,6 @@ int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* of
         if ((rc = grow(ctx, s.d_H2, c3, (size_t)words))) return rc;
         s.cap_words = std::min(std::min(c0, c1), std::min(c2, c3));
     }
-    if (chars) CK(cudaMemcpyAsync(s.d_seq, seqs, chars, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_off, off, ((size_t)n + 1) * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
     s.n = n;
     s.chars = chars;
@@ -502,6 +524,98 @@ int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* of
     s.ran = false;
     s.want_download = false;
     s.want_corrected = false;
+    return BGR_OK;
+}
+}  // namespace
+
+int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* off, uint32_t n) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    if (!off || (!seqs && n)) return fail(ctx, BGR_ERR_ARG, "null argument");
+    if (off[0] != 0) return fail(ctx, BGR_ERR_ARG, "off[0] must be 0");
+    Slot& s = ctx->slots[slot];
+    CK(cudaSetDevice(ctx->device));
+    const u64 chars = off[n];
+    int rc;
+    if ((rc = grow(ctx, s.d_seq, s.cap_seq, (size_t)chars + 16))) return rc;
+    if (chars) CK(cudaMemcpyAsync(s.d_seq, seqs, chars, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = upload_common(ctx, s, off, n))) return rc;
+    s.packed = false;
+    s.n_exc = 0;
+    return BGR_OK;
+}
+
+int bgr_pack_reads(const char* seqs, const uint64_t* off, uint32_t n, uint32_t threads, uint64_t* words,
+                   uint32_t* bad_bits, uint32_t* n_bad) {
+    if (!off || (!seqs && n && off[n]) || !words || !bad_bits) return fail(nullptr, BGR_ERR_ARG, "null argument");
+    if (off[0] != 0) return fail(nullptr, BGR_ERR_ARG, "off[0] must be 0");
+    const uint32_t nb = pack_reads_2bit(seqs ? seqs : "", off, n, threads, words, bad_bits);
+    if (n_bad) *n_bad = nb;
+    return BGR_OK;
+}
+
+int bgr_slot_upload_packed(bgr_ctx* ctx, int slot, const uint64_t* words, const uint64_t* off, uint32_t n,
+                           const uint32_t* bad_bits, uint32_t n_bad, const char* seqs) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    if (!off || (!words && n && off[n]) || (!bad_bits && n)) return fail(ctx, BGR_ERR_ARG, "null argument");
+    if (n_bad && !seqs) return fail(ctx, BGR_ERR_ARG, "flagged reads need their characters (seqs)");
+    if (off[0] != 0) return fail(ctx, BGR_ERR_ARG, "off[0] must be 0");
+    Slot& s = ctx->slots[slot];
+    CK(cudaSetDevice(ctx->device));
+    const u64 chars = off[n];
+    const size_t pk_words = (size_t)((chars + 31) >> 5), bad_words = ((size_t)n + 31) / 32;
+    int rc;
+    // the scan reads up to three words past a read's last word (tile granules, funnel shifts)
+    if ((rc = grow(ctx, s.d_pk, s.cap_pk, pk_words + 8))) return rc;
+    if ((rc = grow(ctx, s.d_bad, s.cap_bad, bad_words + 1))) return rc;
+    if (pk_words) CK(cudaMemcpyAsync(s.d_pk, words, pk_words * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
+    if (bad_words) CK(cudaMemcpyAsync(s.d_bad, bad_bits, bad_words * sizeof(u32), cudaMemcpyHostToDevice, s.stream));
+    u32 n_exc = 0;
+    if (n_bad) {
+        // the flagged reads, in read order: indices, offsets and characters through one pinned staging buffer
+        u64 exc_chars = 0;
+        for (size_t w = 0; w < bad_words; ++w)
+            for (u32 m = bad_bits[w]; m; m &= m - 1) {
+                const u32 r = (u32)(w * 32) + (u32)__builtin_ctz(m);
+                if (r >= n) return fail(ctx, BGR_ERR_ARG, "flag bitmap has bits beyond the batch");
+                exc_chars += off[r + 1] - off[r];
+                ++n_exc;
+            }
+        const size_t off_bytes = ((size_t)n_exc + 1) * sizeof(u64), idx_bytes = (((size_t)n_exc * sizeof(u32)) + 7) & ~(size_t)7;
+        const size_t need = off_bytes + idx_bytes + (size_t)exc_chars + 16;
+        if (need > s.cap_h_exc) {
+            CK(cudaStreamSynchronize(s.stream));  // the previous batch's copies out of the old buffer
+            if (s.h_exc) CK(cudaFreeHost(s.h_exc));
+            s.h_exc = nullptr;
+            s.cap_h_exc = 0;
+            CK(cudaHostAlloc((void**)&s.h_exc, need * 2, cudaHostAllocDefault));
+            s.cap_h_exc = need * 2;
+        }
+        u64* h_off = (u64*)s.h_exc;
+        u32* h_idx = (u32*)(s.h_exc + off_bytes);
+        char* h_seq = s.h_exc + off_bytes + idx_bytes;
+        u32 j = 0;
+        u64 at = 0;
+        for (size_t w = 0; w < bad_words; ++w)
+            for (u32 m = bad_bits[w]; m; m &= m - 1) {
+                const u32 r = (u32)(w * 32) + (u32)__builtin_ctz(m);
+                const u64 len = off[r + 1] - off[r];
+                h_off[j] = at;
+                h_idx[j] = r;
+                memcpy(h_seq + at, seqs + off[r], len);
+                at += len;
+                ++j;
+            }
+        h_off[n_exc] = at;
+        if ((rc = grow(ctx, s.d_exc_off, s.cap_exc_off, (size_t)n_exc + 1))) return rc;
+        if ((rc = grow(ctx, s.d_exc_idx, s.cap_exc_idx, (size_t)n_exc))) return rc;
+        if ((rc = grow(ctx, s.d_exc_seq, s.cap_exc_seq, (size_t)exc_chars + 16))) return rc;
+        CK(cudaMemcpyAsync(s.d_exc_off, h_off, off_bytes, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_exc_idx, h_idx, (size_t)n_exc * sizeof(u32), cudaMemcpyHostToDevice, s.stream));
+        if (exc_chars) CK(cudaMemcpyAsync(s.d_exc_seq, h_seq, exc_chars, cudaMemcpyHostToDevice, s.stream));
+    }
+    if ((rc = upload_common(ctx, s, off, n))) return rc;
+    s.packed = true;
+    s.n_exc = n_exc;
     return BGR_OK;
 }
 
@@ -527,7 +641,8 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
     if (s.n) {
         // reads per tile from the batch's mean read length: a tile's characters must fit one buffer
         const u64 mean_len = (s.chars + s.n - 1) / s.n;
-        u64 tr = (TILE_CB - 32) / std::max<u64>(mean_len, 1);
+        // (a packed batch takes a quarter of a byte per base)
+        u64 tr = (u64)(TILE_CB - 32) * (s.packed ? 4 : 1) / std::max<u64>(mean_len, 1);
         if (tr > ST_MAX_R) tr = ST_MAX_R;
         s.tile_r = (u32)(tr & ~1ull);
         BatchArgs a = make_args(s);
@@ -537,13 +652,16 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
             const size_t smem = tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
             const u32 ntiles = (s.n + s.tile_r - 1) / s.tile_r;
             const u32 blocks = std::min<u32>(ntiles, (u32)ctx->sm_count);
-            if (bloom_smem) {
-                CK(cudaFuncSetAttribute(k_scan_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_scan_tiles<true><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);
-            } else {
-                CK(cudaFuncSetAttribute(k_scan_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_scan_tiles<false><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);
-            }
+#define BGR_LAUNCH_TILES(BS, PK)                                                                                  \
+    do {                                                                                                          \
+        CK(cudaFuncSetAttribute(k_scan_tiles<BS, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        k_scan_tiles<BS, PK><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                                  \
+    } while (0)
+            if (bloom_smem && s.packed) BGR_LAUNCH_TILES(true, true);
+            else if (bloom_smem) BGR_LAUNCH_TILES(true, false);
+            else if (s.packed) BGR_LAUNCH_TILES(false, true);
+            else BGR_LAUNCH_TILES(false, false);
+#undef BGR_LAUNCH_TILES
             ctx->launches++;
             CK(cudaGetLastError());
         } else {

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define BGR_ABI_VERSION 1
+#define BGR_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------- */
 enum {
@@ -142,6 +142,28 @@ int bgr_map_batch(bgr_ctx* ctx, const char* seqs, const uint64_t* off, uint32_t 
  * (bgr_host_alloc) for the copies to overlap. bgr_slot_wait blocks until the slot is idle. */
 int bgr_slot_upload(bgr_ctx* ctx, int slot, const char* seqs, const uint64_t* off, uint32_t n);
 int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p);
+
+/* Packed upload: the batch travels over PCIe at 2 bits per base instead of 8 (the reference encodes
+ * (k-1)-mers from characters on the fly, str2num / nuc2int, utils.cpp:117-151; here the host packs once).
+ *
+ * bgr_pack_reads runs on `threads` host threads and needs no GPU: words[w] = characters [32w, 32w+32) of
+ * the batch's character stream (the concatenation seqs[0 .. off[n])), first character in the most
+ * significant bits, A0 C1 G2 T3 (str2num's digit order); BGR_PACKED_WORDS(off[n]) words are written.
+ * bad_bits is a bitmap over the reads (BGR_BAD_WORDS(n) words, bit i%32 of word i/32): set = read i holds
+ * a character outside ACGT, which has no 2-bit code and which the reference treats three different ways
+ * depending on where it is looked at (str2num -> 3, nuc2int / nuc2intrc -> 0, missmatchNumber -> never
+ * equal). *n_bad receives the number of such reads.
+ *
+ * bgr_slot_upload_packed replaces bgr_slot_upload for such a batch. It copies the 2-bit stream, the
+ * offsets and the bitmap, and -- only for the flagged reads -- their characters out of `seqs` (may be NULL
+ * when n_bad == 0), through a staging buffer of the slot, so every buffer passed in may be reused once
+ * bgr_slot_wait has returned for this slot. Results are identical to those of the character upload. */
+#define BGR_PACKED_WORDS(chars) (((uint64_t)(chars) + 31) >> 5)
+#define BGR_BAD_WORDS(n) (((uint64_t)(n) + 31) >> 5)
+int bgr_pack_reads(const char* seqs, const uint64_t* off, uint32_t n, uint32_t threads, uint64_t* words,
+                   uint32_t* bad_bits, uint32_t* n_bad);
+int bgr_slot_upload_packed(bgr_ctx* ctx, int slot, const uint64_t* words, const uint64_t* off, uint32_t n,
+                           const uint32_t* bad_bits, uint32_t n_bad, const char* seqs);
 int bgr_slot_download(bgr_ctx* ctx, int slot, bgr_result* results, int32_t* path_pool, uint64_t pool_cap);
 int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used);
 

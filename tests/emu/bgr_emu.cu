@@ -16,10 +16,14 @@
 
 using namespace bgr;
 
-extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uint32_t k, const char* seqs,
-                       const uint64_t* off, uint32_t n, uint32_t mode, uint32_t errors, uint32_t effort,
-                       uint32_t scratch_ints, bgr_result* res, int32_t* pool, uint64_t pool_cap, uint64_t* used,
-                       uint64_t counters[BGR_C_COUNT], int* scratch_overflow) {
+// how: bit 0 = the batch goes through the host packer (bgr_pack.cpp) and the scan takes its bases from the
+// 2-bit stream (k_scan_tiles<.., true>, packed_span), flagged reads through the character form; bit 1 = no
+// tile kernel, every read through the general form (k_pack_scan), as for batches of very long reads.
+extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, uint32_t k, const char* seqs,
+                        const uint64_t* off, uint32_t n, uint32_t mode, uint32_t errors, uint32_t effort,
+                        uint32_t scratch_ints, bgr_result* res, int32_t* pool, uint64_t pool_cap, uint64_t* used,
+                        uint64_t counters[BGR_C_COUNT], int* scratch_overflow, uint32_t how) {
+    const bool packed = (how & 1u) != 0, general_only = (how & 2u) != 0;
     std::vector<uint64_t> blob;
     std::string err;
     int rc = build_index_blob(useqs, uoff, nu, k, blob, err);
@@ -77,6 +81,12 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     //      a read with a non-ACGT character goes to the general form below, like on the device
     std::vector<unsigned char> padded(seqs, seqs + chars);
     padded.resize(chars + 128, 'A');
+    // packed upload: the stream and the flag bitmap as the host packer makes them (3 threads: the cuts between
+    // workers are part of what is tested); the words behind the stream hold garbage on the device
+    std::vector<u64> pk(((chars + 31) >> 5) + 8, 0xDEADBEEFDEADBEEFull);
+    std::vector<u32> bad_bits((n + 31) / 32 + 1, 0xFFFFFFFFu);
+    if (packed) pack_reads_2bit(seqs, off, n, 3, pk.data(), bad_bits.data());
+    a.pk = packed ? pk.data() : nullptr;
     for (u32 r = 0; r < n; ++r) {
         const u64 o = off[r];
         const u32 len = (u32)(off[r + 1] - o);
@@ -86,15 +96,17 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         u64* gN = a.NM + wb;
         const u32 nwin_t = (len >= km1) ? len - km1 + 1 : 0;
         const u32 chunks = (nwin_t + 31) >> 5;
-        bool tile_bad = false, tile_hit = false;
-        for (u32 l = 0; l < chunks; ++l) {
+        const bool flagged = packed && (bad_bits[r >> 5] >> (r & 31) & 1u);
+        bool tile_bad = flagged || general_only, tile_hit = false;
+        for (u32 l = 0; l < chunks && !general_only; ++l) {
             u64 w0, w1;
-            u32 bad;
+            u32 bad = 0;
             // on the device the span may run into the next read's characters: only the part inside the
             // read can flag it here, which is the exact rule (a spurious flag just takes the general path)
             unsigned char span[64];
             for (u32 j = 0; j < 64; ++j) span[j] = (32 * l + j < len) ? padded[o + 32 * l + j] : (unsigned char)'A';
-            pack_span(span, w0, w1, bad);
+            if (packed) packed_span(pk.data(), o + 32 * l, w0, w1);
+            else pack_span(span, w0, w1, bad);
             clip_span(len - 32 * l, w0, w1);
             gF[1 + l] = w0;
             if (l == 0) gF[0] = 0;
@@ -131,7 +143,15 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
         gF[nw + 1] = gN[nw + 1] = 0;
         gF[nw + 2] = gN[nw + 2] = 0;
         bool anyN = false;
-        for (u32 c0 = 0; c0 < nw * 32; c0 += 4) {
+        if (packed && !flagged) {  // pack_and_scan with src == null: the words come out of the stream
+            for (u32 j = 0; j < nw; ++j) {
+                u64 w = ld_bases(a.pk, (i64)(o + 32ull * j));
+                const u32 rem = len - 32 * j;
+                if (rem < 32) w &= ~(~0ull >> (2 * rem));
+                gF[1 + j] = w;
+            }
+        }
+        for (u32 c0 = 0; (!packed || flagged) && c0 < nw * 32; c0 += 4) {
             u32 x = 0x41414141u;
             if (c0 < len) {
                 u32 left = len - c0;
@@ -267,6 +287,20 @@ extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uin
     *used = cnt.pool_cursor;
     for (int i = 0; i < BGR_C_COUNT; ++i) counters[i] = cnt.c[i] + scnt.c[i];
     return BGR_OK;
+}
+
+extern "C" int emu_map(const char* useqs, const uint64_t* uoff, uint32_t nu, uint32_t k, const char* seqs,
+                       const uint64_t* off, uint32_t n, uint32_t mode, uint32_t errors, uint32_t effort,
+                       uint32_t scratch_ints, bgr_result* res, int32_t* pool, uint64_t pool_cap, uint64_t* used,
+                       uint64_t counters[BGR_C_COUNT], int* scratch_overflow) {
+    return emu_map2(useqs, uoff, nu, k, seqs, off, n, mode, errors, effort, scratch_ints, res, pool, pool_cap, used,
+                    counters, scratch_overflow, 0);
+}
+
+// the host packer alone (bgr_pack.cpp): words + flag bitmap for a batch
+extern "C" uint32_t emu_pack_reads(const char* seqs, const uint64_t* off, uint32_t n, uint32_t threads, uint64_t* words,
+                                   uint32_t* bad_bits) {
+    return pack_reads_2bit(seqs, off, n, threads, words, bad_bits);
 }
 
 // ---- host-logic hooks: the product's own parser / unitig loader (bgr_host.cpp), for CPU tests

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "bgr_emu.cu")
 LIB = os.path.join(HERE, "emu", "libbgr_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "bgreat_b200", "csrc", f)
-                for f in ("bgr_kernels.cuh", "bgr_common.h", "bgr_host.cpp", "bgr_host.h")]
+                for f in ("bgr_kernels.cuh", "bgr_common.h", "bgr_host.cpp", "bgr_host.h", "bgr_pack.cpp")]
 
 _lib = None
 
@@ -22,7 +22,8 @@ def build():
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler",
                            "-fPIC", "-shared", "-o", LIB, SRC,
-                           os.path.join(ROOT, "bgreat_b200", "csrc", "bgr_host.cpp")])
+                           os.path.join(ROOT, "bgreat_b200", "csrc", "bgr_host.cpp"),
+                           os.path.join(ROOT, "bgreat_b200", "csrc", "bgr_pack.cpp")])
 
 
 def lib():
@@ -41,8 +42,24 @@ def _concat(seqs):
     return b"".join(b), off
 
 
-def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64):
-    """-> ([(overlap_found, rc, path)], counters dict, flags list, scratch_overflow)"""
+def pack_reads(reads, threads=1):
+    """The product's host packer (bgr_pack.cpp) -> (words uint64 array, set of flagged read indices)."""
+    L = lib()
+    L.emu_pack_reads.restype = C.c_uint32
+    rs, roff = _concat(reads)
+    n = len(reads)
+    words = np.full(((len(rs) + 31) >> 5) + 2, 0xDEADBEEFDEADBEEF, dtype=np.uint64)
+    bad = np.full((n + 31) // 32 + 1, 0xFFFFFFFF, dtype=np.uint32)
+    nb = L.emu_pack_reads(rs, roff.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(threads),
+                          words.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p))
+    flagged = {i for i in range(n) if (int(bad[i >> 5]) >> (i & 31)) & 1}
+    assert nb == len(flagged)
+    return words[:(len(rs) + 31) >> 5], flagged
+
+
+def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64, how=0):
+    """-> ([(overlap_found, rc, path)], counters dict, flags list, scratch_overflow).
+    how: bit 0 = packed upload form, bit 1 = general scan form only (see bgr_emu.cu emu_map2)."""
     L = lib()
     us, uoff = _concat(unitigs)
     rs, roff = _concat(reads)
@@ -53,10 +70,12 @@ def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64):
     used = C.c_uint64(0)
     counters = (C.c_uint64 * 8)()
     ovf = C.c_int(0)
-    rc = L.emu_map(us, uoff.ctypes.data_as(C.c_void_p), C.c_uint32(len(unitigs)), C.c_uint32(k), rs,
-                   roff.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(mode), C.c_uint32(errors),
-                   C.c_uint32(effort), C.c_uint32(scratch_ints), res.ctypes.data_as(C.c_void_p),
-                   pool.ctypes.data_as(C.c_void_p), C.c_uint64(pool_cap), C.byref(used), counters, C.byref(ovf))
+    L.emu_map2.restype = C.c_int
+    rc = L.emu_map2(us, uoff.ctypes.data_as(C.c_void_p), C.c_uint32(len(unitigs)), C.c_uint32(k), rs,
+                    roff.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(mode), C.c_uint32(errors),
+                    C.c_uint32(effort), C.c_uint32(scratch_ints), res.ctypes.data_as(C.c_void_p),
+                    pool.ctypes.data_as(C.c_void_p), C.c_uint64(pool_cap), C.byref(used), counters, C.byref(ovf),
+                    C.c_uint32(how))
     if rc != 0:
         raise RuntimeError("emu_map failed: %d" % rc)
     out, flags = [], []

@@ -21,7 +21,7 @@ def test_header_symbols_are_exported():
     for s in declared:
         assert hasattr(L, s), s
     assert sorted(A.SYMBOLS) == declared
-    assert L.bgr_abi_version() == 1
+    assert L.bgr_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -94,3 +94,87 @@ def test_emulated_correction_long_reads(k, rl):
     unitigs, haps = S.make_graph(rng, k, genome_len=4000, mean_unitig=2 * k, n_variants=40)
     reads = S.make_reads(rng, haps, 400, rl, sub_rate=0.02, n_rate=0.001)
     assert _correct_case(k, 3, 2, unitigs, reads) > 10
+
+
+# ---- packed upload (bgr_pack_reads + bgr_slot_upload_packed): the host packer and the scan forms that take
+# their bases from the 2-bit stream must give what the character forms give
+
+def _py_pack(reads):
+    s = "".join(r if isinstance(r, str) else r.decode("latin-1") for r in reads)
+    words = []
+    for w in range((len(s) + 31) // 32):
+        v = 0
+        for j, c in enumerate(s[32 * w:32 * w + 32]):
+            v |= ("ACGT".find(c) & 3 if c in "ACGT" else 0) << (62 - 2 * j)
+        words.append(v)
+    return words
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5, 16])
+def test_host_packer_matches_plain_python(threads):
+    rng = random.Random(100 + threads)
+    reads = []
+    for i in range(3000):
+        ln = rng.choice([0, 1, 3, 31, 32, 33, 64, 100, 150, 151, 250])
+        r = "".join(rng.choice("ACGT") for _ in range(ln))
+        if ln and rng.random() < 0.02:
+            p = rng.randrange(ln)
+            r = r[:p] + rng.choice("NnXacgt*\x00\xff") + r[p + 1:]
+        reads.append(r.encode("latin-1"))
+    words, flagged = E.pack_reads(reads, threads)
+    want_flagged = {i for i, r in enumerate(reads) if any(c not in b"ACGT" for c in r)}
+    assert flagged == want_flagged and len(flagged) > 10
+    want = _py_pack(reads)
+    assert len(words) == len(want)
+    # words that only cover clean reads must match exactly (codes under a flagged read are unspecified)
+    off = [0]
+    for r in reads:
+        off.append(off[-1] + len(r))
+    dirty = set()
+    for i in flagged:
+        dirty.update(range(off[i] // 32, (off[i + 1] + 31) // 32))
+    checked = 0
+    for w, (g, x) in enumerate(zip(words, want)):
+        if w not in dirty:
+            assert int(g) == x, w
+            checked += 1
+    assert checked > len(want) // 2
+
+
+def test_host_packer_edge_batches():
+    for reads in ([], [b""], [b"", b"", b""], [b"A"], [b"N"], [b"ACGT" * 8], [b"ACGT" * 8, b"", b"T"],
+                  [b"ACGT" * 2048 + b"N"], [b"C" * 31, b"G" * 33, b"N" * 5, b"", b"T" * 64]):
+        words, flagged = E.pack_reads(reads, 4)
+        assert flagged == {i for i, r in enumerate(reads) if any(c not in b"ACGT" for c in r)}
+        want = _py_pack(reads)
+        if not flagged:
+            assert [int(x) for x in words] == want
+
+
+@pytest.mark.parametrize("seed", range(3000, 3030))
+@pytest.mark.parametrize("how", [1, 3])
+def test_emulated_packed_upload_forms_match_oracle_fuzz(seed, how):
+    c = S.fuzz_case(seed)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        o = O.Oracle(c["k"], c["m"], c["effort"])
+        o.index_unitigs(c["unitigs"])
+        want = [o.align(r, mode) for r in c["reads"]]
+        got, counters, _, ovf = E.emu_map(c["unitigs"], c["k"], c["reads"], mode, c["m"], c["effort"], scratch_ints=4096,
+                                          how=how)
+        assert not ovf
+        assert got == want
+        wc = o.counters()
+        for name in ("reads", "aligned", "not_aligned", "no_overlap", "overlaps"):
+            assert counters[name] == wc[name]
+
+
+@pytest.mark.parametrize("k,rl", [(16, 70), (31, 150), (32, 200), (31, 1000)])
+def test_emulated_packed_upload_long_reads_with_n(k, rl):
+    rng = random.Random(k + rl)
+    unitigs, haps = S.make_graph(rng, k, genome_len=6000, mean_unitig=2 * k, n_variants=40)
+    reads = S.make_reads(rng, haps, 300, rl, sub_rate=1.0 / rl, n_rate=0.3 / rl)
+    ref, cref, _, _ = E.emu_map(unitigs, k, reads, 0, 2, 2, scratch_ints=4096, how=0)
+    for how in (1, 3):
+        got, cnt, _, _ = E.emu_map(unitigs, k, reads, 0, 2, 2, scratch_ints=4096, how=how)
+        assert got == ref and cnt == cref
+    assert sum(1 for _, _, p in ref if p) > 20
