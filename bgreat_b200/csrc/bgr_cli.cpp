@@ -61,6 +61,17 @@ struct Batch {
         res.alloc = pool.alloc = corr.alloc = pinned_alloc;
         res.dealloc = pool.dealloc = corr.dealloc = pinned_free;
     }
+    // Buffers for a batch cut from `range_bytes` of text, sized once: pinning memory costs about as much per
+    // byte as parsing it, and growing a pinned buffer pins it twice. Reads shorter than ~60 bases make the
+    // per-read arrays grow later, which is only slower.
+    void prealloc(size_t range_bytes) {
+        const size_t reads = range_bytes / 96 + 1024;
+        pb.seqs.reserve(range_bytes + 4096);
+        pb.soff.reserve(reads + 2);
+        pb.hdr.reserve(reads + 1);
+        res.reserve(reads + 1);
+        pool.reserve(reads * 8 + 1024);
+    }
 };
 
 template <typename T>
@@ -78,6 +89,13 @@ class Queue {
         q_.pop_front();
         return x;
     }
+    bool try_pop(T& x) {
+        std::unique_lock<std::mutex> l(m_);
+        if (q_.empty()) return false;
+        x = q_.front();
+        q_.pop_front();
+        return true;
+    }
 
    private:
     std::mutex m_;
@@ -91,27 +109,43 @@ struct Options {
     bool brute = false, incomplete = false, fastq = false, correction = false, dog = false, have_o = false;
 };
 
+// printPath's to_string(x) (aligner.cpp:600-609) is where the writer's time goes (about nine integers per
+// mapped read): digit count by comparisons, digits two at a time from a table, no division loop per digit.
+struct DigitPairs {
+    char t[200];
+    DigitPairs() {
+        for (int i = 0; i < 100; ++i) {
+            t[2 * i] = (char)('0' + i / 10);
+            t[2 * i + 1] = (char)('0' + i % 10);
+        }
+    }
+};
+static const DigitPairs g_pairs;
+
+static inline unsigned u32_digits(uint32_t u) {
+    return 1u + (u >= 10u) + (u >= 100u) + (u >= 1000u) + (u >= 10000u) + (u >= 100000u) + (u >= 1000000u) +
+           (u >= 10000000u) + (u >= 100000000u) + (u >= 1000000000u);
+}
+
 static inline char* put_int(char* p, int32_t v) {
-    char tmp[12];
     uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
-    int n = 0;
-    do {
-        tmp[n++] = (char)('0' + u % 10);
-        u /= 10;
-    } while (u);
     if (v < 0) *p++ = '-';
-    while (n) *p++ = tmp[--n];
-    return p;
+    char* const e = p + u32_digits(u);
+    char* q = e;
+    while (u >= 100) {
+        const uint32_t r = u % 100;
+        u /= 100;
+        q -= 2;
+        memcpy(q, g_pairs.t + 2 * r, 2);
+    }
+    if (u >= 10) memcpy(q - 2, g_pairs.t + 2 * u, 2);
+    else q[-1] = (char)('0' + u);
+    return e;
 }
 
 static inline unsigned int_chars(int32_t v) {
-    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
-    unsigned n = v < 0 ? 2 : 1;
-    while (u >= 10) {
-        u /= 10;
-        ++n;
-    }
-    return n;
+    const uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    return u32_digits(u) + (v < 0 ? 1u : 0u);
 }
 
 // One output file, written batch by batch. A regular file is extended and memory-mapped per batch so
@@ -263,6 +297,19 @@ static void format_range(const Batch& b, size_t lo, size_t hi, bool split_no_ove
     }
 }
 
+// the comma separated read file list (aligner.cpp:554-576)
+static std::vector<std::string> split_list(const std::string& csv) {
+    std::vector<std::string> files;
+    size_t last = 0;
+    for (size_t i = 0; i < csv.size(); ++i)
+        if (csv[i] == ',') {
+            files.push_back(csv.substr(last, i - last));
+            last = i + 1;
+        }
+    files.push_back(csv.substr(last));
+    return files;
+}
+
 static void usage() {
     // reference bgreat.cpp:117-127
     std::cout << "-r read_file" << std::endl
@@ -362,29 +409,36 @@ int main(int argc, char** argv) {
     params.effort = (uint32_t)o.effort;
     params.flags = correction ? BGR_P_CORRECT : 0u;
 
-    const size_t n_batches = n_slots + 3;
+    const size_t n_batches = n_slots + 4;
     std::vector<Batch> batches(n_batches);
     Queue<Batch*> free_q, parsed_q, done_q;
-    for (auto& b : batches) free_q.push(&b);
-    // text per batch: about 400 k reads of 150 bases; BGR_RANGE_BYTES overrides (tests cut small files)
-    size_t range_bytes = 64u << 20;
+    // text per batch: about 100 k reads of 150 bases (measured on 20 M reads: 16-32 MB beats 8 and 64 MB: the
+    // pipeline fills sooner and there is less memory to pin); BGR_RANGE_BYTES overrides (tests cut small files)
+    size_t range_bytes = 16u << 20;
     if (const char* e = getenv("BGR_RANGE_BYTES")) range_bytes = std::max<size_t>(1, strtoull(e, nullptr, 10));
+    // the batches' pinned buffers are allocated beside the pipeline: the reader starts on the first batch while
+    // the others are still being pinned
+    size_t total_text = 0;
+    for (const std::string& f : split_list(o.reads)) {
+        struct stat st;
+        if (stat(f.c_str(), &st) == 0 && S_ISREG(st.st_mode)) total_text += (size_t)st.st_size;
+        else total_text += range_bytes;  // pipes: size unknown
+    }
+    const size_t batch_text = std::min(range_bytes, total_text + 4096);
+    std::thread allocator([&] {
+        for (auto& b : batches) {
+            b.prealloc(batch_text);
+            free_q.push(&b);
+        }
+    });
     bool io_error = false;
     double parse_s = 0, gpu_wait_s = 0, write_s = 0;  // busy time per stage (BGR_VERBOSE)
+    double reader_phase[3] = {0, 0, 0}, writer_phase[4] = {0, 0, 0, 0}, free_wait_s = 0, done_wait_s = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(now() - t).count(); };
 
     // files of the comma separated list, in order (aligner.cpp:554-576)
-    std::vector<std::string> files;
-    {
-        size_t last = 0;
-        for (size_t i = 0; i < o.reads.size(); ++i)
-            if (o.reads[i] == ',') {
-                files.push_back(o.reads.substr(last, i - last));
-                last = i + 1;
-            }
-        files.push_back(o.reads.substr(last));
-    }
+    const std::vector<std::string> files = split_list(o.reads);
     // the header lines of a batch are views into the mapped input: every file stays mapped until the end
     std::vector<std::unique_ptr<MappedFile>> mapped;
 
@@ -400,13 +454,16 @@ int main(int argc, char** argv) {
             // alignPartGreedy's loop (alignerGreedy.cpp:372-377): getReads(10000) until eof
             ParallelReader pr(mf.data, mf.size, (uint32_t)o.k, o.fastq, threads, range_bytes);
             do {
+                const auto tw = now();
                 Batch* b = free_q.pop();
+                free_wait_s += since(tw);
                 const auto t = now();
                 b->pb.clear();
                 pr.next(b->pb);
                 parse_s += since(t);
                 parsed_q.push(b);  // possibly empty: still flows through so that order is kept
             } while (!pr.done());
+            for (int i = 0; i < 3; ++i) reader_phase[i] += pr.phase_s[i];
         }
         parsed_q.push(nullptr);
     });
@@ -433,8 +490,19 @@ int main(int argc, char** argv) {
             done_q.push(b);
         };
         while (!input_done || !inflight.empty()) {
+            // take the next parsed batch if a slot is free -- but only wait for one when nothing is in flight:
+            // otherwise a finished batch would sit here, kept from the writer, until the reader delivers
+            Batch* b = nullptr;
+            bool got = false;
             if (!input_done && (int)inflight.size() < n_slots) {
-                Batch* b = parsed_q.pop();
+                if (inflight.empty()) {
+                    b = parsed_q.pop();
+                    got = true;
+                } else {
+                    got = parsed_q.try_pop(b);
+                }
+            }
+            if (got) {
                 if (!b) {
                     input_done = true;
                     continue;
@@ -457,9 +525,9 @@ int main(int argc, char** argv) {
                 }
                 inflight.push_back(b);
             } else {
-                Batch* b = inflight.front();
+                Batch* oldest = inflight.front();
                 inflight.pop_front();
-                finish(b);
+                finish(oldest);
             }
         }
         done_q.push(nullptr);
@@ -471,12 +539,16 @@ int main(int argc, char** argv) {
         std::vector<size_t> sz(3 * (size_t)threads), at(3 * (size_t)threads);
         WorkerPool pool(threads - 1);
         for (;;) {
+            const auto tw = now();
             Batch* b = done_q.pop();
+            done_wait_s += since(tw);
             if (!b) break;
             const auto t0w = now();
             const size_t n = b->pb.size();
             const unsigned T = (unsigned)std::min<size_t>(threads, n / 4096 + 1);
             pool.run(T, [&](unsigned t) { measure_range(*b, n * t / T, n * (t + 1) / T, o.have_o, correction, &sz[3 * t]); });
+            writer_phase[0] += since(t0w);
+            const auto t1w = now();
             size_t total[3] = {0, 0, 0};
             for (unsigned t = 0; t < T; ++t)
                 for (int f = 0; f < 3; ++f) {
@@ -485,23 +557,34 @@ int main(int argc, char** argv) {
                 }
             for (int f = 0; f < 3; ++f)
                 if (!out[f].begin(total[f])) write_error = true;
+            writer_phase[1] += since(t1w);
+            const auto t2w = now();
             pool.run(T, [&](unsigned t) {
                 char* dst[3];
                 for (int f = 0; f < 3; ++f) dst[f] = out[f].base ? out[f].base + at[3 * t + f] : nullptr;
                 format_range(*b, n * t / T, n * (t + 1) / T, o.have_o, correction, dst);
             });
+            writer_phase[2] += since(t2w);
+            const auto t3w = now();
             for (int f = 0; f < 3; ++f)
                 if (!out[f].end(total[f])) write_error = true;
+            writer_phase[3] += since(t3w);
             write_s += since(t0w);
             free_q.push(b);
         }
     }
     parser.join();
     gpu.join();
+    allocator.join();
     lap("mapping done");
-    if (verbose)
+    if (verbose) {
         fprintf(stderr, "[bgreat] busy: reader %.3f s, waiting for the GPU %.3f s, writer %.3f s\n", parse_s, gpu_wait_s,
                 write_s);
+        fprintf(stderr, "[bgreat] reader: cut %.3f parse %.3f copy %.3f, waited for a free batch %.3f s\n", reader_phase[0],
+                reader_phase[1], reader_phase[2], free_wait_s);
+        fprintf(stderr, "[bgreat] writer: measure %.3f open %.3f format %.3f close %.3f, waited for results %.3f s\n",
+                writer_phase[0], writer_phase[1], writer_phase[2], writer_phase[3], done_wait_s);
+    }
     for (const std::string& file : files) std::cout << file << std::endl;
 
     uint64_t cnt[BGR_C_COUNT];
@@ -526,9 +609,18 @@ int main(int argc, char** argv) {
     for (int f = 0; f < 3; ++f) out[f].close();
     if (write_error) fprintf(stderr, "bgreat: error while writing the output files\n");
     lap("outputs closed");
+    const int status = (io_error || write_error) ? 1 : 0;
+    if (!getenv("BGR_TEARDOWN")) {
+        // Everything is written; unpinning the buffers, unmapping the inputs and tearing the CUDA context down
+        // takes 0.1 - 3 s that the operating system does faster (the reference leaves its files to exit() too,
+        // aligner.h:85). BGR_TEARDOWN=1 runs the orderly path (leak checkers).
+        std::cout.flush();
+        fflush(nullptr);
+        _exit(status);
+    }
     batches.clear();
     mapped.clear();
     bgr_ctx_destroy(ctx);
     lap("context destroyed");
-    return (io_error || write_error) ? 1 : 0;
+    return status;
 }

@@ -12,6 +12,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -678,14 +679,21 @@ void ParallelReader::next_fasta(ParsedBatch& out) {
     cut[0] = a;
     cut[T] = b;
     WorkerPool& pool = impl_->pool;
+    const auto t0 = std::chrono::steady_clock::now();
     pool.run(T, [&](unsigned t) {
         if (t) cut[t] = std::min(b, fasta_boundary(a + (size_t)((b - a) / T) * t));
     });
+    const auto t1 = std::chrono::steady_clock::now();
     std::vector<Shard>& sh = impl_->shards(T);
     pool.run(T, [&](unsigned t) {
         if (cut[t] < cut[t + 1]) parse_fasta_range(d_, cut[t], cut[t + 1], k_, sh[t]);
     });
+    const auto t2 = std::chrono::steady_clock::now();
     gather(sh, T, pool, out);
+    const auto t3 = std::chrono::steady_clock::now();
+    phase_s[0] += std::chrono::duration<double>(t1 - t0).count();
+    phase_s[1] += std::chrono::duration<double>(t2 - t1).count();
+    phase_s[2] += std::chrono::duration<double>(t3 - t2).count();
     pos_ = b;
     if (pos_ >= n_) finished_ = true;
 }
