@@ -132,31 +132,57 @@ BGR_HD u64 bucket_of(u64 key, u64 n_buckets) {
 
 // ---- Bloom filter of the seed scan. One 32-bit word per probe, three bits per key.
 //   word  = umulhi(h1, n_bloom)
-//   bits  = three 5-bit fields of p, where p = h1 (single-hash mode: n_bloom <= 2^15, so the word index
-//           consumes the top 15 bits and the fields use the low 15) or p = h2 >> 17 (two-hash mode).
-// Kept to 32-bit integer ops: the scan computes one per window and is instruction-issue bound.
+//   bits  = bloom_pattern(bloom_pidx(p)): one of 1024 fixed three-bit patterns, where p = h1 (single-hash mode:
+//           the shared-memory tier) or p = h2 (two-hash mode: large filters).
+// h1 / h2 take a (k-1)-mer code AND its reverse complement and are symmetric in the two, so the scan does not
+// need the canonical minimum of the pair; they are multiply-adds only, and the pattern comes out of a table
+// (shared memory in the scan kernel): the scan computes one filter probe per window and is bound by the
+// integer ALU pipe, while the multiply-add pipe and the load/store pipe have room
+// (profiles/r01_ncu_k_scan_tiles_v6_5Mbp.txt: ALU 67 %, FMA 8 %, LSU 9 %).
 static const u32 BLOOM_SMEM_WORDS = 32768;  // 128 KB: the largest filter the scan keeps in shared memory
-BGR_HD u32 bloom_h1(u64 key) {
-    u32 lo = (u32)key, hi = (u32)(key >> 32);
-    u32 h = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
+static const u32 BLOOM_PATTERNS = 1024;
+BGR_HD u32 bloom_h1(u64 x, u64 r) {
+    u32 h = (u32)x * 0x9E3779B1u;
+    h += (u32)(x >> 32) * 0x85EBCA77u;
+    h += (u32)r * 0x9E3779B1u;
+    h += (u32)(r >> 32) * 0x85EBCA77u;
     return h;
 }
-BGR_HD u32 bloom_h2(u64 key) {
-    u32 lo = (u32)key, hi = (u32)(key >> 32);
-    u32 t = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
-    t ^= t >> 16;
-    t *= 0x85EBCA6Bu;
-    return t;
+BGR_HD u32 bloom_h2(u64 x, u64 r) {
+    u32 h = (u32)x * 0xC2B2AE3Du;
+    h += (u32)(x >> 32) * 0x27D4EB2Fu;
+    h += (u32)r * 0xC2B2AE3Du;
+    h += (u32)(r >> 32) * 0x27D4EB2Fu;
+    return h;
 }
-BGR_HD u32 bloom_mask(u32 p) { return (1u << (p & 31)) | (1u << ((p >> 5) & 31)) | (1u << ((p >> 10) & 31)); }
+BGR_HD u32 bloom_pidx(u32 p) { return (p * 0x2C1B3C6Du) >> 22; }
+// pattern i: three DISTINCT bits of a 32-bit word
+BGR_HD u32 bloom_pattern(u32 i) {
+    u32 r = (i + 1) * 0x9E3779B1u;
+    r ^= r >> 16;
+    r *= 0x85EBCA6Bu;
+    r ^= r >> 13;
+    const u32 b0 = r & 31;
+    const u32 b1 = (b0 + 1 + ((r >> 5) & 1023) % 31) & 31;
+    const u32 lo = b0 < b1 ? b0 : b1, hi = b0 < b1 ? b1 : b0;
+    u32 b2 = ((r >> 15) & 1023) % 30;
+    if (b2 >= lo) ++b2;
+    if (b2 >= hi) ++b2;
+    return (1u << b0) | (1u << b1) | (1u << b2);
+}
 BGR_HD u32 bloom_word_of(u32 h1, u32 n_bloom) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(h1, n_bloom);
 #else
     return (u32)(((u64)h1 * (u64)n_bloom) >> 32);
 #endif
+}
+// word index and bit pattern of a canonical key (the index builders; km1 = k-1)
+BGR_HD void bloom_slot(u64 key, u32 km1, bool two_hashes, u32 n_bloom, u32& word, u32& pattern) {
+    const u64 r = rcb(key, km1);
+    const u32 h1 = bloom_h1(key, r);
+    word = bloom_word_of(h1, n_bloom);
+    pattern = bloom_pattern(bloom_pidx(two_hashes ? bloom_h2(key, r) : h1));
 }
 // number of filter words for n_keys keys (power of two not required)
 inline u64 bloom_words_for(u64 n_keys, bool& two_hashes) {

@@ -252,7 +252,7 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     BlobHeader h;
     memset(&h, 0, sizeof h);
     h.magic = BLOB_MAGIC;
-    h.version = 3;
+    h.version = 4;
     h.k = k;
     h.n_unitigs = nu;
     h.n_keys = n_keys;
@@ -309,9 +309,9 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
         memcpy(B, &h, sizeof h);
         u32* bloom = (u32*)(B + h.off_bloom);
         for (u64 i = 0; i < n_keys; ++i) {
-            const u32 h1 = bloom_h1(keys[i]);
-            const u32 p = two_hashes ? (bloom_h2(keys[i]) >> 17) : h1;
-            bloom[bloom_word_of(h1, (u32)h.n_bloom)] |= bloom_mask(p);
+            u32 word, pattern;
+            bloom_slot(keys[i], k - 1, two_hashes, (u32)h.n_bloom, word, pattern);
+            bloom[word] |= pattern;
         }
     }
 

@@ -98,7 +98,7 @@ __global__ void k_run_starts(const u32* head, const u32* run_id, u64 n, u32 n_ke
 }
 
 __global__ void k_insert_keys(const u64* skeys, const u32* run_start, u32 n_keys, u64* tkeys, u64 n_buckets, u32* bloom,
-                              u32 n_bloom, u32 two_hashes, u32* slot_of) {
+                              u32 n_bloom, u32 two_hashes, u32 km1, u32* slot_of) {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_keys) return;
     const u64 key = skeys[run_start[r]];
@@ -117,9 +117,9 @@ __global__ void k_insert_keys(const u64* skeys, const u32* run_start, u32 n_keys
         if (placed) break;
         if (++b == n_buckets) b = 0;
     }
-    const u32 h1 = bloom_h1(key);
-    const u32 p = two_hashes ? (bloom_h2(key) >> 17) : h1;
-    atomicOr(&bloom[bloom_word_of(h1, n_bloom)], bloom_mask(p));
+    u32 word, pattern;
+    bloom_slot(key, km1, two_hashes != 0, n_bloom, word, pattern);
+    atomicOr(&bloom[word], pattern);
 }
 
 __global__ void k_fill_payload(const u32* sidx, const u32* flags, const u32* run_start, const u32* slot_of, u32 n_keys,
@@ -293,7 +293,7 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     BlobHeader h;
     memset(&h, 0, sizeof h);
     h.magic = BLOB_MAGIC;
-    h.version = 3;
+    h.version = 4;
     h.k = k;
     h.n_unitigs = nu;
     h.n_keys = n_keys;
@@ -329,7 +329,7 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     if (n_keys) {
         k_insert_keys<<<grid_for(n_keys, B), B>>>(d_skeys.as<u64>(), d_runstart.as<u32>(), n_keys, (u64*)(Bp + h.off_keys),
                                                    n_buckets, (u32*)(Bp + h.off_bloom), (u32)h.n_bloom, h.bloom_two_hashes,
-                                                   d_slot.as<u32>());
+                                                   k - 1, d_slot.as<u32>());
         k_fill_payload<<<grid_for(n_keys, B), B>>>(d_sidx.as<u32>(), d_flags.as<u32>(), d_runstart.as<u32>(),
                                                     d_slot.as<u32>(), n_keys, (Payload*)(Bp + h.off_payload));
         *launches += 2;

@@ -547,27 +547,30 @@ BGR_HD void packed_span(const u64* W, u64 p, u64& w0, u64& w1) {
 
 // Bloom test of the chunk's windows: bit j = window 32l+j may be a border. The first window is taken
 // from w0, the following ones roll the forward and the reverse-complement code like update / updateRC
-// (aligner.cpp:305-315). TWO: word index and bit positions come from two hashes (large filters).
-template <bool TWO>
-BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, u32 km1, u64 w0, u64 w1, u32 count) {
+// (aligner.cpp:305-315). TWO: word index and bit pattern come from two hashes (large filters). pat: the table
+// of bloom_pattern values (shared memory on the device). KM1S: k-1 known at compile time (0: use km1_rt):
+// with the loop unrolled every shift count and mask below is then a constant, which takes about a third of
+// the integer instructions out of the loop (the scan is bound by the integer ALU pipe).
+template <bool TWO, u32 KM1S>
+BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, const u32* pat, u32 km1_rt, u64 w0, u64 w1, u32 count) {
+    const u32 km1 = KM1S ? KM1S : km1_rt;
     const u32 sh = 64 - 2 * km1, top = 2 * (km1 - 1);
     const u64 mask = ~0ull >> sh;
     u64 num = w0 >> sh;
     u64 rc = rcb(num, km1);
-    u64 inc = (w0 << (2 * km1)) | (w1 >> sh);  // the bases that follow the first window
+    const u64 inc = (w0 << (2 * km1)) | (w1 >> sh);  // the bases that follow the first window
     u32 hits = 0;
     // All 32 window slots are tested, the slots past `count` are dropped at the end: no branch per
     // window, so the filter loads of several windows are in flight together (a slot past the end reads
     // some valid filter word: the index is always < n_bloom).
 #pragma unroll
     for (u32 j = 0; j < 32; ++j) {
-        const u64 rep = num < rc ? num : rc;
-        const u32 h1 = bloom_h1(rep);
-        const u32 m = bloom_mask(TWO ? (bloom_h2(rep) >> 17) : h1);
+        // symmetric in (num, rc): no canonical minimum needed
+        const u32 h1 = bloom_h1(num, rc);
+        const u32 m = pat[bloom_pidx(TWO ? bloom_h2(num, rc) : h1)];
         const u32 w = bloom[bloom_word_of(h1, n_bloom)];
         hits |= ((w & m) == m ? 1u : 0u) << j;
-        const u64 nb = inc >> 62;
-        inc <<= 2;
+        const u64 nb = (inc >> (62 - 2 * j)) & 3;
         num = ((num << 2) | nb) & mask;
         rc = (rc >> 2) | ((3 - nb) << top);
     }
@@ -628,6 +631,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, 
 
 struct TileSmem {
     u32* bloom;
+    u32* pat;  // BLOOM_PATTERNS filter bit patterns
     unsigned char* chars[2];
     u64* off;     // ST_MAX_R + 2
     u32* prefix;  // ST_MAX_R + 2
@@ -637,6 +641,7 @@ struct TileSmem {
 };
 __host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb) {
     size_t b = ((size_t)bloom_words_in_smem * 4 + 127) & ~(size_t)127;
+    b += BLOOM_PATTERNS * 4;
     b += 2 * ((size_t)tile_cb + ST_CHAR_SLACK);
     b += (ST_MAX_R + 2) * 8 + 2 * (ST_MAX_R + 2) * 4 + 2 * 8 + 32 * 4;
     return b + 128;
@@ -645,7 +650,8 @@ __host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 t
 // PACKED: the batch came as a 2-bit stream (bgr_slot_upload_packed); a tile is then the stream's words under
 // its reads, a chunk's two words are cut out of them with funnel shifts (packed_span) instead of being packed
 // from characters, and the reads the host flagged as holding a non-ACGT character are left to k_pack_scan.
-template <bool BLOOM_SMEM, bool PACKED>
+// KM1S: k-1 as a compile-time constant for the usual k = 31 (0: any k, taken from the index at run time).
+template <bool BLOOM_SMEM, bool PACKED, u32 KM1S>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, BatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem S;
@@ -653,6 +659,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
         unsigned char* q = smem_raw;
         S.bloom = (u32*)q;
         q += BLOOM_SMEM ? (((size_t)ix.n_bloom * 4 + 127) & ~(size_t)127) : 0;
+        S.pat = (u32*)q;
+        q += BLOOM_PATTERNS * 4;
         S.chars[0] = q;
         q += a.tile_cb + ST_CHAR_SLACK;
         S.chars[1] = q;
@@ -670,9 +678,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 R = a.tile_r, n = a.n, G = gridDim.x;
     const u32 ntiles = (n + R - 1) / R;
-    const u32 km1 = ix.k - 1;
+    const u32 km1 = KM1S ? KM1S : ix.k - 1;
     const bool exhaustive = a.mode != BGR_MODE_GREEDY;
     const u32* bloom = BLOOM_SMEM ? S.bloom : ix.bloom;
+    for (u32 i = threadIdx.x; i < BLOOM_PATTERNS; i += ST_THREADS) S.pat[i] = bloom_pattern(i);
 
     u64 policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -820,7 +829,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
                 }
                 const u32 count = min(32u, rnwin - 32 * l);
                 // the shared-memory tier is the single-hash tier (bloom_words_for)
-                u32 hits = scan_chunk<!BLOOM_SMEM>(bloom, ix.n_bloom, km1, w0, w1, count);
+                u32 hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, S.pat, km1, w0, w1, count);
                 c_verify += __popc(hits);
                 hits = verify_chunk(ix, w0, w1, hits);
                 a.H1[wb + l] = hits;

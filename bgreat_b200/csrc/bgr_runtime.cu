@@ -130,7 +130,7 @@ int grow(bgr_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack_num = 5, si
 int set_index_from_device_blob(bgr_ctx* ctx) {
     CK(cudaMemcpy(&ctx->hdr, ctx->d_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost));
     const BlobHeader& h = ctx->hdr;
-    if (h.magic != BLOB_MAGIC || h.version != 3) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
+    if (h.magic != BLOB_MAGIC || h.version != 4) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
     char* B = (char*)ctx->d_blob;
     ctx->ix.keys = (const u64*)(B + h.off_keys);
     ctx->ix.payload = (const Payload*)(B + h.off_payload);
@@ -158,7 +158,7 @@ int install_host_blob(bgr_ctx* ctx, const void* blob, u64 bytes) {
     if (bytes < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index blob too small");
     BlobHeader h;
     memcpy(&h, blob, sizeof h);
-    if (h.magic != BLOB_MAGIC || h.version != 3 || h.total_bytes != bytes)
+    if (h.magic != BLOB_MAGIC || h.version != 4 || h.total_bytes != bytes)
         return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version/size");
     CK(cudaSetDevice(ctx->device));
     int rc = drop_index(ctx);
@@ -652,15 +652,21 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
             const size_t smem = tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
             const u32 ntiles = (s.n + s.tile_r - 1) / s.tile_r;
             const u32 blocks = std::min<u32>(ntiles, (u32)ctx->sm_count);
-#define BGR_LAUNCH_TILES(BS, PK)                                                                                  \
+#define BGR_LAUNCH_TILES(BS, PK, KS)                                                                              \
     do {                                                                                                          \
-        CK(cudaFuncSetAttribute(k_scan_tiles<BS, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        k_scan_tiles<BS, PK><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                                  \
+        CK(cudaFuncSetAttribute(k_scan_tiles<BS, PK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_scan_tiles<BS, PK, KS><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                               \
     } while (0)
-            if (bloom_smem && s.packed) BGR_LAUNCH_TILES(true, true);
-            else if (bloom_smem) BGR_LAUNCH_TILES(true, false);
-            else if (s.packed) BGR_LAUNCH_TILES(false, true);
-            else BGR_LAUNCH_TILES(false, false);
+#define BGR_LAUNCH_TILES_K(BS, PK)               \
+    do {                                         \
+        if (ctx->ix.k == 31) BGR_LAUNCH_TILES(BS, PK, 30); \
+        else BGR_LAUNCH_TILES(BS, PK, 0);        \
+    } while (0)
+            if (bloom_smem && s.packed) BGR_LAUNCH_TILES_K(true, true);
+            else if (bloom_smem) BGR_LAUNCH_TILES_K(true, false);
+            else if (s.packed) BGR_LAUNCH_TILES_K(false, true);
+            else BGR_LAUNCH_TILES_K(false, false);
+#undef BGR_LAUNCH_TILES_K
 #undef BGR_LAUNCH_TILES
             ctx->launches++;
             CK(cudaGetLastError());

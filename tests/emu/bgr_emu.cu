@@ -87,6 +87,8 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     std::vector<u32> bad_bits((n + 31) / 32 + 1, 0xFFFFFFFFu);
     if (packed) pack_reads_2bit(seqs, off, n, 3, pk.data(), bad_bits.data());
     a.pk = packed ? pk.data() : nullptr;
+    std::vector<u32> pat(BLOOM_PATTERNS);
+    for (u32 i = 0; i < BLOOM_PATTERNS; ++i) pat[i] = bloom_pattern(i);
     for (u32 r = 0; r < n; ++r) {
         const u64 o = off[r];
         const u32 len = (u32)(off[r + 1] - o);
@@ -116,8 +118,19 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
                 gF[nw + 2] = 0;
             }
             const u32 count = nwin_t - 32 * l < 32u ? nwin_t - 32 * l : 32u;
-            u32 hits = ix.bloom_two_hashes ? scan_chunk<true>(ix.bloom, ix.n_bloom, km1, w0, w1, count)
-                                           : scan_chunk<false>(ix.bloom, ix.n_bloom, km1, w0, w1, count);
+            // both the k-1 = 30 specialisation and the run-time form, like the kernel's dispatch
+            u32 hits;
+            if (ix.bloom_two_hashes)
+                hits = km1 == 30 ? scan_chunk<true, 30>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
+                                 : scan_chunk<true, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
+            else
+                hits = km1 == 30 ? scan_chunk<false, 30>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
+                                 : scan_chunk<false, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
+            if (km1 == 30) {  // the two forms must agree
+                const u32 h0 = ix.bloom_two_hashes ? scan_chunk<true, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
+                                                   : scan_chunk<false, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
+                if (h0 != hits) return 1003;
+            }
             scnt.c[BGR_C_VERIFIED] += (u64)__builtin_popcount(hits);
             hits = verify_chunk(ix, w0, w1, hits);
             a.H1[wb + l] = hits;
