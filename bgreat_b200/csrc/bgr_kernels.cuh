@@ -898,6 +898,290 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
         }
     }
 }
+
+// ------------------------------------------------------------------------------ tile scan, warp-specialised
+//
+// Same work as k_scan_tiles, other schedule. In k_scan_tiles all 32 warps meet at four barriers per tile, and
+// between them the per-tile bookkeeping (offsets, chunk prefix sums, classification, hit-list append with its
+// global atomic) runs on 8 warps while 24 wait: a quarter of all warp time is spent at those barriers
+// (profiles/r01_ncu_k_scan_tiles_v8_5Mbp.txt). Here warp 0 does nothing but the bookkeeping, one tile ahead
+// (prologue of tile i+1, then epilogue of tile i), and the other 31 warps do nothing but chunks. They meet
+// through mbarriers per buffer -- full[b]: tile metadata (and TMA issued) in buffer b; done[b]: the workers are
+// through with buffer b -- which a warp passes as soon as ITS condition holds, so a fast warp runs into the
+// next tile instead of waiting for the slowest one.
+struct TileMeta {
+    u64 off[ST_MAX_R + 2];
+    u32 prefix[ST_MAX_R + 2];
+    u32 flags[ST_MAX_R + 2];
+    u64 t_lo;
+    u32 cnt, r0, T, fits, wait_tma, tma_parity;
+};
+static const u32 WS_WORKERS = ST_THREADS - 32;
+
+__host__ __device__ inline size_t tile_ws_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb) {
+    size_t b = ((size_t)bloom_words_in_smem * 4 + 127) & ~(size_t)127;
+    b += BLOOM_PATTERNS * 4;
+    b += 2 * ((size_t)tile_cb + ST_CHAR_SLACK);
+    b += 2 * ((sizeof(TileMeta) + 15) & ~(size_t)15) + 6 * 8;
+    return b + 128;
+}
+
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool BLOOM_SMEM, bool PACKED, u32 KM1S>
+__global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, BatchArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32 *s_bloom, *s_pat;
+    unsigned char* s_chars[2];
+    TileMeta* M;
+    u64 *bar_tma, *bar_full, *bar_done;
+    {
+        unsigned char* q = smem_raw;
+        s_bloom = (u32*)q;
+        q += BLOOM_SMEM ? (((size_t)ix.n_bloom * 4 + 127) & ~(size_t)127) : 0;
+        s_pat = (u32*)q;
+        q += BLOOM_PATTERNS * 4;
+        s_chars[0] = q;
+        q += a.tile_cb + ST_CHAR_SLACK;
+        s_chars[1] = q;
+        q += a.tile_cb + ST_CHAR_SLACK;
+        M = (TileMeta*)q;  // sizeof(TileMeta) is a multiple of 8; two of them, each padded to 16
+        q += 2 * ((sizeof(TileMeta) + 15) & ~(size_t)15);
+        bar_tma = (u64*)q;
+        bar_full = bar_tma + 2;
+        bar_done = bar_tma + 4;
+    }
+    auto meta = [&](u32 b) -> TileMeta& { return *(TileMeta*)((unsigned char*)M + b * ((sizeof(TileMeta) + 15) & ~(size_t)15)); };
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 R = a.tile_r, n = a.n, G = gridDim.x;
+    const u32 ntiles = (n + R - 1) / R;
+    const u32 km1 = KM1S ? KM1S : ix.k - 1;
+    const bool exhaustive = a.mode != BGR_MODE_GREEDY;
+    const u32* bloom = BLOOM_SMEM ? s_bloom : ix.bloom;
+    for (u32 i = tid; i < BLOOM_PATTERNS; i += ST_THREADS) s_pat[i] = bloom_pattern(i);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bar_tma[b], 1);
+            mbar_init(&bar_full[b], 1);
+            mbar_init(&bar_done[b], WS_WORKERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (BLOOM_SMEM) {
+        const uint4* src = (const uint4*)ix.bloom;  // the blob pads the filter to a 256-byte boundary
+        uint4* dst = (uint4*)s_bloom;
+        for (u32 i = tid; i < (ix.n_bloom + 3) / 4; i += ST_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const u32 my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + G - 1) / G : 0;
+    auto tile_start = [](u64 lo) -> u64 { return PACKED ? ((lo >> 5) & ~1ull) << 5 : (lo & ~15ull); };
+    auto tile_bytes = [](u64 lo, u64 hi) -> u64 {
+        if (PACKED) return (((((hi + 31) >> 5) + 1) & ~1ull) - ((lo >> 5) & ~1ull)) * 8;
+        return ((hi + 15) & ~15ull) - (lo & ~15ull);
+    };
+
+    if (warp == 0) {
+        // ================================================================== bookkeeper
+        u64 policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        u32 tma_uses[2] = {0, 0};  // lane 0: TMA rounds issued per buffer (mbarrier phase parity)
+        unsigned long long c_windows = 0;
+        u32 c_reads = 0, c_nohit = 0;
+
+        // metadata of local tile i into buffer i&1, its characters on their way, then full[i&1]
+        auto prologue = [&](u32 i) {
+            const u32 b = i & 1;
+            TileMeta& m = meta(b);
+            const u32 r0 = (blockIdx.x + i * G) * R;
+            const u32 cnt = min(R, n - r0);
+            for (u32 t = lane; t <= cnt; t += 32) m.off[t] = a.off[(u64)r0 + t];
+            __syncwarp();
+            u32 carry = 0;
+            for (u32 base = 0; base < cnt; base += 32) {
+                const u32 t = base + lane;
+                u32 chunks = 0;
+                if (t < cnt) {
+                    const u32 len = (u32)(m.off[t + 1] - m.off[t]);
+                    const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
+                    chunks = (nwin + 31) >> 5;
+                    const u32 r = r0 + t;
+                    m.flags[t] = (PACKED && (a.bad[r >> 5] >> (r & 31) & 1u)) ? TS_FLAG_BAD : 0u;
+                }
+                u32 incl = chunks;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= (u32)d) incl += x;
+                }
+                if (t < cnt) m.prefix[t] = carry + incl - chunks;
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            if (lane == 0) {
+                m.prefix[cnt] = carry;
+                m.T = carry;
+                m.cnt = cnt;
+                m.r0 = r0;
+                const u64 lo = m.off[0], hi = m.off[cnt];
+                m.t_lo = lo;
+                const u64 bytes = tile_bytes(lo, hi);
+                const bool fits = bytes <= a.tile_cb;
+                m.fits = fits ? 1u : 0u;
+                m.wait_tma = 0;
+                if (fits && bytes != 0) {
+                    mbar_expect_tx(&bar_tma[b], (u32)bytes);
+                    const void* src =
+                        PACKED ? (const void*)(a.pk + (tile_start(lo) >> 5)) : (const void*)(a.seq + tile_start(lo));
+                    bulk_g2s(s_chars[b], src, (u32)bytes, &bar_tma[b], policy);
+                    m.wait_tma = 1;
+                    m.tma_parity = tma_uses[b] & 1;
+                    ++tma_uses[b];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[b]);
+        };
+
+        // classification of the tile's reads and the hit-list append: one atomic per tile
+        auto epilogue = [&](u32 i) {
+            TileMeta& m = meta(i & 1);
+            const u32 cnt = m.cnt, r0 = m.r0;
+            const bool fits = m.fits != 0;
+            const u32 lt = (1u << lane) - 1;
+            u32 mp[ST_MAX_R / 32];
+            u32 total = 0;
+#pragma unroll
+            for (u32 q = 0; q < ST_MAX_R / 32; ++q) {
+                const u32 t = 32 * q + lane;
+                const bool valid = t < cnt;
+                const u32 r = r0 + t;
+                const u32 fl = valid ? m.flags[t] : 0u;
+                const u32 len = valid ? (u32)(m.off[t + 1] - m.off[t]) : 0u;
+                const u32 nwin = (len >= km1) ? len - km1 + 1 : 0;
+                const bool slow = valid && (!fits || (fl & TS_FLAG_BAD));
+                const bool hit = (fl & TS_FLAG_HIT) != 0;
+                const bool pass_on = valid && !slow && (hit || (exhaustive && len == km1));
+                if (valid && !slow) {
+                    a.info[r] = hit ? INFO_HIT1 : 0u;
+                    c_windows += nwin;
+                    c_reads += 1;
+                    if (!pass_on) {
+                        bgr_result res;
+                        res.flags_len = no_hit_flags(exhaustive);
+                        res.path_off = 0;
+                        a.res[r] = res;
+                        c_nohit += 1;
+                    }
+                }
+                mp[q] = __ballot_sync(0xFFFFFFFFu, pass_on);
+                total += __popc(mp[q]);
+                // reads for the general kernel's list (rare); flagged reads of a packed batch reach it as exceptions
+                const bool to_slow = PACKED ? (slow && !(fl & TS_FLAG_BAD)) : slow;
+                const u32 ms = __ballot_sync(0xFFFFFFFFu, to_slow);
+                if (ms) {
+                    u32 bs = 0;
+                    if (lane == 0) bs = atomicAdd(&a.scnt->slow_n, (u32)__popc(ms));
+                    bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
+                    if (to_slow) a.slow_list[bs + __popc(ms & lt)] = r;
+                }
+            }
+            if (total) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&a.scnt->list_n, total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (u32 q = 0; q < ST_MAX_R / 32; ++q) {
+                    if ((mp[q] >> lane) & 1u) a.list[base + __popc(mp[q] & lt)] = r0 + 32 * q + lane;
+                    base += __popc(mp[q]);
+                }
+            }
+        };
+
+        if (my_tiles) prologue(0);
+        for (u32 i = 0; i < my_tiles; ++i) {
+            // buffer (i+1)&1 is free: its last tile (i-1) was waited for and classified in the previous turn
+            if (i + 1 < my_tiles) prologue(i + 1);
+            mbar_wait(&bar_done[i & 1], (i >> 1) & 1);
+            epilogue(i);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            c_windows += __shfl_xor_sync(0xFFFFFFFFu, c_windows, d);
+            c_reads += __shfl_xor_sync(0xFFFFFFFFu, c_reads, d);
+            c_nohit += __shfl_xor_sync(0xFFFFFFFFu, c_nohit, d);
+        }
+        if (lane == 0) {
+            if (c_windows) atomicAdd(&a.scnt->c[BGR_C_WINDOWS], c_windows);
+            if (c_reads) atomicAdd(&a.scnt->c[BGR_C_READS], (unsigned long long)c_reads);
+            if (exhaustive) {
+                if (c_windows) atomicAdd(&a.scnt->c[BGR_C_OVERLAPS], c_windows);  // overlaps += listOverlap.size()
+                if (c_nohit) atomicAdd(&a.scnt->c[BGR_C_NOTALIGNED], (unsigned long long)c_nohit);
+            } else if (c_nohit) {
+                atomicAdd(&a.scnt->c[BGR_C_NOOVERLAP], (unsigned long long)c_nohit);
+            }
+        }
+    } else {
+        // ================================================================== workers
+        const u32 wtid = tid - 32;
+        u32 c_verify = 0;
+        for (u32 i = 0; i < my_tiles; ++i) {
+            const u32 b = i & 1;
+            TileMeta& m = meta(b);
+            mbar_wait(&bar_full[b], (i >> 1) & 1);
+            if (m.fits) {
+                if (m.wait_tma) mbar_wait(&bar_tma[b], m.tma_parity);
+                const u32 T = m.T, cnt = m.cnt, r0 = m.r0;
+                const unsigned char* cb = s_chars[b];
+                const u64 gs = tile_start(m.t_lo);
+                for (u32 j = wtid; j < T; j += WS_WORKERS) {
+                    // the read this chunk belongs to: last rd with prefix[rd] <= j
+                    u32 rd = 0;
+#pragma unroll
+                    for (u32 sft = ST_MAX_R / 2; sft; sft >>= 1) {
+                        const u32 c = rd + sft;
+                        if (c < cnt && m.prefix[c] <= j) rd = c;
+                    }
+                    const u32 l = j - m.prefix[rd];
+                    const u64 ro = m.off[rd];
+                    const u32 rlen = (u32)(m.off[rd + 1] - ro);
+                    const u32 rnwin = rlen - km1 + 1;
+                    const u32 rchunks = (rnwin + 31) >> 5;
+                    const u32 r = r0 + rd;
+                    const u64 wb = read_word_base(ro, r);
+                    u64 w0, w1;
+                    u32 bad = 0;
+                    if (PACKED) packed_span((const u64*)cb, ro - gs + 32 * l, w0, w1);
+                    else pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
+                    clip_span(rlen - 32 * l, w0, w1);
+                    // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
+                    u64* gF = a.F + wb;
+                    const u32 nw = (rlen + 31) >> 5;
+                    gF[1 + l] = w0;
+                    if (l == 0) gF[0] = 0;
+                    if (l + 1 == rchunks) {
+                        if (l + 1 < nw) gF[2 + l] = w1;
+                        gF[nw + 1] = 0;
+                        gF[nw + 2] = 0;
+                    }
+                    const u32 count = min(32u, rnwin - 32 * l);
+                    u32 hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, s_pat, km1, w0, w1, count);
+                    c_verify += __popc(hits);
+                    hits = verify_chunk(ix, w0, w1, hits);
+                    a.H1[wb + l] = hits;
+                    const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
+                    if (fl) atomicOr(&m.flags[rd], fl);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_done[b]);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c_verify += __shfl_xor_sync(0xFFFFFFFFu, c_verify, d);
+        if (lane == 0 && c_verify) atomicAdd(&a.scnt->c[BGR_C_VERIFIED], (unsigned long long)c_verify);
+    }
+}
+
 #endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------ extension: shared pieces

@@ -98,6 +98,7 @@ struct bgr_ctx {
     // resident CTAs per SM the kernels are compiled for (register budget); tuned on B200, see
     // profiles/. BGR_SCAN_MINB / BGR_EXT_MINB override for experiments.
     u32 scan_blocks_per_sm = 4, ext_blocks_per_sm = 5;
+    bool scan_ws = true;  // tile scan in its warp-specialised form (BGR_SCAN=classic: the barrier-per-phase form)
     std::string err;
 };
 
@@ -308,6 +309,7 @@ int bgr_ctx_create(int device, int n_slots, bgr_ctx** out) {
         int v = atoi(e);
         if (v == 4 || v == 6 || v == 8) ctx->scan_blocks_per_sm = (u32)v;
     }
+    if (const char* e = getenv("BGR_SCAN")) ctx->scan_ws = strcmp(e, "classic") != 0;
     if (const char* e = getenv("BGR_EXT_MINB")) {
         int v = atoi(e);
         if (v == 5 || v == 6 || v == 8) ctx->ext_blocks_per_sm = (u32)v;
@@ -644,18 +646,30 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
         // (a packed batch takes a quarter of a byte per base)
         u64 tr = (u64)(TILE_CB - 32) * (s.packed ? 4 : 1) / std::max<u64>(mean_len, 1);
         if (tr > ST_MAX_R) tr = ST_MAX_R;
+        if (ctx->scan_ws) {
+            // one chunk (32 windows) per worker thread and tile where the reads allow it
+            const u64 km1 = ctx->ix.k - 1;
+            const u64 chunks = mean_len >= km1 ? (mean_len - km1 + 1 + 31) / 32 : 1;
+            tr = std::min<u64>(tr, std::max<u64>(WS_WORKERS / std::max<u64>(chunks, 1), 2));
+        }
         s.tile_r = (u32)(tr & ~1ull);
         BatchArgs a = make_args(s);
         if (s.tile_r >= 2) {
             // tile scan: one persistent CTA per SM; the Bloom filter rides in shared memory when it is small
             const bool bloom_smem = !ctx->ix.bloom_two_hashes;
-            const size_t smem = tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
+            const size_t smem = ctx->scan_ws ? tile_ws_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB)
+                                             : tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
             const u32 ntiles = (s.n + s.tile_r - 1) / s.tile_r;
             const u32 blocks = std::min<u32>(ntiles, (u32)ctx->sm_count);
-#define BGR_LAUNCH_TILES(BS, PK, KS)                                                                              \
-    do {                                                                                                          \
-        CK(cudaFuncSetAttribute(k_scan_tiles<BS, PK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_scan_tiles<BS, PK, KS><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                               \
+#define BGR_LAUNCH_TILES(BS, PK, KS)                                                                                 \
+    do {                                                                                                             \
+        if (ctx->scan_ws) {                                                                                          \
+            CK(cudaFuncSetAttribute(k_scan_tiles_ws<BS, PK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_scan_tiles_ws<BS, PK, KS><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                           \
+        } else {                                                                                                     \
+            CK(cudaFuncSetAttribute(k_scan_tiles<BS, PK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_scan_tiles<BS, PK, KS><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                              \
+        }                                                                                                            \
     } while (0)
 #define BGR_LAUNCH_TILES_K(BS, PK)               \
     do {                                         \
