@@ -130,11 +130,21 @@ BGR_HD u64x4 ld_bucket(const u64* p) {
 }
 
 // 32 bases starting at base p (left-aligned). W[p/32 + 1] must be readable.
-BGR_HD u64 ld_bases(const u64* W, i64 p) {
-    i64 w = p >> 5;
-    u32 s = (u32)(p & 31) * 2;
-    u64 hi = W[w], lo = W[w + 1];
+// the same for two words already loaded: hi holds base 32*(p/32), lo the 32 bases after it
+BGR_HD u64 align_bases(u64 hi, u64 lo, u32 s /* 2 * (p % 32) */) {
+#if defined(__CUDA_ARCH__)
+    // 32-bit funnel shifts over the four half words: a variable 64-bit shift costs twice as much
+    const u32 h1 = (u32)(hi >> 32), h0 = (u32)hi, l1 = (u32)(lo >> 32), l0 = (u32)lo;
+    const bool big = s >= 32;
+    const u32 a = big ? h0 : h1, b = big ? l1 : h0, c = big ? l0 : l1;
+    return ((u64)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
+#else
     return (hi << s) | ((lo >> 1) >> (63 - s));
+#endif
+}
+BGR_HD u64 ld_bases(const u64* W, i64 p) {
+    const i64 w = p >> 5;
+    return align_bases(W[w], W[w + 1], (u32)(p & 31) * 2);
 }
 
 // slot index of `key`, or -1. A key lives in the first bucket at/after its home bucket that had a
@@ -1257,7 +1267,9 @@ BGR_HD Cands index_query(const DevIndex& ix, u64 bin, bool want_end) {
 #endif
     c.fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
     // slots are scanned in order up to the first empty one (aligner.cpp:172-203)
-    while (c.n < 4 && (c.raw[c.n] & SLOT_ID_MASK) != 0) ++c.n;
+    const bool s0 = (c.raw[0] & SLOT_ID_MASK) != 0, s1 = s0 && (c.raw[1] & SLOT_ID_MASK) != 0,
+               s2 = s1 && (c.raw[2] & SLOT_ID_MASK) != 0, s3 = s2 && (c.raw[3] & SLOT_ID_MASK) != 0;
+    c.n = (int)s0 + (int)s1 + (int)s2 + (int)s3;
     return c;
 }
 
@@ -1299,27 +1311,43 @@ BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, 
     const bool flip = u.rc != v.pass;    // the read segment is reverse-complemented before comparing
     const bool orN = v.pass && v.hasN;   // pass 1 sequence is F0|NM
     const bool useM = !v.pass && v.hasN;  // pass 0 carries the N mask
+    // The words of chunk c+1 are requested before chunk c is judged: the early exit below would otherwise
+    // put one memory round trip per 32 bases on the walk's critical path (the kernel waits on exactly these
+    // loads: profiles/r01_ncu_k_extend_greedy_v8_5Mbp.txt, long scoreboard).
+    //   chunk at `done`: unitig bases [ua+done, +m); read bases [sa+done, +m), or, flipped, the m bases that
+    //   end at sa+n-done
+    auto read_at = [&](i32 done, i32 m) -> i32 { return flip ? sa + n - done - m : sa + done; };
+    i32 m = n < 32 ? n : 32;
+    u64 xu = n > 0 ? ld_bases(ix.pool, ua) : 0ull;
+    u64 y = n > 0 ? ld_bases(v.D, read_at(0, m)) : 0ull;
+    u64 ymask = (n > 0 && v.hasN) ? ld_bases(v.ND, read_at(0, m)) : 0ull;
     u32 miss = 0;
     for (i32 done = 0; done < n; done += 32) {
-        const i32 m = (n - done < 32) ? n - done : 32;
-        u64 xu = ld_bases(ix.pool, ua + done);
+        const i32 left = n - done - 32;  // bases after this chunk
+        const i32 m_next = left < 32 ? left : 32;
+        u64 xu_n = 0, y_n = 0, ymask_n = 0;
+        if (left > 0) {
+            xu_n = ld_bases(ix.pool, ua + done + 32);
+            y_n = ld_bases(v.D, read_at(done + 32, m_next));
+            if (v.hasN) ymask_n = ld_bases(v.ND, read_at(done + 32, m_next));
+        }
         u64 xr, nm = 0;
         if (!flip) {
-            xr = ld_bases(v.D, sa + done);
-            if (orN) xr |= ld_bases(v.ND, sa + done);
-            if (useM) nm = ld_bases(v.ND, sa + done);
+            xr = orN ? (y | ymask) : y;
+            if (useM) nm = ymask;
         } else {
-            const i32 a = sa + n - done - m;
-            u64 y = ld_bases(v.D, a);
-            if (orN) y |= ld_bases(v.ND, a);
-            xr = rc64(y) << (64 - 2 * m);
-            if (useM) nm = rev2(ld_bases(v.ND, a)) << (64 - 2 * m);
+            xr = rc64(orN ? (y | ymask) : y) << (64 - 2 * m);
+            if (useM) nm = rev2(ymask) << (64 - 2 * m);
         }
         u64 d = xu ^ xr;
         d = (d | (d >> 1) | nm) & 0x5555555555555555ull;
         if (m < 32) d &= ~(~0ull >> (2 * m));
         miss += (u32)BGR_POPCLL(d);
         if (miss > cap) return cap + 1;
+        xu = xu_n;
+        y = y_n;
+        ymask = ymask_n;
+        m = m_next;
     }
     return miss;
 }
@@ -1704,6 +1732,9 @@ struct GreedyState {
                     rpos = pos;
                     nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
                 }
+                // the overlap this candidate would hand to the next level, requested together with the words
+                // of the comparison rather than after it (one dependent round trip less per level)
+                const u64 cand_code = ends_here ? 0ull : ((phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u));
                 const u32 miss = mismatches(ix, v, u, upos, rpos, nn, budget);
                 if (miss < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
                     best = miss;
@@ -1711,7 +1742,7 @@ struct GreedyState {
                     ended = ends_here;
                     offset = (i32)(L - pos);
                     next_L = L;
-                    if (!ends_here) next_code = (phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u);
+                    next_code = cand_code;
                     accepted = miss == 0;
                 }
             }
