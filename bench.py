@@ -447,6 +447,29 @@ def run_b200_arm(args):
     steps = max(args.steps, 1)
     value = world * n_reads * steps / (dev_ms[2] / 1e3)
 
+    # the same leg with the reads resident as the 2-bit stream the packed / mixed end-to-end forms upload
+    # (extra information: `value` above stays on the character form)
+    pk_all = torch.empty(n_reads * READ_LEN // 32 + 16, dtype=torch.int64, pin_memory=True)
+    bad_all = torch.empty(n_reads // 32 + 2, dtype=torch.int32, pin_memory=True)
+    nb = C.c_uint32()
+    ck(L.bgr_pack_reads(seqs.ctypes.data, off.ctypes.data, n_reads, max(1, host_cores() // max(1, world)),
+                        pk_all.data_ptr(), bad_all.data_ptr(), C.byref(nb)))
+    ck(L.bgr_slot_upload_packed(ctx, 0, pk_all.data_ptr(), off.ctypes.data, n_reads, bad_all.data_ptr(), nb.value,
+                                seqs.ctypes.data))
+    ck(L.bgr_slot_wait(ctx, 0, None))
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    dev_pk = np.zeros(3)
+    for _ in range(args.steps):
+        dev_pk += np.array(resident_step())
+    barrier()
+    dev_pk_t = torch.tensor(dev_pk, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dev_pk_t, op=dist.ReduceOp.MAX)
+    dev_pk = dev_pk_t.cpu().numpy()
+    del pk_all, bad_all
+
     # ================= leg 2: end to end through the C ABI with host buffers =================
     B = min(args.batch, n_reads)
     n_batches = (n_reads + B - 1) // B
@@ -604,6 +627,9 @@ def run_b200_arm(args):
                      "windows_per_read": w_per_read, "windows_source": w_src, "kernel_ms": scan_ms,
                      "note": ROOFLINE_NOTE % (stats["device_bytes"] / 1e6)},
         "kernel_ms": {"pack_scan": scan_ms, "extend": dev_ms[1] / steps},
+        "packed_input": {"value": world * n_reads * steps / (dev_pk[2] / 1e3), "unit": "reads/s",
+                         "kernel_ms": {"scan": dev_pk[0] / steps, "extend": dev_pk[1] / steps},
+                         "what": "same resident leg with the reads in HBM as the 2-bit stream of a packed upload"},
         "wall_ms_per_step_resident": 1e3 * (t_res1 - t_res0) / steps,
         "outcome": {"scope": "all ranks, per step", "reads": counters["reads"] // steps, "aligned": counters["aligned"] // steps,
                     "not_aligned": counters["not_aligned"] // steps, "no_overlap": counters["no_overlap"] // steps,

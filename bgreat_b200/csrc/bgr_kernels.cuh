@@ -657,6 +657,54 @@ __host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 t
     return b + 128;
 }
 
+// One chunk of a tile (both schedules of the tile scan): chunk j of the tile whose reads start at r0, with the
+// tile's offsets / chunk prefix sums / flag words in shared memory and its characters (or 2-bit words) at cb,
+// whose first base is base gs of the batch. Packs, stores the words for the extension kernel, scans, verifies,
+// stores the hit mask and flags the read. Returns the number of windows that passed the filter.
+template <bool BLOOM_SMEM, bool PACKED, u32 KM1S>
+__device__ __forceinline__ u32 tile_chunk(const DevIndex& ix, const BatchArgs& a, const u32* bloom, const u32* pat,
+                                          const u32 km1, const unsigned char* cb, const u64 gs, const u64* s_off,
+                                          const u32* s_prefix, u32* s_flags, const u32 cnt, const u32 r0, const u32 j) {
+    // the read this chunk belongs to: last rd with prefix[rd] <= j
+    u32 rd = 0;
+#pragma unroll
+    for (u32 sft = ST_MAX_R / 2; sft; sft >>= 1) {
+        const u32 c = rd + sft;
+        if (c < cnt && s_prefix[c] <= j) rd = c;
+    }
+    const u32 l = j - s_prefix[rd];
+    const u64 ro = s_off[rd];
+    const u32 rlen = (u32)(s_off[rd + 1] - ro);
+    const u32 rnwin = rlen - km1 + 1;
+    const u32 rchunks = (rnwin + 31) >> 5;
+    const u32 r = r0 + rd;
+    const u64 wb = read_word_base(ro, r);
+    u64 w0, w1;
+    u32 bad = 0;
+    if (PACKED) packed_span((const u64*)cb, ro - gs + 32 * l, w0, w1);
+    else pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
+    clip_span(rlen - 32 * l, w0, w1);
+    // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
+    u64* gF = a.F + wb;
+    const u32 nw = (rlen + 31) >> 5;
+    gF[1 + l] = w0;
+    if (l == 0) gF[0] = 0;
+    if (l + 1 == rchunks) {
+        if (l + 1 < nw) gF[2 + l] = w1;
+        gF[nw + 1] = 0;
+        gF[nw + 2] = 0;
+    }
+    const u32 count = min(32u, rnwin - 32 * l);
+    // the shared-memory tier is the single-hash tier (bloom_words_for)
+    u32 hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, pat, km1, w0, w1, count);
+    const u32 passed = (u32)__popc(hits);
+    hits = verify_chunk(ix, w0, w1, hits);
+    a.H1[wb + l] = hits;
+    const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
+    if (fl) atomicOr(&s_flags[rd], fl);
+    return passed;
+}
+
 // PACKED: the batch came as a 2-bit stream (bgr_slot_upload_packed); a tile is then the stream's words under
 // its reads, a chunk's two words are cut out of them with funnel shifts (packed_span) instead of being packed
 // from characters, and the reads the host flagged as holding a non-ACGT character are left to k_pack_scan.
@@ -807,45 +855,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
             const u32 T = S.prefix[cnt];
             const unsigned char* cb = S.chars[buf];
             const u64 gs = tile_start(t_lo);
-            for (u32 j = tid; j < T; j += ST_THREADS) {
-                // the read this chunk belongs to: last rd with prefix[rd] <= j
-                u32 rd = 0;
-#pragma unroll
-                for (u32 sft = ST_MAX_R / 2; sft; sft >>= 1) {
-                    const u32 c = rd + sft;
-                    if (c < cnt && S.prefix[c] <= j) rd = c;
-                }
-                const u32 l = j - S.prefix[rd];
-                const u64 ro = S.off[rd];
-                const u32 rlen = (u32)(S.off[rd + 1] - ro);
-                const u32 rnwin = rlen - km1 + 1;
-                const u32 rchunks = (rnwin + 31) >> 5;
-                const u32 r = r0 + rd;
-                const u64 wb = read_word_base(ro, r);
-                u64 w0, w1;
-                u32 bad = 0;
-                if (PACKED) packed_span((const u64*)cb, ro - gs + 32 * l, w0, w1);
-                else pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
-                clip_span(rlen - 32 * l, w0, w1);
-                // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
-                u64* gF = a.F + wb;
-                const u32 nw = (rlen + 31) >> 5;
-                gF[1 + l] = w0;
-                if (l == 0) gF[0] = 0;
-                if (l + 1 == rchunks) {
-                    if (l + 1 < nw) gF[2 + l] = w1;
-                    gF[nw + 1] = 0;
-                    gF[nw + 2] = 0;
-                }
-                const u32 count = min(32u, rnwin - 32 * l);
-                // the shared-memory tier is the single-hash tier (bloom_words_for)
-                u32 hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, S.pat, km1, w0, w1, count);
-                c_verify += __popc(hits);
-                hits = verify_chunk(ix, w0, w1, hits);
-                a.H1[wb + l] = hits;
-                const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
-                if (fl) atomicOr(&S.flags[rd], fl);
-            }
+            for (u32 j = tid; j < T; j += ST_THREADS)
+                c_verify += tile_chunk<BLOOM_SMEM, PACKED, KM1S>(ix, a, bloom, S.pat, km1, cb, gs, S.off, S.prefix, S.flags, cnt,
+                                                                  r0, j);
         }
         __syncthreads();
 
@@ -1144,44 +1156,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, Ba
                 const u32 T = m.T, cnt = m.cnt, r0 = m.r0;
                 const unsigned char* cb = s_chars[b];
                 const u64 gs = tile_start(m.t_lo);
-                for (u32 j = wtid; j < T; j += WS_WORKERS) {
-                    // the read this chunk belongs to: last rd with prefix[rd] <= j
-                    u32 rd = 0;
-#pragma unroll
-                    for (u32 sft = ST_MAX_R / 2; sft; sft >>= 1) {
-                        const u32 c = rd + sft;
-                        if (c < cnt && m.prefix[c] <= j) rd = c;
-                    }
-                    const u32 l = j - m.prefix[rd];
-                    const u64 ro = m.off[rd];
-                    const u32 rlen = (u32)(m.off[rd + 1] - ro);
-                    const u32 rnwin = rlen - km1 + 1;
-                    const u32 rchunks = (rnwin + 31) >> 5;
-                    const u32 r = r0 + rd;
-                    const u64 wb = read_word_base(ro, r);
-                    u64 w0, w1;
-                    u32 bad = 0;
-                    if (PACKED) packed_span((const u64*)cb, ro - gs + 32 * l, w0, w1);
-                    else pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
-                    clip_span(rlen - 32 * l, w0, w1);
-                    // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
-                    u64* gF = a.F + wb;
-                    const u32 nw = (rlen + 31) >> 5;
-                    gF[1 + l] = w0;
-                    if (l == 0) gF[0] = 0;
-                    if (l + 1 == rchunks) {
-                        if (l + 1 < nw) gF[2 + l] = w1;
-                        gF[nw + 1] = 0;
-                        gF[nw + 2] = 0;
-                    }
-                    const u32 count = min(32u, rnwin - 32 * l);
-                    u32 hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, s_pat, km1, w0, w1, count);
-                    c_verify += __popc(hits);
-                    hits = verify_chunk(ix, w0, w1, hits);
-                    a.H1[wb + l] = hits;
-                    const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
-                    if (fl) atomicOr(&m.flags[rd], fl);
-                }
+                for (u32 j = wtid; j < T; j += WS_WORKERS)
+                    c_verify += tile_chunk<BLOOM_SMEM, PACKED, KM1S>(ix, a, bloom, s_pat, km1, cb, gs, m.off, m.prefix, m.flags,
+                                                                      cnt, r0, j);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_done[b]);
