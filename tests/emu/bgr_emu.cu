@@ -71,6 +71,7 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     a.slow_list = nullptr;
     a.tile_r = 0;
     a.tile_cb = 0;
+    a.ext_lazy = 8;
     a.errors = errors;
     a.effort = effort;
     a.mode = mode;
