@@ -42,3 +42,50 @@ def test_product_does_not_reference_oracle_or_emulator():
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle/" not in src and "liboracle" not in src and "bgr_emu" not in src, f
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_packer_through_the_abi_needs_no_gpu():
+    """bgr_pack_reads is host code: the product library's own entry point, checked against plain Python
+    (the device side of the packed upload is covered by tests/test_gpu_packed_upload.py)."""
+    import ctypes as C
+    import random
+
+    import numpy as np
+    from bgreat_b200 import _abi as A
+    L = A.lib()
+    rng = random.Random(7)
+    reads = []
+    for i in range(5000):
+        ln = rng.choice([0, 1, 31, 32, 33, 100, 150, 151])
+        r = "".join(rng.choice("ACGT") for _ in range(ln))
+        if ln and rng.random() < 0.01:
+            p = rng.randrange(ln)
+            r = r[:p] + rng.choice("Nn*") + r[p + 1:]
+        reads.append(r)
+    text = "".join(reads).encode()
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    buf = np.frombuffer(text + b"\0", dtype=np.uint8)
+    for threads in (1, 3, 8):
+        words = np.full((len(text) + 31) // 32 + 1, 0xDEADBEEFDEADBEEF, dtype=np.uint64)
+        bad = np.full((len(reads) + 31) // 32 + 1, 0xFFFFFFFF, dtype=np.uint32)
+        nb = C.c_uint32()
+        assert L.bgr_pack_reads(buf.ctypes.data, off.ctypes.data, len(reads), threads, words.ctypes.data, bad.ctypes.data,
+                                C.byref(nb)) == 0
+        flagged = {i for i in range(len(reads)) if (int(bad[i >> 5]) >> (i & 31)) & 1}
+        assert flagged == {i for i, r in enumerate(reads) if any(c not in "ACGT" for c in r)}
+        assert nb.value == len(flagged) > 5
+        dirty = set()
+        for i in flagged:
+            dirty.update(range(int(off[i]) // 32, (int(off[i + 1]) + 31) // 32))
+        code = {"A": 0, "C": 1, "G": 2, "T": 3}
+        s = text.decode()
+        for w in range((len(s) + 31) // 32):
+            if w in dirty:
+                continue
+            v = 0
+            for j, c in enumerate(s[32 * w:32 * w + 32]):
+                v |= code[c] << (62 - 2 * j)
+            assert int(words[w]) == v, w
+    # argument checks
+    assert L.bgr_pack_reads(buf.ctypes.data, None, 1, 1, words.ctypes.data, bad.ctypes.data, None) == 2  # BGR_ERR_ARG
