@@ -115,6 +115,14 @@ class Aligner:
     def import_index_host(self, blob):
         self._ck(self.L.bgr_index_import_host(self.ctx, blob.ctypes.data, blob.nbytes))
 
+    def save_index(self, path):
+        """the index blob as a file (bgr_index_save_file)"""
+        self._ck(self.L.bgr_index_save_file(self.ctx, path.encode()))
+
+    def load_index(self, path):
+        """index from a file written by save_index, for this aligner's k (bgr_index_load_file)"""
+        self._ck(self.L.bgr_index_load_file(self.ctx, path.encode(), self.k))
+
     def get_begin(self, code):
         """getBegin (aligner.cpp:209): signed ids of the unitigs beginning with the (k-1)-mer code."""
         return self._query(code, 0)

@@ -391,10 +391,20 @@ int main(int argc, char** argv) {
 
     // ---- indexUnitigs (aligner.cpp:537-547)
     auto t0 = std::chrono::system_clock::now();
-    int rc = bgr_index_build_file(ctx, o.unitigs.c_str(), (uint32_t)o.k);
-    if (rc != BGR_OK && rc != BGR_ERR_IO) {  // a missing unitig file means an empty index, like the reference
-        fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
-        return 1;
+    // BGR_INDEX_CACHE=FILE: the index blob is taken from FILE when it is there and fits this k, and written to
+    // FILE after a build otherwise (keeping FILE in step with the unitig file is the user's business)
+    const char* cache = getenv("BGR_INDEX_CACHE");
+    int rc = (cache && *cache) ? bgr_index_load_file(ctx, cache, (uint32_t)o.k) : BGR_ERR_IO;
+    if (rc != BGR_OK) {
+        if (cache && *cache && rc != BGR_ERR_IO) fprintf(stderr, "bgreat: index cache not used: %s\n", bgr_last_error(ctx));
+        rc = bgr_index_build_file(ctx, o.unitigs.c_str(), (uint32_t)o.k);
+        if (rc != BGR_OK && rc != BGR_ERR_IO) {  // a missing unitig file means an empty index, like the reference
+            fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
+            return 1;
+        }
+        if (rc == BGR_OK && cache && *cache && bgr_index_save_file(ctx, cache) != BGR_OK)
+            fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
+        rc = BGR_OK;
     }
     auto t1 = std::chrono::system_clock::now();
     std::cout << "Indexing in seconds : " << std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count()

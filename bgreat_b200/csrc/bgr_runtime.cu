@@ -474,6 +474,39 @@ int bgr_index_import_host(bgr_ctx* ctx, const void* host_src, uint64_t bytes) {
     return install_host_blob(ctx, host_src, bytes);
 }
 
+int bgr_index_save_file(const bgr_ctx* cctx, const char* path) {
+    bgr_ctx* ctx = const_cast<bgr_ctx*>(cctx);
+    if (!ctx || !path) return fail(ctx, BGR_ERR_ARG, "null argument");
+    if (!ctx->has_index) return fail(ctx, BGR_ERR_NO_INDEX, "no index");
+    const u64 bytes = ctx->hdr.total_bytes;
+    std::vector<char> host(bytes);
+    int rc = bgr_index_export_host(ctx, host.data(), bytes);
+    if (rc) return rc;
+    // written under a temporary name and renamed: a reader never sees half a blob
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(ctx, BGR_ERR_IO, std::string("cannot write ") + tmp);
+    const bool ok = fwrite(host.data(), 1, bytes, f) == bytes;
+    if (fclose(f) != 0 || !ok || rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        return fail(ctx, BGR_ERR_IO, std::string("cannot write ") + path);
+    }
+    return BGR_OK;
+}
+
+int bgr_index_load_file(bgr_ctx* ctx, const char* path, uint32_t k) {
+    if (!ctx || !path) return fail(ctx, BGR_ERR_ARG, "null argument");
+    MappedFile mf;
+    if (!mf.open(path)) return fail(ctx, BGR_ERR_IO, std::string("cannot read ") + path);
+    if (mf.size < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index file too small");
+    BlobHeader h;
+    memcpy(&h, mf.data, sizeof h);
+    if (h.magic != BLOB_MAGIC || h.version != 4 || h.total_bytes != mf.size)
+        return fail(ctx, BGR_ERR_FORMAT, "index file: bad magic/version/size");
+    if (h.k != k) return fail(ctx, BGR_ERR_FORMAT, "index file was built for another k");
+    return install_host_blob(ctx, mf.data, mf.size);
+}
+
 int bgr_index_query(const bgr_ctx* cctx, uint64_t kmer_code, int want_end, int32_t ids[4]) {
     bgr_ctx* ctx = const_cast<bgr_ctx*>(cctx);
     if (!ctx || !ctx->has_index) return -BGR_ERR_NO_INDEX;

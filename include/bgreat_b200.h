@@ -122,6 +122,13 @@ int bgr_index_import_device(bgr_ctx* ctx, const void* dev_src, uint64_t bytes);
 int bgr_index_export_host(const bgr_ctx* ctx, void* host_dst, uint64_t bytes);
 int bgr_index_import_host(bgr_ctx* ctx, const void* host_src, uint64_t bytes);
 
+/* On-disk index cache (cf. the reference's unused mphf::save / load, BooPHF.h:927-1005):
+ * the flat blob as a file. bgr_index_load_file checks magic, version, size and that the blob was built for
+ * this k (BGR_ERR_FORMAT otherwise; BGR_ERR_IO if the file cannot be read); whether the file still matches the
+ * unitig file it was built from is the caller's business. */
+int bgr_index_save_file(const bgr_ctx* ctx, const char* path);
+int bgr_index_load_file(bgr_ctx* ctx, const char* path, uint32_t k);
+
 /* Debug/test view of the index: getBegin / getEnd (aligner.cpp:147-267) for one (k-1)-mer code
  * (str2num encoding, utils.cpp:117). Writes up to 4 signed unitig ids, returns the count (<0 on error). */
 int bgr_index_query(const bgr_ctx* ctx, uint64_t kmer_code, int want_end, int32_t ids[4]);

@@ -178,3 +178,31 @@ def test_cli_threads_and_fastq_mid_size(tmp_path):
         c = o.counters()
         assert "Reads : %d" % c["reads"] in lines
         assert any(l.startswith("Overlap and aligned : %d " % c["aligned"]) for l in lines)
+
+
+def test_cli_index_cache_file(tmp_path):
+    """BGR_INDEX_CACHE: the first run builds the index and writes the file, the second run maps from the file
+    (the unitig file is gone by then) with identical outputs; a cache built for another k is not used."""
+    case = next(c for c in CLI if "-b" not in c["args"] and "-o" not in c["args"] and "-c" not in c["args"]
+                and c["outputs"].get("paths"))
+    for fn, content in case["files"].items():
+        with open(tmp_path / fn, "w", newline="") as f:
+            f.write(content)
+    cache = str(tmp_path / "graph.bgr")
+    rc, lines, err = run_cli(case["args"], str(tmp_path), {"BGR_INDEX_CACHE": cache})
+    assert rc == 0, err
+    assert lines == case["stdout"] and os.path.getsize(cache) > 0
+    first = {fn: open(tmp_path / fn, newline="").read() for fn, w in case["outputs"].items() if w is not None}
+    unitig_file = case["args"][case["args"].index("-g") + 1] if "-g" in case["args"] else "unitig.fa"
+    os.rename(tmp_path / unitig_file, tmp_path / "moved_away.fa")
+    rc, lines, err = run_cli(case["args"], str(tmp_path), {"BGR_INDEX_CACHE": cache})
+    assert rc == 0, err
+    assert lines == case["stdout"]
+    for fn, want in first.items():
+        assert open(tmp_path / fn, newline="").read() == want == case["outputs"][fn], fn
+    # another k: the cache is refused (message on stderr) and, the unitig file being gone, the index is empty
+    args = list(case["args"])
+    ki = args.index("-k") + 1
+    args[ki] = str(int(args[ki]) + 1)
+    rc, lines, err = run_cli(args, str(tmp_path), {"BGR_INDEX_CACHE": cache})
+    assert "index cache not used" in err

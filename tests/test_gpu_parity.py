@@ -363,3 +363,36 @@ def test_correction_mode_k31_with_rc_and_n(bg):
         import ctypes as C
         al._ck(al.L.bgr_slot_run(al.ctx, 0, C.byref(p)))
     al.close()
+
+
+def test_index_file_cache_round_trip(bg, tmp_path):
+    """bgr_index_save_file / bgr_index_load_file: an index loaded from its file maps exactly like the one it
+    was saved from; a file built for another k, a truncated file and a missing file are refused."""
+    unitigs, reads = _k31_case(17, 3000)
+    al = bg.Aligner(31, 2, 2)
+    al.index_unitigs(unitigs)
+    want = al.align_batch(reads, O.GREEDY).as_tuples()
+    stats = al.index_stats()
+    path = str(tmp_path / "index.bgr")
+    al.save_index(path)
+    al.close()
+    assert os.path.getsize(path) == stats["device_bytes"]
+    al2 = bg.Aligner(31, 2, 2)
+    al2.load_index(path)
+    assert al2.index_stats() == stats
+    assert al2.align_batch(reads, O.GREEDY).as_tuples() == want
+    assert al2.align_batch_packed(reads, O.EXHAUSTIVE).as_tuples() == oracle_results(31, 2, 2, unitigs, reads, O.EXHAUSTIVE)[0]
+    al2.close()
+    al3 = bg.Aligner(25, 2, 2)
+    with pytest.raises(bg.BgrError) as e:
+        al3.load_index(path)
+    assert e.value.code == 5  # BGR_ERR_FORMAT
+    with open(path, "r+b") as f:
+        f.truncate(stats["device_bytes"] // 2)
+    with pytest.raises(bg.BgrError) as e:
+        al3.load_index(path)
+    assert e.value.code == 5
+    with pytest.raises(bg.BgrError) as e:
+        al3.load_index(str(tmp_path / "missing.bgr"))
+    assert e.value.code == 3  # BGR_ERR_IO
+    al3.close()
