@@ -47,8 +47,11 @@ WORKLOAD = "configs[1]: synthetic 5 Mbp diploid genome (SNP 1/150), k=31 unitigs
 ROOFLINE_NOTE = ("achieved = SURVEY 8(d) algorithmic bytes (one 32-byte index sector per (k-1)-mer window the reference "
                  "examines + 40 B of packed read) / measured kernel time. The kernel answers most windows from a Bloom "
                  "filter (shared memory for small indexes, L2 for large ones) and only verifies survivors in the key "
-                 "table, so it moves far fewer DRAM bytes than that model (see traffic) and frac can exceed 1: it is "
-                 "issue bound, not HBM bound. Index blob: %.1f MB.")
+                 "table, so it moves far fewer DRAM bytes than that model (see traffic) and frac can exceed 1: with the "
+                 "filter in shared memory it is bound by the integer ALU pipe (80 %% of peak, issue slots 68 %% busy: "
+                 "profiles/r01_ncu_k_scan_tiles_v9_5Mbp.txt), with the filter in L2 by L2 sector throughput (one random "
+                 "sector per window, 1.6 G sectors in 5.8 ms: profiles/r01_ncu_k_scan_tiles_v9_1Gbp.txt). "
+                 "Index blob: %.1f MB.")
 
 
 def configure(args):
