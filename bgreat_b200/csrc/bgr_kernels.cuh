@@ -88,8 +88,13 @@ struct BatchArgs {
     u32* H2;    // hit mask for the scan of the reverse-complemented read (only for reads with N)
     u32* info;  // per read: bit0 has N, bit1 any H1 hit, bit2 any H2 hit
     bgr_result* res;
-    i32* scratch;  // n * scratch_ints, interleaved (entry j of read r at scratch[j*n + r])
+    // extension scratch, scratch_ints per listed read: entry j of list row t at scratch[t*sc_row + j*sc_ent].
+    // Interleaved (sc_row 1, sc_ent n: a warp's accesses to the same entry of 32 rows coalesce; the greedy walk
+    // only appends) or row by row (sc_row scratch_ints, sc_ent 1: a row stays within a few cache lines; the
+    // exhaustive search reads and rewrites its frames and id lists all the time).
+    i32* scratch;
     u32 scratch_ints;
+    u32 sc_row, sc_ent;
     i32* pool;
     u64 pool_cap;
     DevCounters* cnt;
@@ -1595,7 +1600,7 @@ struct GreedyState {
     BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
         s = setup_read(ix, a, r);
         sc.base = scratch_row;
-        sc.stride = a.n;
+        sc.stride = a.sc_ent;
         sc.cap = a.scratch_ints;
         sc.overflow = false;
         flags = 0;
@@ -2028,7 +2033,7 @@ struct ExhaustiveState {
     BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
         s = setup_read(ix, a, r);
         sc.base = scratch_row;
-        sc.stride = a.n;
+        sc.stride = a.sc_ent;
         sc.cap = a.scratch_ints;
         sc.overflow = false;
         lay.init(a.scratch_ints);
@@ -2614,7 +2619,7 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
                 if (!have && rank < chunk_left) {
                     t = chunk_base + rank;
                     r = a.list[t];
-                    g.start(ix, a, r, a.scratch + t);
+                    g.start(ix, a, r, a.scratch + (size_t)t * a.sc_row);
                     have = true;
                 }
                 const u32 taken = min((u32)__popc(want), chunk_left);
@@ -2677,7 +2682,7 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_exhaustive_nodes(D
                 if (!have && rank < chunk_left) {
                     t = chunk_base + rank;
                     r = a.list[t];
-                    g.start(ix, a, r, a.scratch + t);
+                    g.start(ix, a, r, a.scratch + (size_t)t * a.sc_row);
                     have = true;
                 }
                 const u32 taken = min((u32)__popc(want), chunk_left);
@@ -2698,8 +2703,8 @@ __global__ void __launch_bounds__(EXT_THREADS) k_extend_exhaustive(DevIndex ix, 
     const bool valid = t < a.scnt->list_n;
     const u32 r = valid ? a.list[t] : 0;
     Scratch sc;
-    sc.base = a.scratch + (valid ? t : 0);
-    sc.stride = a.n;
+    sc.base = a.scratch + (size_t)(valid ? t : 0) * a.sc_row;
+    sc.stride = a.sc_ent;
     sc.cap = a.scratch_ints;
     sc.overflow = false;
     u32 flags = 0, n = 0, overlaps = 0;
@@ -2797,11 +2802,11 @@ __global__ void __launch_bounds__(CP_THREADS) k_path_gather(BatchArgs a, const u
         const u32 r = r0 + j;
         if (len[j]) {
             bgr_result res = rs[j];
-            const i32* src = a.scratch + res.path_off;  // scratch row
+            const i32* src = a.scratch + (size_t)res.path_off * a.sc_row;  // scratch row
             i32* dst = a.pool + off;
             // pathBegin was pushed walking away from the seed: reverse(pathBegin) (alignerGreedy.cpp:48)
-            const u32 nl = (res.flags_len & RES_REV_HEAD) ? (u32)src[(size_t)(a.scratch_ints - 1) * a.n] : 0u;
-            for (u32 q = 0; q < len[j]; ++q) dst[q] = src[(size_t)(q < nl ? nl - 1 - q : q) * a.n];
+            const u32 nl = (res.flags_len & RES_REV_HEAD) ? (u32)src[(size_t)(a.scratch_ints - 1) * a.sc_ent] : 0u;
+            for (u32 q = 0; q < len[j]; ++q) dst[q] = src[(size_t)(q < nl ? nl - 1 - q : q) * a.sc_ent];
             res.flags_len &= ~RES_REV_HEAD;
             res.path_off = (u32)off;
             a.res[r] = res;

@@ -223,6 +223,13 @@ BatchArgs make_args(Slot& s) {
     a.res = s.d_res;
     a.scratch = s.d_scratch;
     a.scratch_ints = s.scratch_ints;
+    {
+        // the node-per-turn exhaustive search keeps its rows compact, everything else interleaves them
+        bool rows = s.params.mode == BGR_MODE_EXHAUSTIVE || s.params.mode == BGR_MODE_EXHAUSTIVE_PATH;
+        if (const char* e = getenv("BGR_SCRATCH")) rows = !strcmp(e, "rows");
+        a.sc_row = rows ? s.scratch_ints : 1u;
+        a.sc_ent = rows ? 1u : s.n;
+    }
     a.pool = s.d_pool;
     a.pool_cap = s.cap_pool;
     a.cnt = s.d_cnt;

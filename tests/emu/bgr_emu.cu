@@ -63,6 +63,8 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     a.res = res;
     a.scratch = scratch.data();
     a.scratch_ints = scratch_ints;
+    a.sc_row = 1;
+    a.sc_ent = n;
     a.pool = pool;
     a.pool_cap = pool_cap;
     a.cnt = &cnt;
