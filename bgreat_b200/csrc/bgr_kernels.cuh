@@ -1286,13 +1286,18 @@ BGR_HD u64 last_code(const DevIndex& ix, const Oriented& u) {
 // missmatchNumber (utils.cpp:154-168) between n bases of the oriented unitig starting at upos and n
 // bases of the pass's read starting at rpos; the value is capped at cap+1 like the reference's
 // early exit. XOR + popc on 2-bit words, N mask ORed in.
-BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+// HASN_: 1 = the read holds non-ACGT characters (rare): only then are the mask words loaded and applied; 0 =
+// it does not; 2 = decided at run time (one copy of the loop: the exhaustive search calls this from four
+// places and runs slower with two specialised copies at each).
+template <int HASN_>
+BGR_HD u32 mismatches_t(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
     // forward pool coordinates of the unitig segment, stored coordinates of the read segment
     const i64 ua = (i64)u.start + (u.rc ? u.len - upos - n : upos);
     const i32 sa = v.pass ? v.len - rpos - n : rpos;
     const bool flip = u.rc != v.pass;    // the read segment is reverse-complemented before comparing
-    const bool orN = v.pass && v.hasN;   // pass 1 sequence is F0|NM
-    const bool useM = !v.pass && v.hasN;  // pass 0 carries the N mask
+    const bool HASN = HASN_ == 2 ? v.hasN : (HASN_ == 1);
+    const bool orN = HASN && v.pass;    // pass 1 sequence is F0|NM
+    const bool useM = HASN && !v.pass;  // pass 0 carries the N mask
     // The words of chunk c+1 are requested before chunk c is judged: the early exit below would otherwise
     // put one memory round trip per 32 bases on the walk's critical path (the kernel waits on exactly these
     // loads: profiles/r01_ncu_k_extend_greedy_v8_5Mbp.txt, long scoreboard).
@@ -1302,7 +1307,7 @@ BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, 
     i32 m = n < 32 ? n : 32;
     u64 xu = n > 0 ? ld_bases(ix.pool, ua) : 0ull;
     u64 y = n > 0 ? ld_bases(v.D, read_at(0, m)) : 0ull;
-    u64 ymask = (n > 0 && v.hasN) ? ld_bases(v.ND, read_at(0, m)) : 0ull;
+    u64 ymask = (HASN && n > 0) ? ld_bases(v.ND, read_at(0, m)) : 0ull;
     u32 miss = 0;
     for (i32 done = 0; done < n; done += 32) {
         const i32 left = n - done - 32;  // bases after this chunk
@@ -1311,7 +1316,7 @@ BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, 
         if (left > 0) {
             xu_n = ld_bases(ix.pool, ua + done + 32);
             y_n = ld_bases(v.D, read_at(done + 32, m_next));
-            if (v.hasN) ymask_n = ld_bases(v.ND, read_at(done + 32, m_next));
+            if (HASN) ymask_n = ld_bases(v.ND, read_at(done + 32, m_next));
         }
         u64 xr, nm = 0;
         if (!flip) {
@@ -1332,6 +1337,13 @@ BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, 
         m = m_next;
     }
     return miss;
+}
+BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+    return mismatches_t<2>(ix, v, u, upos, rpos, n, cap);
+}
+// the greedy walk's call site: N-free reads take a loop without any mask handling
+BGR_HD u32 mismatches_split(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+    return v.hasN ? mismatches_t<1>(ix, v, u, upos, rpos, n, cap) : mismatches_t<0>(ix, v, u, upos, rpos, n, cap);
 }
 
 // forward code of window i of the pass's read, as the seed scans store it
@@ -1714,7 +1726,7 @@ struct GreedyState {
                     rpos = pos;
                     nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
                 }
-                const u32 miss = mismatches(ix, v, u, upos, rpos, nn, budget);
+                const u32 miss = mismatches_split(ix, v, u, upos, rpos, nn, budget);
                 if (miss < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
                     best = miss;
                     best_sid = u.sid;
