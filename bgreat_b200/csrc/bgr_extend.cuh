@@ -1,0 +1,1294 @@
+// Overlap extension: what every aligner shares (read views, index queries, mismatch counting), the greedy
+// aligner (alignerGreedy.cpp:35-57,167-364), the exhaustive aligner (alignerExhaustive.cpp:35-259) and the
+// greedy "paths" aligner (alignerPaths.cpp). Per-read bodies only; the kernels are in bgr_emit.cuh.
+// Part of bgr_kernels.cuh.
+#pragma once
+#include "bgr_dev.cuh"
+
+namespace bgr {
+
+// ------------------------------------------------------------------------------ extension: shared pieces
+
+// One pass over a read: pass 0 is the read as given (N mismatches everything: missmatchNumber
+// compares characters, utils.cpp:154); pass 1 is reverseComplements(read) (utils.cpp:66), in which
+// every N has become 'A'. Both are views of the same stored words:
+//   pass 0 sequence  = F0 (N->0) with mask NM
+//   pass 1 sequence  = reverse complement of F2 = F0|NM (N->3), no mask
+struct ReadView {
+    const u64* D;   // data words (D[-1] and D[nw] are zero pads)
+    const u64* ND;  // N mask words
+    i32 len;
+    bool hasN;
+    bool pass;
+};
+
+struct Oriented {
+    u64 start;  // first base of the FORWARD unitig in the pool
+    i64 len;
+    i32 sid;  // signed id: negative = reverse complemented
+    bool rc;
+};
+
+struct Cands {
+    u32 raw[4];
+    int n;
+    u32 fwd_bit;
+};
+
+// getBegin / getEnd (aligner.cpp:147-267). The key's bucket and the payloads of that bucket's four slots
+// (one 128-byte line) are requested together: a key sits in its home bucket nearly always, and the walk
+// is a chain of dependent round trips, so the extra sectors are cheaper than a second trip.
+BGR_HD Cands index_query(const DevIndex& ix, u64 bin, bool want_end) {
+    Cands c;
+    c.n = 0;
+    c.fwd_bit = 0;
+    u64 rc = rcb(bin, ix.k - 1);
+    bool canon = bin <= rc;
+    const u64 key = canon ? bin : rc;
+    // getEnd: canonical -> right table, else left; getBegin: canonical -> left, else right
+    bool right = (want_end == canon);
+    const u64 b0 = bucket_of(key, ix.n_buckets);
+    const u64x4 v = ld_bucket(ix.keys + b0 * 4);
+    const u32* line = right ? ix.payload[b0 * 4].right : ix.payload[b0 * 4].left;
+    i64 slot;
+#if defined(__CUDA_ARCH__)
+    const uint4 p0 = __ldg((const uint4*)line), p1 = __ldg((const uint4*)(line + 8)), p2 = __ldg((const uint4*)(line + 16)),
+                p3 = __ldg((const uint4*)(line + 24));
+    uint4 p;
+    if (v.a == key) p = p0, slot = 0;
+    else if (v.b == key) p = p1, slot = 1;
+    else if (v.c == key) p = p2, slot = 2;
+    else if (v.d == key) p = p3, slot = 3;
+    else if (v.d == EMPTY_KEY) return c;
+    else {
+        slot = index_find(ix, key);  // overflowed into a later bucket
+        if (slot < 0) return c;
+        const u32* q = right ? ix.payload[slot].right : ix.payload[slot].left;
+        p = __ldg((const uint4*)q);
+    }
+    c.raw[0] = p.x;
+    c.raw[1] = p.y;
+    c.raw[2] = p.z;
+    c.raw[3] = p.w;
+#else
+    (void)v;
+    (void)line;
+    slot = index_find(ix, key);
+    if (slot < 0) return c;
+    const u32* q = right ? ix.payload[slot].right : ix.payload[slot].left;
+    for (int j = 0; j < 4; ++j) c.raw[j] = q[j];
+#endif
+    c.fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+    // slots are scanned in order up to the first empty one (aligner.cpp:172-203)
+    const bool s0 = (c.raw[0] & SLOT_ID_MASK) != 0, s1 = s0 && (c.raw[1] & SLOT_ID_MASK) != 0,
+               s2 = s1 && (c.raw[2] & SLOT_ID_MASK) != 0, s3 = s2 && (c.raw[3] & SLOT_ID_MASK) != 0;
+    c.n = (int)s0 + (int)s1 + (int)s2 + (int)s3;
+    return c;
+}
+
+BGR_HD Oriented orient(const DevIndex& ix, const Cands& c, int i) {
+    Oriented u;
+    u32 id = c.raw[i] & SLOT_ID_MASK;
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 m = __ldg((const ulonglong2*)&ix.meta[id]);
+    u.start = m.x;
+    u.len = (i64)(u32)m.y;
+#else
+    u.start = ix.meta[id].start;
+    u.len = ix.meta[id].len;
+#endif
+    u.rc = (c.raw[i] & c.fwd_bit) == 0;
+    u.sid = u.rc ? -(i32)id : (i32)id;
+    return u;
+}
+
+// str2num of the first / last k-1 bases of the oriented unitig
+BGR_HD u64 first_code(const DevIndex& ix, const Oriented& u) {
+    u32 km1 = ix.k - 1;
+    if (!u.rc) return ld_bases(ix.pool, (i64)u.start) >> (64 - 2 * km1);
+    return rcb(ld_bases(ix.pool, (i64)u.start + u.len - km1) >> (64 - 2 * km1), km1);
+}
+BGR_HD u64 last_code(const DevIndex& ix, const Oriented& u) {
+    u32 km1 = ix.k - 1;
+    if (!u.rc) return ld_bases(ix.pool, (i64)u.start + u.len - km1) >> (64 - 2 * km1);
+    return rcb(ld_bases(ix.pool, (i64)u.start) >> (64 - 2 * km1), km1);
+}
+
+// missmatchNumber (utils.cpp:154-168) between n bases of the oriented unitig starting at upos and n
+// bases of the pass's read starting at rpos; the value is capped at cap+1 like the reference's
+// early exit. XOR + popc on 2-bit words, N mask ORed in.
+// HASN_: 1 = the read holds non-ACGT characters (rare): only then are the mask words loaded and applied; 0 =
+// it does not; 2 = decided at run time (one copy of the loop: the exhaustive search calls this from four
+// places and runs slower with two specialised copies at each).
+template <int HASN_>
+BGR_HD u32 mismatches_t(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+    // forward pool coordinates of the unitig segment, stored coordinates of the read segment
+    const i64 ua = (i64)u.start + (u.rc ? u.len - upos - n : upos);
+    const i32 sa = v.pass ? v.len - rpos - n : rpos;
+    const bool flip = u.rc != v.pass;    // the read segment is reverse-complemented before comparing
+    const bool HASN = HASN_ == 2 ? v.hasN : (HASN_ == 1);
+    const bool orN = HASN && v.pass;    // pass 1 sequence is F0|NM
+    const bool useM = HASN && !v.pass;  // pass 0 carries the N mask
+    // The words of chunk c+1 are requested before chunk c is judged: the early exit below would otherwise
+    // put one memory round trip per 32 bases on the walk's critical path (the kernel waits on exactly these
+    // loads: profiles/r01_ncu_k_extend_greedy_v8_5Mbp.txt, long scoreboard).
+    //   chunk at `done`: unitig bases [ua+done, +m); read bases [sa+done, +m), or, flipped, the m bases that
+    //   end at sa+n-done
+    auto read_at = [&](i32 done, i32 m) -> i32 { return flip ? sa + n - done - m : sa + done; };
+    i32 m = n < 32 ? n : 32;
+    u64 xu = n > 0 ? ld_bases(ix.pool, ua) : 0ull;
+    u64 y = n > 0 ? ld_bases(v.D, read_at(0, m)) : 0ull;
+    u64 ymask = (HASN && n > 0) ? ld_bases(v.ND, read_at(0, m)) : 0ull;
+    u32 miss = 0;
+    for (i32 done = 0; done < n; done += 32) {
+        const i32 left = n - done - 32;  // bases after this chunk
+        const i32 m_next = left < 32 ? left : 32;
+        u64 xu_n = 0, y_n = 0, ymask_n = 0;
+        if (left > 0) {
+            xu_n = ld_bases(ix.pool, ua + done + 32);
+            y_n = ld_bases(v.D, read_at(done + 32, m_next));
+            if (HASN) ymask_n = ld_bases(v.ND, read_at(done + 32, m_next));
+        }
+        u64 xr, nm = 0;
+        if (!flip) {
+            xr = orN ? (y | ymask) : y;
+            if (useM) nm = ymask;
+        } else {
+            xr = rc64(orN ? (y | ymask) : y) << (64 - 2 * m);
+            if (useM) nm = rev2(ymask) << (64 - 2 * m);
+        }
+        u64 d = xu ^ xr;
+        d = (d | (d >> 1) | nm) & 0x5555555555555555ull;
+        if (m < 32) d &= ~(~0ull >> (2 * m));
+        miss += (u32)BGR_POPCLL(d);
+        if (miss > cap) return cap + 1;
+        xu = xu_n;
+        y = y_n;
+        ymask = ymask_n;
+        m = m_next;
+    }
+    return miss;
+}
+BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+    return mismatches_t<2>(ix, v, u, upos, rpos, n, cap);
+}
+// the greedy walk's call site: N-free reads take a loop without any mask handling
+BGR_HD u32 mismatches_split(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
+    return v.hasN ? mismatches_t<1>(ix, v, u, upos, rpos, n, cap) : mismatches_t<0>(ix, v, u, upos, rpos, n, cap);
+}
+
+// forward code of window i of the pass's read, as the seed scans store it
+// (getNOverlap / getListOverlap push `num`, aligner.cpp:326,354)
+BGR_HD u64 seed_code(const DevIndex& ix, const ReadView& v, i32 i) {
+    const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
+    if (!v.pass) {
+        u64 x = ld_bases(v.D, i) >> sh;
+        if (v.hasN && (u32)i < km1) {
+            u64 nm = ld_bases(v.ND, i) >> sh;
+            x |= nm & ~((1ull << (2 * i)) - 1);
+        }
+        return x;
+    }
+    i32 j = v.len - (i32)km1 - i;  // same window in stored coordinates
+    u64 x = ld_bases(v.D, j);
+    if (v.hasN) x |= ld_bases(v.ND, j);
+    return rcb(x >> sh, km1);
+}
+
+// per-read scratch: entry j of this read is base[j*stride]
+struct Scratch {
+    i32* base;
+    u32 stride, cap;
+    bool overflow;
+    BGR_HD void set(u32 j, i32 x) {
+        if (j < cap) base[(size_t)j * stride] = x;
+        else overflow = true;
+    }
+    BGR_HD i32 get(u32 j) const { return j < cap ? base[(size_t)j * stride] : 0; }
+};
+
+// Iterator over the seed windows of one pass in the order the reference visits them. Pass 0 walks
+// the set bits of the hit mask upwards. The windows of the reverse-complemented read are the same
+// (k-1)-mers mirrored, so pass 1 walks the stored bits downwards (of H2 when the read has N: its RC
+// copy has none and is scanned with the plain encoders). Positions are returned in pass coordinates.
+struct SeedIter {
+    const u32* H;
+    i32 nwin, lim, cur;
+    bool down;
+    BGR_HD void init(const u32* h, i32 nwin_, bool down_, i32 lim_) {
+        H = h;
+        nwin = nwin_;
+        down = down_;
+        cur = 0;
+        lim = lim_ < nwin_ ? lim_ : nwin_;
+    }
+    BGR_HD i32 next() {
+        while (cur < lim) {
+            i32 j = down ? nwin - 1 - cur : cur;
+            if (!down) {
+                u32 w = H[j >> 5] >> (j & 31);
+                if (w == 0) {
+                    cur += 32 - (j & 31);
+                    continue;
+                }
+                cur += BGR_FFS(w) - 1;
+            } else {
+                u32 w = H[j >> 5] << (31 - (j & 31));
+                if (w == 0) {
+                    cur += (j & 31) + 1;
+                    continue;
+                }
+                cur += BGR_CLZ(w);
+            }
+            if (cur >= lim) return -1;
+            return cur++;
+        }
+        return -1;
+    }
+};
+
+// ------------------------------------------------------------------------------ greedy extension
+
+// checkBeginGreedy == mapOnLeftEndGreedy (alignerGreedy.cpp:268-319,167-218), tail recursion
+// unrolled into a loop. Pushes to sc[n...]; returns false when the walk fails.
+BGR_HD bool greedy_left(const DevIndex& ix, const ReadView& v, u64 code, i32 pos, u32 budget, Scratch& sc, u32& n,
+                        u32& total) {
+    const i64 km1 = ix.k - 1;
+    u32 acc = 0;
+    for (;;) {
+        if (pos == 0) {
+            sc.set(n++, 0);
+            total = acc;
+            return true;
+        }
+        Cands c = index_query(ix, code, true);
+        u32 best = budget + 1;
+        i32 best_sid = 0, offset = 0;
+        bool ended = false, stepped = false;
+        u64 next_code = 0;
+        i64 next_L = 0;
+        for (int i = 0; i < c.n; ++i) {
+            Oriented u = orient(ix, c, i);
+            const i64 L = u.len - km1;  // bases left of the overlap
+            if (L >= pos) {
+                u32 miss = mismatches(ix, v, u, L - pos, 0, pos, budget);
+                if (miss == 0) {  // accepted at once (quirk 9)
+                    sc.set(n++, u.sid);
+                    sc.set(n++, (i32)(L - pos));
+                    total = acc;
+                    return true;
+                } else if (miss < best) {
+                    best = miss;
+                    best_sid = u.sid;
+                    ended = true;
+                    offset = (i32)(L - pos);
+                }
+            } else {
+                u32 miss = mismatches(ix, v, u, 0, pos - (i32)L, (i32)L, budget);
+                if (miss == 0) {
+                    sc.set(n++, u.sid);
+                    code = first_code(ix, u);
+                    pos -= (i32)L;
+                    stepped = true;  // continue the walk with the budget untouched
+                    break;
+                } else if (miss < best) {
+                    ended = false;
+                    best = miss;
+                    best_sid = u.sid;
+                    next_L = L;
+                    next_code = first_code(ix, u);
+                }
+            }
+        }
+        if (stepped) continue;
+        if (best > budget) return false;
+        sc.set(n++, best_sid);
+        if (ended) {
+            sc.set(n++, offset);
+            total = acc + best;
+            return true;
+        }
+        acc += best;
+        budget -= best;
+        code = next_code;
+        pos -= (i32)next_L;
+    }
+}
+
+// checkEndGreedy (first step, alignerGreedy.cpp:322-364) then mapOnRightEndGreedy (:221-265).
+// In the first step comparisons start after the anchor overlap; in later steps the remaining read
+// starts AT the overlap and the whole unitig is compared, so mismatches inside an overlap count
+// again (quirk 8).
+BGR_HD bool greedy_right(const DevIndex& ix, const ReadView& v, u64 code, i32 pos, u32 budget, Scratch& sc, u32& n,
+                         u32& total) {
+    const i64 km1 = ix.k - 1;
+    u32 acc = 0;
+    bool first = true;
+    for (;;) {
+        // first: readLeft = read[pos+k-1:], later: readLeft = read[pos:]
+        const i32 rstart = first ? pos + (i32)km1 : pos;
+        const i32 rl = v.len - rstart;
+        if (first ? (rl == 0) : (rl < (i32)ix.k)) {
+            total = acc;
+            return true;
+        }
+        Cands c = index_query(ix, code, false);
+        u32 best = budget + 1;
+        i32 best_sid = 0;
+        bool ended = false, stepped = false;
+        u64 next_code = 0;
+        i64 next_L = 0;
+        for (int i = 0; i < c.n; ++i) {
+            Oriented u = orient(ix, c, i);
+            const i64 L = u.len - km1;
+            const bool ends_here = L >= rl;
+            u32 miss;
+            if (first) {
+                // unitig[k-1 : k-1+n) against readLeft[0:n)
+                i32 n2 = ends_here ? rl : (i32)L;
+                miss = mismatches(ix, v, u, km1, rstart, n2, budget);
+            } else {
+                // unitig[0:n) against read[pos : pos+n): n = |readLeft| if it ends here, else
+                // min(|unitig|, |readLeft|) (substr is cut at the end of the read)
+                i32 n2 = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
+                miss = mismatches(ix, v, u, 0, rstart, n2, budget);
+            }
+            if (ends_here) {
+                if (miss == 0) {
+                    sc.set(n++, u.sid);
+                    total = acc;
+                    return true;
+                } else if (miss < best) {
+                    best = miss;
+                    best_sid = u.sid;
+                    ended = true;
+                }
+            } else {
+                if (miss == 0) {
+                    sc.set(n++, u.sid);
+                    code = last_code(ix, u);
+                    pos += (i32)L;
+                    stepped = true;
+                    break;
+                } else if (miss < best) {
+                    ended = false;
+                    best = miss;
+                    best_sid = u.sid;
+                    next_L = L;
+                    next_code = last_code(ix, u);
+                }
+            }
+        }
+        first = false;
+        if (stepped) continue;
+        if (best > budget) return false;
+        sc.set(n++, best_sid);
+        if (ended) {
+            total = acc + best;
+            return true;
+        }
+        acc += best;
+        budget -= best;
+        code = next_code;
+        pos += (i32)next_L;
+    }
+}
+
+struct ReadSetup {
+    ReadView v;
+    u64 wb;
+    u32 info;
+    i32 nwin;
+};
+
+BGR_HD ReadSetup setup_read(const DevIndex& ix, const BatchArgs& a, u32 r) {
+    ReadSetup s;
+    const u64 o = a.off[r];
+    const u32 len = (u32)(a.off[r + 1] - o);
+    s.wb = read_word_base(o, r);
+    s.info = a.info[r];
+    s.v.D = a.F + s.wb + 1;
+    s.v.ND = a.NM + s.wb + 1;
+    s.v.len = (i32)len;
+    s.v.hasN = (s.info & INFO_HAS_N) != 0;
+    s.v.pass = false;
+    const u32 km1 = ix.k - 1;
+    s.nwin = (len >= km1) ? (i32)(len - km1 + 1) : 0;
+    return s;
+}
+
+// alignReadGreedy (alignerGreedy.cpp:35-57) for read r. The path is left in scratch as
+// [0, nl) = pathBegin in push order (to be reversed) followed by [nl, n) = pathEnd.
+//
+// Written as ONE loop whose body is "settle the current level / pick the next seed / query the index"
+// followed by "compare one candidate unitig": threads of a warp work on different reads and are at
+// different points of their walks, but they all execute this same body, so the warp stays converged
+// (the first version, a call tree of walkers, ran with 1.65 of 32 lanes active:
+// profiles/r01_ncu_k_extend_greedy_v1.txt). The walkers greedy_left / greedy_right above are the
+// readable statement of the same procedure and are kept for the emulator's cross-check.
+enum { GP_SEED = 0, GP_LEFT = 1, GP_RIGHT_FIRST = 2, GP_RIGHT_MORE = 3, GP_DONE = 4 };
+
+struct GreedyState {
+    ReadSetup s;
+    Scratch sc;
+    SeedIter it;
+    u32 flags, n, nl, tried, phase;
+    // walk state
+    u64 code, seed_c;
+    i32 pos, seed_pos;
+    u32 budget, acc, eb;
+
+    BGR_HD bool done() const { return phase == GP_DONE; }
+
+    BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
+        s = setup_read(ix, a, r);
+        sc.base = scratch_row;
+        sc.stride = a.sc_ent;
+        sc.cap = a.scratch_ints;
+        sc.overflow = false;
+        flags = 0;
+        n = nl = 0;
+        tried = 0;
+        phase = GP_SEED;
+        // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
+        it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, a.effort ? s.nwin : 1);
+        code = seed_c = 0;
+        pos = seed_pos = 0;
+        budget = acc = eb = 0;
+    }
+
+    BGR_HD void succeed() {
+        flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (s.v.pass ? BGR_F_RC : 0u);
+        phase = GP_DONE;
+    }
+    BGR_HD void go_right(const BatchArgs& a) {  // the left walk is complete with `eb` mismatches
+        nl = n;
+        phase = GP_RIGHT_FIRST;
+        budget = a.errors - eb;
+        acc = 0;
+        code = seed_c;
+        pos = seed_pos;
+    }
+
+    // Seed selection, possibly switching to the reverse-complement pass: needed once per seed, i.e. rarely
+    // compared with the levels of a walk, so the kernel runs it for several lanes at once (see k_extend_greedy).
+    BGR_HD void pick_seed(const DevIndex& ix, const BatchArgs& a) {
+        ReadView& v = s.v;
+        const u32 max_seeds = a.effort ? a.effort : 1;
+        for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
+            i32 p = tried < max_seeds ? it.next() : -1;
+            if (p >= 0) {
+                ++tried;
+                seed_c = code = seed_code(ix, v, p);
+                seed_pos = pos = p;
+                budget = a.errors;
+                acc = 0;
+                n = 0;
+                phase = GP_LEFT;
+            } else if (tried == 0) {  // getNOverlap found nothing: ++noOverlapRead, return {}
+                flags |= BGR_F_CNT_NOOVERLAP;
+                phase = GP_DONE;
+            } else if (!v.pass) {  // every seed failed: rc=true, retry on the reverse complement
+                flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
+                v.pass = true;
+                const bool useH2 = v.hasN;
+                const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
+                it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, true, a.effort ? s.nwin : 1);
+                tried = 0;
+            } else {
+                flags |= BGR_F_CNT_NOTALIGNED;
+                phase = GP_DONE;
+            }
+        }
+    }
+
+    // One turn of the loop = one level of a walk: query the index -> compare the <= 4 candidates ->
+    // settle. Every lane of a warp that holds a seed runs these same stages every turn.
+    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+        if (phase == GP_SEED) pick_seed(ix, a);
+        if (phase != GP_SEED && phase != GP_DONE) step_level(ix, a);
+    }
+
+    BGR_HD void step_level(const DevIndex& ix, const BatchArgs& a) {
+        ReadView& v = s.v;
+        const i64 km1 = ix.k - 1;
+        // ---- ends of walks that need no index query
+        if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
+            sc.set(n++, 0);
+            eb = acc;
+            go_right(a);
+        }
+        if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) succeed();  // checkEndGreedy:324
+        if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) succeed();         // mapOnRightEndGreedy:223
+        if (phase == GP_DONE) return;
+        // ---- candidates of this level: getEnd on the way left, getBegin on the way right
+        const Cands c = index_query(ix, code, phase == GP_LEFT);
+        u32 best = budget + 1;
+        i32 best_sid = 0, offset = 0;
+        i64 next_L = 0;
+        u64 next_code = 0;
+        bool ended = false, accepted = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < c.n && !accepted) {
+                const Oriented u = orient(ix, c, i);
+                const i64 L = u.len - km1;
+                bool ends_here;
+                i64 upos;
+                i32 rpos, nn;
+                if (phase == GP_LEFT) {
+                    // unitig covers the rest: unitig[L-pos, L) vs read[0,pos); else unitig[0,L) vs read[pos-L,pos)
+                    ends_here = L >= pos;
+                    upos = ends_here ? L - pos : 0;
+                    rpos = ends_here ? 0 : pos - (i32)L;
+                    nn = ends_here ? pos : (i32)L;
+                } else if (phase == GP_RIGHT_FIRST) {
+                    // comparisons start after the anchor overlap
+                    const i32 rstart = pos + (i32)km1, rl = v.len - rstart;
+                    ends_here = L >= rl;
+                    upos = km1;
+                    rpos = rstart;
+                    nn = ends_here ? rl : (i32)L;
+                } else {
+                    // the remaining read starts AT the overlap; whole unitig compared, cut at the read end
+                    const i32 rl = v.len - pos;
+                    ends_here = L >= rl;
+                    upos = 0;
+                    rpos = pos;
+                    nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
+                }
+                const u32 miss = mismatches_split(ix, v, u, upos, rpos, nn, budget);
+                if (miss < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
+                    best = miss;
+                    best_sid = u.sid;
+                    ended = ends_here;
+                    offset = (i32)(L - pos);
+                    next_L = L;
+                    // (asking for this code together with the comparison's words, for every candidate, was
+                    // measured and lost: 3.91 vs 3.66 ms at 5 Mbp, 6.65 vs 5.35 ms at 1 Gbp -- the extra
+                    // random sectors cost more than the saved round trip)
+                    if (!ends_here) next_code = (phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u);
+                    accepted = miss == 0;
+                }
+            }
+        }
+        // ---- settle the level
+        if (best > budget) {
+            phase = GP_SEED;  // this seed failed
+            return;
+        }
+        sc.set(n++, best_sid);
+        // an exact candidate leaves the budget untouched, an inexact one pays for its mismatches
+        if (ended) {
+            if (phase == GP_LEFT) {
+                sc.set(n++, offset);
+                eb = acc + best;
+                go_right(a);
+            } else {
+                succeed();
+            }
+        } else {
+            acc += best;
+            budget -= best;
+            code = next_code;
+            if (phase == GP_LEFT) pos -= (i32)next_L;
+            else {
+                pos += (i32)next_L;
+                phase = GP_RIGHT_MORE;
+            }
+        }
+    }
+
+    // Path in final order in scratch [0, plen): pathBegin is reversed in place (alignerGreedy.cpp:48).
+    // Returns the path length (0 when unmapped or when the scratch overflowed).
+    BGR_HD u32 finish() {
+        if (!(flags & BGR_F_MAPPED) || sc.overflow) return 0;
+        for (u32 i = 0, j = nl; i + 1 < j; ++i) {
+            --j;
+            i32 x = sc.get(i), y = sc.get(j);
+            sc.set(i, y);
+            sc.set(j, x);
+        }
+        return n;
+    }
+    // Kernel form: pathBegin stays in walk order; its length goes into the last scratch entry and
+    // k_path_gather reverses it while copying the path into the pool (the in-place loop above runs with
+    // a few lanes of a warp active). The caller sets RES_REV_HEAD in the result's flags.
+    BGR_HD u32 finish_deferred() {
+        if (!(flags & BGR_F_MAPPED) || sc.overflow) return 0;
+        if (n + 1 > sc.cap) {
+            sc.overflow = true;
+            return 0;
+        }
+        sc.set(sc.cap - 1, (i32)nl);
+        return n;
+    }
+};
+
+// whole read in one go (emulator, and the shape the persistent kernel unrolls over time)
+BGR_HD u32 greedy_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
+    GreedyState g;
+    g.start(ix, a, r, sc.base);
+    g.sc.stride = sc.stride;
+    while (!g.done()) g.step(ix, a);
+    sc.overflow = g.sc.overflow;
+    n = (g.flags & BGR_F_MAPPED) ? g.n : 0;
+    nl = g.nl;
+    return g.flags;
+}
+
+// Reference-shaped version (walkers called in sequence); tests/emu checks that both agree.
+BGR_HD u32 greedy_read_walkers(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& nl) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    u32 flags = 0;
+    n = nl = 0;
+    const i32 lim = a.effort ? s.nwin : 1;
+    const u32 max_seeds = a.effort ? a.effort : 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        v.pass = pass != 0;
+        const bool useH2 = v.pass && v.hasN;
+        const bool anyhit = (s.info & (useH2 ? INFO_HIT2 : INFO_HIT1)) != 0;
+        SeedIter it;
+        it.init((useH2 ? a.H2 : a.H1) + s.wb, anyhit ? s.nwin : 0, v.pass, lim);
+        u32 tried = 0;
+        while (tried < max_seeds) {
+            i32 pos = it.next();
+            if (pos < 0) break;
+            ++tried;
+            u64 code = seed_code(ix, v, pos);
+            n = 0;
+            u32 eb = 0, ee = 0;
+            if (!greedy_left(ix, v, code, pos, a.errors, sc, n, eb)) continue;
+            nl = n;
+            if (!greedy_right(ix, v, code, pos, a.errors - eb, sc, n, ee)) continue;
+            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED | BGR_F_OVERLAP_FOUND | (pass ? BGR_F_RC : 0u);
+            return flags;
+        }
+        if (tried == 0) {
+            flags |= BGR_F_CNT_NOOVERLAP;
+            n = 0;
+            return flags;
+        }
+        flags |= BGR_F_OVERLAP_FOUND | BGR_F_RC;
+    }
+    flags |= BGR_F_CNT_NOTALIGNED;
+    n = 0;
+    return flags;
+}
+
+// ------------------------------------------------------------------------------ exhaustive extension
+//
+// The reference's recursion (alignerExhaustive.cpp:61-259) returns, at every level, the FIRST
+// candidate in slot order whose subtree reaches the minimal total mismatch count: equivalently the
+// first complete walk in depth-first order that attains the global minimum, provided it is within the
+// budget. That is what the iterative branch-and-bound search below keeps (strict < on update;
+// subtrees whose partial sum cannot beat the incumbent are skipped, which the reference also does
+// level by level with `miss < miniMiss`). alignReadExhaustivePath (alignerPaths.cpp:66-88) calls the
+// *Path helpers with empty vectors, so their "unitig already in path" filters never fire and the
+// results are the same.
+//
+// Scratch layout (ints): [0, 2*D+2) final path | cur ids [D] | best ids [D] | frames 5*[D].
+struct DfsLayout {
+    u32 D, out0, cur0, best0, fr0;
+    BGR_HD void init(u32 scratch_ints) {
+        D = scratch_ints > 11 ? (scratch_ints - 2) / 9 : 1;
+        out0 = 0;
+        cur0 = 2 * D + 2;
+        best0 = cur0 + D;
+        fr0 = best0 + D;
+    }
+};
+
+// Search one side. Returns true and (best_total, best_n ids at best0.., term) when a walk within
+// `budget` exists. term: left side = start offset or -1 (ended exactly on a unitig start: nothing
+// emitted); right side = end marker (|readLeft|+k-1, or 0 when the read ends on a unitig boundary).
+// avoid_n > 0 (greedy "paths" aligner only): the first avoid_n ints of the scratch row are the path built
+// so far, and a first-level candidate found in it is skipped (alignerPaths.cpp:136,307,370: the deeper
+// levels of the reference test against vectors that are still empty, so only depth 0 filters).
+BGR_HD bool exhaustive_side(const DevIndex& ix, const ReadView& v, bool right, u64 code0, i32 pos0, u32 budget,
+                            Scratch& sc, const DfsLayout& lay, u32& best_total, u32& best_n, i32& term,
+                            u32 avoid_n = 0) {
+    const i64 km1 = ix.k - 1;
+    best_total = budget + 1;
+    best_n = 0;
+    term = -1;
+    i32 depth = 0;
+    // frame: code (2 ints), pos, acc, next candidate
+    auto fr_set = [&](u32 d, u64 code, i32 pos, u32 acc, u32 next) {
+        u32 b = lay.fr0 + 5 * d;
+        sc.set(b, (i32)(u32)code);
+        sc.set(b + 1, (i32)(u32)(code >> 32));
+        sc.set(b + 2, pos);
+        sc.set(b + 3, (i32)acc);
+        sc.set(b + 4, (i32)next);
+    };
+    fr_set(0, code0, pos0, 0, 0);
+    while (depth >= 0) {
+        const u32 fb = lay.fr0 + 5 * (u32)depth;
+        const u64 code = (u64)(u32)sc.get(fb) | ((u64)(u32)sc.get(fb + 1) << 32);
+        const i32 pos = sc.get(fb + 2);
+        const u32 acc = (u32)sc.get(fb + 3);
+        const u32 next = (u32)sc.get(fb + 4);
+        // how much of the read is left on this side
+        const i32 rl = right ? v.len - (pos + (i32)km1) : pos;
+        if (rl == 0) {
+            // the read is used up exactly at a unitig boundary (mapOnLeftEndExhaustive:112 returns 0
+            // pushing nothing; mapOnRightEndExhaustive:64 pushes 0)
+            if (acc < best_total) {
+                best_total = acc;
+                best_n = (u32)depth;
+                term = right ? 0 : -1;
+                for (u32 j = 0; j < best_n; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+            }
+            --depth;
+            continue;
+        }
+        Cands c = index_query(ix, code, !right);
+        bool descended = false;
+        for (u32 i = next; i < (u32)c.n; ++i) {
+            if (acc >= best_total) break;  // nothing below can be strictly better
+            Oriented u = orient(ix, c, (int)i);
+            if (avoid_n && depth == 0) {
+                bool seen = false;
+                for (u32 j = 0; j < avoid_n; ++j) seen |= sc.get(j) == u.sid;
+                if (seen) continue;
+            }
+            const i64 L = u.len - km1;
+            const u32 cap = best_total - 1 - acc;  // a candidate is useful only if acc+miss < best_total
+            if (L >= rl) {
+                u32 miss = right ? mismatches(ix, v, u, km1, pos + (i32)km1, rl, cap)
+                                 : mismatches(ix, v, u, L - rl, 0, rl, cap);
+                if (miss <= cap) {
+                    best_total = acc + miss;
+                    best_n = (u32)depth + 1;
+                    term = right ? rl + (i32)km1 : (i32)(L - rl);
+                    for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+                    sc.set(lay.best0 + (u32)depth, u.sid);
+                }
+            } else {
+                u32 miss = right ? mismatches(ix, v, u, km1, pos + (i32)km1, (i32)L, cap)
+                                 : mismatches(ix, v, u, 0, rl - (i32)L, (i32)L, cap);
+                if (miss <= cap) {
+                    if ((u32)depth + 1 >= lay.D) {
+                        // search stack too small: give up on this read at once, the host re-runs the
+                        // batch with a larger scratch (carrying on would only enumerate dead ends)
+                        sc.overflow = true;
+                        return false;
+                    }
+                    sc.set(lay.cur0 + (u32)depth, u.sid);
+                    sc.set(fb + 4, (i32)(i + 1));
+                    u64 nc = right ? last_code(ix, u) : first_code(ix, u);
+                    fr_set((u32)depth + 1, nc, right ? pos + (i32)L : pos - (i32)L, acc + miss, 0);
+                    ++depth;
+                    descended = true;
+                    break;
+                }
+            }
+        }
+        if (!descended) --depth;
+    }
+    return best_total <= budget;
+}
+
+// alignReadExhaustive (alignerExhaustive.cpp:35-58) for read r; the final path is left in scratch
+// [0, n) in output order.
+BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n, u32& overlaps) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    const u32 km1 = ix.k - 1;
+    DfsLayout lay;
+    lay.init(a.scratch_ints);
+    n = 0;
+    overlaps = (u32)s.nwin;  // overlaps += listOverlap.size(): every window is listed
+    u32 flags = BGR_F_OVERLAP_FOUND;
+    if (s.nwin == 0) return flags | BGR_F_CNT_NOTALIGNED;  // shorter than k-1: see DESIGN.md
+    if ((u32)v.len == km1) {
+        // single window, nothing on either side: checkBegin pushes 0, checkEnd pushes 0
+        sc.set(0, 0);
+        sc.set(1, 0);
+        n = 2;
+        return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+    }
+    // Every window is tried in order, but only windows whose (k-1)-mer is a border can succeed: a
+    // window at pos>0 needs getEnd non-empty, window 0 needs getBegin non-empty (the read is longer
+    // than the window here).
+    SeedIter it;
+    it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, s.nwin);
+    for (;;) {
+        i32 pos = it.next();
+        if (pos < 0) break;
+        u64 code = seed_code(ix, v, pos);
+        u32 eb = 0, nb = 0, ee = 0, ne = 0;
+        i32 tb = 0, te = 0;
+        u32 w = 0;
+        if (pos == 0) {
+            sc.set(w++, 0);  // checkBeginExhaustive:159
+        } else {
+            if (!exhaustive_side(ix, v, false, code, pos, a.errors, sc, lay, eb, nb, tb)) {
+                if (sc.overflow) break;
+                continue;
+            }
+            // left part in output order: [offset] then the ids from the far end to the anchor
+            if (tb >= 0) sc.set(w++, tb);
+            for (u32 j = 0; j < nb; ++j) sc.set(w++, sc.get(lay.best0 + nb - 1 - j));
+        }
+        if (!exhaustive_side(ix, v, true, code, pos, a.errors - eb, sc, lay, ee, ne, te)) {
+            if (sc.overflow) break;
+            continue;
+        }
+        for (u32 j = 0; j < ne; ++j) sc.set(w++, sc.get(lay.best0 + j));
+        sc.set(w++, te);
+        n = w;
+        return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+    }
+    n = 0;
+    return flags | BGR_F_CNT_NOTALIGNED;
+}
+
+// ---- the same search as a resumable state machine: one turn = one node of the depth-first search
+// (index query -> candidate compares until one is worth descending into -> descend or return). This is
+// what the persistent kernel runs: lanes of a warp are at different nodes of different searches but
+// execute the same body every turn. exhaustive_read above is the loop-shaped statement of the same
+// procedure; tests/emu runs both and compares.
+enum { XP_SEED = 0, XP_LEFT = 1, XP_RIGHT = 2, XP_DONE = 3 };
+
+struct ExhaustiveState {
+    ReadSetup s;
+    Scratch sc;
+    SeedIter it;
+    DfsLayout lay;
+    u32 flags, phase, n;
+    // current seed
+    u64 seed_c;
+    i32 seed_pos;
+    u32 w, eb;  // ints of the final path written so far; mismatches spent on the left side
+    // current search (one side)
+    u32 budget, best_total, best_n;
+    i32 term, depth;
+    // top frame, kept in registers; the frames below it live in the scratch row
+    u64 f_code;
+    i32 f_pos;
+    u32 f_acc, f_next;
+
+    BGR_HD bool done() const { return phase == XP_DONE; }
+
+    BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
+        s = setup_read(ix, a, r);
+        sc.base = scratch_row;
+        sc.stride = a.sc_ent;
+        sc.cap = a.scratch_ints;
+        sc.overflow = false;
+        lay.init(a.scratch_ints);
+        flags = BGR_F_OVERLAP_FOUND;
+        n = 0;
+        w = eb = 0;
+        phase = XP_SEED;
+        seed_c = 0;
+        seed_pos = 0;
+        budget = best_total = best_n = 0;
+        term = -1;
+        depth = -1;
+        f_code = 0;
+        f_pos = 0;
+        f_acc = f_next = 0;
+        const u32 km1 = ix.k - 1;
+        it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, s.nwin);
+        if (s.nwin == 0) {  // shorter than k-1: see DESIGN.md
+            flags |= BGR_F_CNT_NOTALIGNED;
+            phase = XP_DONE;
+        } else if ((u32)s.v.len == km1) {  // single window, nothing on either side: [0, 0]
+            sc.set(0, 0);
+            sc.set(1, 0);
+            n = 2;
+            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+            phase = XP_DONE;
+        }
+    }
+
+    BGR_HD void begin_side(bool right, u32 budget_) {
+        phase = right ? XP_RIGHT : XP_LEFT;
+        budget = budget_;
+        best_total = budget_ + 1;
+        best_n = 0;
+        term = -1;
+        depth = 0;
+        f_code = seed_c;
+        f_pos = seed_pos;
+        f_acc = 0;
+        f_next = 0;
+    }
+
+    // alignReadExhaustive's loop header (alignerExhaustive.cpp:41): the next window that can be a seed
+    BGR_HD void pick_seed(const DevIndex& ix, const BatchArgs& a) {
+        if (phase != XP_SEED) return;
+        const i32 p = it.next();
+        if (p < 0) {
+            n = 0;
+            flags |= BGR_F_CNT_NOTALIGNED;
+            phase = XP_DONE;
+            return;
+        }
+        seed_pos = p;
+        seed_c = seed_code(ix, s.v, p);
+        w = 0;
+        eb = 0;
+        if (p == 0) {
+            sc.set(w++, 0);  // checkBeginExhaustive:159
+            begin_side(true, a.errors);
+        } else {
+            begin_side(false, a.errors);
+        }
+    }
+
+    BGR_HD void pop_frame() {
+        --depth;
+        if (depth >= 0) {
+            const u32 b = lay.fr0 + 5 * (u32)depth;
+            f_code = (u64)(u32)sc.get(b) | ((u64)(u32)sc.get(b + 1) << 32);
+            f_pos = sc.get(b + 2);
+            f_acc = (u32)sc.get(b + 3);
+            f_next = (u32)sc.get(b + 4);
+        }
+    }
+
+    // the side's search is over: left -> store its part of the path and search the right side;
+    // right -> the read is mapped. A side without a walk within the budget fails the seed.
+    BGR_HD void side_finished(const BatchArgs& a) {
+        const bool ok = best_total <= budget;
+        if (!ok || sc.overflow) {
+            if (sc.overflow) {  // the host re-runs the batch with a larger scratch
+                n = 0;
+                flags |= BGR_F_CNT_NOTALIGNED;
+                phase = XP_DONE;
+            } else {
+                phase = XP_SEED;
+            }
+            return;
+        }
+        if (phase == XP_LEFT) {
+            // left part in output order: [offset] then the ids from the far end to the anchor
+            if (term >= 0) sc.set(w++, term);
+            for (u32 j = 0; j < best_n; ++j) sc.set(w++, sc.get(lay.best0 + best_n - 1 - j));
+            eb = best_total;
+            begin_side(true, a.errors - eb);
+        } else {
+            for (u32 j = 0; j < best_n; ++j) sc.set(w++, sc.get(lay.best0 + j));
+            sc.set(w++, term);
+            n = w;
+            flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+            phase = XP_DONE;
+        }
+    }
+
+    // one node of the search (the body of exhaustive_side's while loop)
+    BGR_HD void step_node(const DevIndex& ix, const BatchArgs& a) {
+        const ReadView& v = s.v;
+        const i64 km1 = ix.k - 1;
+        const bool right = phase == XP_RIGHT;
+        const i32 rl = right ? v.len - (f_pos + (i32)km1) : f_pos;
+        if (rl == 0) {
+            if (f_acc < best_total) {
+                best_total = f_acc;
+                best_n = (u32)depth;
+                term = right ? 0 : -1;
+                for (u32 j = 0; j < best_n; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+            }
+            pop_frame();
+        } else {
+            const Cands c = index_query(ix, f_code, !right);
+            bool descended = false;
+            for (u32 i = f_next; i < (u32)c.n; ++i) {
+                if (f_acc >= best_total) break;  // nothing below can be strictly better
+                const Oriented u = orient(ix, c, (int)i);
+                const i64 L = u.len - km1;
+                const u32 cap = best_total - 1 - f_acc;
+                if (L >= rl) {
+                    const u32 miss = right ? mismatches(ix, v, u, km1, f_pos + (i32)km1, rl, cap)
+                                           : mismatches(ix, v, u, L - rl, 0, rl, cap);
+                    if (miss <= cap) {
+                        best_total = f_acc + miss;
+                        best_n = (u32)depth + 1;
+                        term = right ? rl + (i32)km1 : (i32)(L - rl);
+                        for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+                        sc.set(lay.best0 + (u32)depth, u.sid);
+                    }
+                } else {
+                    const u32 miss = right ? mismatches(ix, v, u, km1, f_pos + (i32)km1, (i32)L, cap)
+                                           : mismatches(ix, v, u, 0, rl - (i32)L, (i32)L, cap);
+                    if (miss <= cap) {
+                        if ((u32)depth + 1 >= lay.D) {  // search stack too small: give up, the host grows the scratch
+                            sc.overflow = true;
+                            depth = -1;
+                            side_finished(a);
+                            return;
+                        }
+                        // park this frame (resume with candidate i+1), make the child the top frame
+                        const u32 b = lay.fr0 + 5 * (u32)depth;
+                        sc.set(b, (i32)(u32)f_code);
+                        sc.set(b + 1, (i32)(u32)(f_code >> 32));
+                        sc.set(b + 2, f_pos);
+                        sc.set(b + 3, (i32)f_acc);
+                        sc.set(b + 4, (i32)(i + 1));
+                        sc.set(lay.cur0 + (u32)depth, u.sid);
+                        f_code = right ? last_code(ix, u) : first_code(ix, u);
+                        f_pos = right ? f_pos + (i32)L : f_pos - (i32)L;
+                        f_acc += miss;
+                        f_next = 0;
+                        ++depth;
+                        descended = true;
+                        break;
+                    }
+                }
+            }
+            if (!descended) pop_frame();
+        }
+        if (depth < 0) side_finished(a);
+    }
+
+    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+        if (phase == XP_SEED) pick_seed(ix, a);
+        if (phase == XP_LEFT || phase == XP_RIGHT) step_node(ix, a);
+    }
+};
+
+// ------------------------------------------------------------------------------ greedy "paths" aligner
+//
+// alignReadGreedyPath and its helpers (alignerPaths.cpp:35-63 driver, :91-124 coverGreedyPath,
+// :178-234 mapOnRightPath, :237-286 checkPairPaths; the two ends use the exhaustive path walkers,
+// :289-411). Unreachable from the reference's command line (pathOption is never set) but part of
+// class Aligner's public interface. ONE path vector collects everything in call order: the left walk
+// of the start seed, the right walk of the END seed, then the cover between them, and it is not
+// cleared between failed (start, end) attempts: reproduced as is. "Already in the path" compares a
+// signed unitig id with every int of that vector, offsets included (std::find over vector<uNumber>).
+//
+// Scratch row: [0, P) the path | cur ids [D] | best ids [D] | search frames 5*[D].
+struct PathLayout {
+    u32 P;
+    DfsLayout dfs;
+    BGR_HD void init(u32 scratch_ints) {
+        P = scratch_ints / 2;
+        const u32 rest = scratch_ints - P;
+        dfs.D = rest >= 14 ? rest / 7 : 1;
+        dfs.out0 = 0;
+        dfs.cur0 = P;
+        dfs.best0 = dfs.cur0 + dfs.D;
+        dfs.fr0 = dfs.best0 + dfs.D;
+    }
+};
+
+struct PathBuf {
+    Scratch* sc;
+    u32 n, cap;
+    BGR_HD void push(i32 x) {
+        if (n < cap) sc->set(n, x);
+        else sc->overflow = true;
+        ++n;
+    }
+    BGR_HD bool contains(i32 x) const {
+        bool seen = false;
+        const u32 m = n < cap ? n : cap;
+        for (u32 j = 0; j < m; ++j) seen |= sc->get(j) == x;
+        return seen;
+    }
+};
+
+// checkPairPaths (alignerPaths.cpp:237-286): the unitig that begins with the (k-1)-mer of window p1
+// and ends with the one of window p2. Returns the mismatch count (allowed+1 = none) and the id in `number`.
+BGR_HD u32 check_pair_paths(const DevIndex& ix, const ReadView& v, const PathBuf& path, i32 p1, i32 p2, i32& number,
+                            u32 allowed) {
+    const i32 km1 = (i32)ix.k - 1;
+    const Cands c1 = index_query(ix, seed_code(ix, v, p1), false);  // getBegin(overlap1)
+    const Cands c2 = index_query(ix, seed_code(ix, v, p2), true);   // getEnd(overlap2)
+    if (p2 - p1 < (i32)ix.k) {
+        // the two windows overlap: any common unitig is taken without looking at the read
+        for (int i = 0; i < c1.n; ++i) {
+            const i32 id1 = orient(ix, c1, i).sid;
+            for (int j = 0; j < c2.n; ++j)
+                if (orient(ix, c2, j).sid == id1) {
+                    if (!path.contains(id1)) number = id1;
+                    return 0;
+                }
+        }
+        return allowed + 1;
+    }
+    const i32 sub_len = p2 - p1 - km1;
+    u32 best = allowed + 1;
+    i32 best_sid = 0;
+    for (int i = 0; i < c1.n; ++i) {
+        const Oriented u = orient(ix, c1, i);
+        for (int j = 0; j < c2.n; ++j) {
+            if (orient(ix, c2, j).sid == u.sid && !path.contains(u.sid)) {
+                if (u.len - 2 * (i64)km1 == (i64)sub_len) {
+                    const u32 miss = mismatches(ix, v, u, km1, p1 + km1, sub_len, allowed);
+                    if (miss < best) {
+                        best = miss;
+                        best_sid = u.sid;
+                    }
+                }
+            }
+        }
+    }
+    if (best <= allowed) number = best_sid;
+    return best;
+}
+
+// mapOnRightPath (alignerPaths.cpp:178-234), tail recursion as a loop. Walks right from window
+// `start` until the read ends (ended) or the walk lands exactly on a later listed window (first = its
+// index). Returns false when no walk within `budget` exists; second = mismatches spent.
+BGR_HD bool map_on_right_path(const DevIndex& ix, const ReadView& v, PathBuf& path, i32 start, i32 nwin, u32 budget,
+                              bool& ended, i32& first, u32& second) {
+    const i32 km1 = (i32)ix.k - 1;
+    u64 code = seed_code(ix, v, start);
+    i32 pos = start;
+    u32 total = 0;
+    for (;;) {
+        const i32 rl = v.len - (pos + km1);
+        if (rl <= 0) {  // the reference prints "should not appears" and exits; unreachable (start < end)
+            first = start;
+            second = total;
+            return true;
+        }
+        const Cands c = index_query(ix, code, false);
+        u32 best = budget + 1;
+        i32 best_sid = 0, next = start;
+        bool have_best = false;
+        u64 next_code = 0;
+        i64 next_L = 0;
+        for (int i = 0; i < c.n; ++i) {
+            const Oriented u = orient(ix, c, i);
+            if (path.contains(u.sid)) continue;
+            const i64 L = u.len - km1;
+            if ((i64)rl <= L) {
+                const u32 miss = mismatches(ix, v, u, km1, pos + km1, rl, budget);
+                if (miss < best) {
+                    ended = true;
+                    best = miss;
+                    best_sid = u.sid;
+                    have_best = true;
+                }
+            } else {
+                const u32 miss = mismatches(ix, v, u, km1, pos + km1, (i32)L, budget);
+                if (miss < best) {
+                    const u64 oc = last_code(ix, u);
+                    ended = false;
+                    best = miss;
+                    best_sid = u.sid;
+                    have_best = true;
+                    next_code = oc;
+                    next_L = L;
+                    next = start;
+                    // a later listed overlap at exactly that position with that code (list[j].pos == j)
+                    const i64 j = (i64)pos + L;
+                    if (j >= (i64)start + 1 && j < (i64)nwin && seed_code(ix, v, (i32)j) == oc) next = (i32)j;
+                }
+            }
+        }
+        if (ended) {
+            if (have_best) path.push(best_sid);
+            first = start;
+            second = total + best;
+            return true;
+        }
+        if (best > budget) return false;
+        path.push(best_sid);
+        total += best;
+        if (next > start) {
+            first = next;
+            second = total;
+            return true;
+        }
+        budget -= best;
+        code = next_code;
+        pos += (i32)next_L;
+    }
+}
+
+// coverGreedyPath (alignerPaths.cpp:91-124), recursion as a loop: joins window `start` to window
+// `end` by single unitigs between listed windows (checkPairPaths) or, failing that, by a rightward walk.
+BGR_HD bool cover_greedy_path(const DevIndex& ix, const ReadView& v, PathBuf& path, i32 start, i32 end, i32 nwin,
+                              u32 budget, u32 effort) {
+    bool ended = false;
+    for (;;) {
+        if (start == end) return true;
+        i32 indice = 0, keep = 0;
+        u32 best = budget + 1;
+        for (u32 i = 1; (i64)i + start <= (i64)end && i <= effort; ++i) {
+            i32 number = 0;
+            const u32 miss = check_pair_paths(ix, v, path, start, start + (i32)i, number, budget);
+            if (miss < best) {
+                indice = (i32)i;
+                keep = number;
+                best = miss;
+            }
+        }
+        if (best <= budget) {
+            path.push(keep);
+            budget -= best;
+            start += indice;
+            continue;
+        }
+        i32 first = start;
+        u32 second = 0;
+        if (!map_on_right_path(ix, v, path, start, nwin, budget, ended, first, second)) return false;
+        if (second > budget) return false;
+        if (ended) return true;
+        if (first <= start) return false;
+        budget -= second;
+        start = first;
+    }
+}
+
+// alignReadGreedyPath (alignerPaths.cpp:35-63) for read r; the path is left in scratch [0, n).
+BGR_HD u32 greedy_path_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratch& sc, u32& n) {
+    ReadSetup s = setup_read(ix, a, r);
+    ReadView& v = s.v;
+    PathLayout lay;
+    lay.init(a.scratch_ints);
+    n = 0;
+    const u32 flags = BGR_F_OVERLAP_FOUND;
+    if (s.nwin == 0) return flags | BGR_F_CNT_NOTALIGNED;  // shorter than k-1: see DESIGN.md
+    const i32 nwin = s.nwin;  // listOverlap holds every window: list[j].second == j
+    const u32 last_start = (a.effort - 1u) < (u32)(nwin - 1) ? (a.effort - 1u) : (u32)(nwin - 1);
+    PathBuf path;
+    path.sc = &sc;
+    path.cap = lay.P;
+    for (u32 start = 0; start <= last_start; ++start) {
+        path.n = 0;
+        u32 eb = 0, nb = 0;
+        i32 tb = 0;
+        if (start == 0) {
+            path.push(0);  // checkBeginExhaustivePath:352
+        } else {
+            if (!exhaustive_side(ix, v, false, seed_code(ix, v, (i32)start), (i32)start, a.errors, sc, lay.dfs, eb, nb,
+                                 tb)) {
+                if (sc.overflow) return flags | BGR_F_CNT_NOTALIGNED;
+                continue;
+            }
+            if (tb >= 0) path.push(tb);
+            for (u32 j = 0; j < nb; ++j) path.push(sc.get(lay.dfs.best0 + nb - 1 - j));
+        }
+        const i32 lo = (i32)start > nwin - (i32)a.effort ? (i32)start : nwin - (i32)a.effort;
+        for (i32 end = nwin - 1; end >= lo; --end) {
+            u32 ee = 0, ne = 0;
+            i32 te = 0;
+            const u32 avoid = path.n < path.cap ? path.n : path.cap;  // >= 1: the left part is never empty
+            if (!exhaustive_side(ix, v, true, seed_code(ix, v, end), end, a.errors - eb, sc, lay.dfs, ee, ne, te,
+                                 avoid)) {
+                if (sc.overflow) return flags | BGR_F_CNT_NOTALIGNED;
+                continue;
+            }
+            for (u32 j = 0; j < ne; ++j) path.push(sc.get(lay.dfs.best0 + j));
+            path.push(te);
+            if (cover_greedy_path(ix, v, path, (i32)start, end, nwin, a.errors - ee - eb, a.effort)) {
+                n = path.n;
+                return flags | BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
+            }
+            if (sc.overflow) return flags | BGR_F_CNT_NOTALIGNED;
+        }
+    }
+    n = 0;
+    return flags | BGR_F_CNT_NOTALIGNED;
+}
+
+}  // namespace bgr

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "bgr_emu.cu")
 LIB = os.path.join(HERE, "emu", "libbgr_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "bgreat_b200", "csrc", f)
-                for f in ("bgr_kernels.cuh", "bgr_common.h", "bgr_host.cpp", "bgr_host.h", "bgr_pack.cpp")]
+                for f in ("bgr_kernels.cuh", "bgr_dev.cuh", "bgr_scan.cuh", "bgr_extend.cuh", "bgr_emit.cuh", "bgr_common.h",
+                          "bgr_host.cpp", "bgr_host.h", "bgr_pack.cpp")]
 
 _lib = None
 
