@@ -232,8 +232,10 @@ static inline int out_of(uint32_t flags, bool split_no_overlap) {
 }
 
 // bytes reads [lo, hi) of the batch put into each of the three files
-static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, bool correction, size_t sz[3]) {
-    sz[0] = sz[1] = sz[2] = 0;
+static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_overlap, bool correction, size_t out_sz[3]) {
+    // summed in locals: the workers' result slots are neighbours in one array, and adding to them per read made
+    // the cores fight over the cache line
+    size_t sz[3] = {0, 0, 0};
     for (size_t i = lo; i < hi; ++i) {
         const bgr_result r = b.res.p[i];
         const uint32_t flags = BGR_RESULT_FLAGS(r), len = BGR_RESULT_LEN(r);
@@ -249,6 +251,9 @@ static void measure_range(const Batch& b, size_t lo, size_t hi, bool split_no_ov
         }
         sz[o] += n;
     }
+    out_sz[0] = sz[0];
+    out_sz[1] = sz[1];
+    out_sz[2] = sz[2];
 }
 
 // header\npath\n for mapped reads (printPath, aligner.cpp:600-609), header\nread\n otherwise

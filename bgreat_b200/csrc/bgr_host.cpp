@@ -504,7 +504,9 @@ struct Rec {
     uint32_t hn, sn;
 };
 
-struct Shard {
+// one per worker; padded to its own cache lines: the workers push records and add to `chars` for every read, and
+// two shards sharing a line made two workers slower than one (parse phase 0.158 s -> 0.208 s on 4 M reads)
+struct alignas(128) Shard {
     std::vector<Rec> recs;
     std::deque<std::string> joined;  // multi-line FASTA reads (stable addresses)
     uint64_t chars = 0;
@@ -575,7 +577,7 @@ void parse_fastq_range(const char* d, size_t a, size_t b, Shard& out) {
     }
 }
 
-size_t count_newlines(const char* d, size_t a, size_t b) {
+size_t count_newlines_scalar(const char* d, size_t a, size_t b) {
     size_t c = 0;
     for (size_t pos = a; pos < b;) {
         const void* nl = memchr(d + pos, '\n', b - pos);
@@ -586,12 +588,96 @@ size_t count_newlines(const char* d, size_t a, size_t b) {
     return c;
 }
 
+#ifdef BGR_HAVE_AVX2_PATH
+// newline bitmask of the 32 bytes at p
+__attribute__((target("avx2"))) inline uint32_t newline_mask32(const char* p) {
+    const __m256i x = _mm256_loadu_si256((const __m256i*)p);
+    return (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('\n')));
+}
+__attribute__((target("avx2,popcnt"))) size_t count_newlines_avx2(const char* d, size_t a, size_t b) {
+    size_t c = 0, pos = a;
+    for (; pos + 32 <= b; pos += 32) c += (size_t)__builtin_popcount(newline_mask32(d + pos));
+    return c + count_newlines_scalar(d, pos, b);
+}
+// position right after the j-th newline (1-based) at or after a; the caller guarantees that it exists
+__attribute__((target("avx2,popcnt"))) size_t after_newline_avx2(const char* d, size_t a, size_t j) {
+    size_t pos = a;
+    for (;;) {
+        // 32 bytes at a time while the j-th newline cannot be in them; the newline exists, so the bytes up to it
+        // are readable -- a block is only loaded whole when even all-newlines would not overshoot
+        if (j > 32) {
+            j -= (size_t)__builtin_popcount(newline_mask32(d + pos));
+            pos += 32;
+            continue;
+        }
+        const char* nl = (const char*)rawmemchr(d + pos, '\n');
+        pos = (size_t)(nl - d) + 1;
+        if (--j == 0) return pos;
+    }
+}
+#endif
+
+// newlines in [a, b): the FASTQ reader and the unitig loader cut their input by line numbers, so this pass runs
+// over every byte of such a file; one 32-byte compare + popcount per step instead of a memchr call per line
+size_t count_newlines(const char* d, size_t a, size_t b) {
+#ifdef BGR_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+    if (avx2) return count_newlines_avx2(d, a, b);
+#endif
+    return count_newlines_scalar(d, a, b);
+}
+
 // position right after the j-th newline (1-based) at or after a; j newlines must exist
 size_t after_newline(const char* d, size_t a, size_t j) {
+#ifdef BGR_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+    if (avx2) return after_newline_avx2(d, a, j);
+#endif
     size_t pos = a;
     while (j--) pos = (size_t)((const char*)rawmemchr(d + pos, '\n') - d) + 1;
     return pos;
 }
+
+// Line numbers -> positions for a text [a, b): the newlines of T slices are counted in parallel, per 64 KB block,
+// so that "right after the j-th newline" is found by skipping whole blocks and scanning one (a second pass over
+// the text otherwise, and the last cut was made by one thread).
+struct LineIndex {
+    static const size_t BLK = (size_t)1 << 16;
+    std::vector<size_t> lo, cnt;  // T+1 slice bounds; cnt[t] = newlines before slice t
+    std::vector<std::vector<uint32_t>> blk;
+    void build(const char* d, size_t a, size_t b, unsigned T, WorkerPool& pool) {
+        lo.assign(T + 1, 0);
+        cnt.assign(T + 1, 0);
+        blk.assign(T, std::vector<uint32_t>());
+        for (unsigned t = 0; t <= T; ++t) lo[t] = a + (size_t)((b - a) / T) * t;
+        lo[T] = b;
+        pool.run(T, [&](unsigned t) {
+            std::vector<uint32_t> mine;  // local: the slices' vectors are neighbours in memory
+            mine.reserve((lo[t + 1] - lo[t]) / BLK + 1);
+            size_t c = 0;
+            for (size_t pos = lo[t]; pos < lo[t + 1]; pos += BLK) {
+                const size_t n = count_newlines(d, pos, std::min(pos + BLK, lo[t + 1]));
+                mine.push_back((uint32_t)n);
+                c += n;
+            }
+            blk[t].swap(mine);
+            cnt[t + 1] = c;
+        });
+        for (unsigned t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
+    }
+    size_t total() const { return cnt.back(); }
+    // position right after newline number j (1-based, j <= total())
+    size_t after(const char* d, size_t j) const {
+        const unsigned t = (unsigned)(std::upper_bound(cnt.begin(), cnt.end(), j - 1) - cnt.begin()) - 1;  // cnt[t] < j <= cnt[t+1]
+        size_t left = j - cnt[t], pos = lo[t];
+        for (uint32_t n : blk[t]) {
+            if (left <= n) break;  // the newline is in this block
+            left -= n;
+            pos += BLK;
+        }
+        return after_newline(d, pos, left);
+    }
+};
 
 // append the shards' records to the batch, in shard order, copying in parallel
 void gather(std::vector<Shard>& sh, size_t T, WorkerPool& pool, ParsedBatch& out) {
@@ -707,13 +793,11 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
         const size_t b = final ? n_ : a + win;
         const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, (b - a) / min_slice_ + 1));
         // newline counts per slice
-        std::vector<size_t> lo(T + 1), cnt(T + 1, 0);
-        for (unsigned t = 0; t <= T; ++t) lo[t] = a + (size_t)((b - a) / T) * t;
-        lo[T] = b;
         WorkerPool& pool = impl_->pool;
-        pool.run(T, [&](unsigned t) { cnt[t + 1] = count_newlines(d_, lo[t], lo[t + 1]); });
-        for (unsigned t = 0; t < T; ++t) cnt[t + 1] += cnt[t];  // cnt[t] = newlines before slice t
-        const size_t q = cnt[T] / 4;  // whole newline-terminated records in [a, b)
+        const auto t0 = std::chrono::steady_clock::now();
+        LineIndex li;
+        li.build(d_, a, b, T, pool);
+        const size_t q = li.total() / 4;  // whole newline-terminated records in [a, b)
         size_t P;                     // records parsed here by the workers
         if (final) P = q ? ((q - 1) / CH) * CH : 0;  // the last <= 2*CH records go to the sequential parser
         else P = (q / CH) * CH;
@@ -724,18 +808,22 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
         // start of record r = right after newline number 4r
         auto record_start = [&](size_t r) -> size_t {
             if (r == 0) return a;
-            const size_t j = 4 * r;  // 1-based newline number
-            unsigned t = (unsigned)(std::upper_bound(cnt.begin(), cnt.end(), j - 1) - cnt.begin()) - 1;  // cnt[t] < j <= cnt[t+1]
-            return after_newline(d_, lo[t], j - cnt[t]);
+            return li.after(d_, 4 * r);  // 1-based newline number
         };
         std::vector<size_t> cut(T + 1);
         pool.run(T, [&](unsigned t) { cut[t] = record_start(P / T * t); });
         cut[T] = record_start(P);
+        const auto t1 = std::chrono::steady_clock::now();
         std::vector<Shard>& sh = impl_->shards(T);
         pool.run(T, [&](unsigned t) {
             if (cut[t] < cut[t + 1]) parse_fastq_range(d_, cut[t], cut[t + 1], sh[t]);
         });
+        const auto t2 = std::chrono::steady_clock::now();
         gather(sh, T, pool, out);
+        const auto t3 = std::chrono::steady_clock::now();
+        phase_s[0] += std::chrono::duration<double>(t1 - t0).count();
+        phase_s[1] += std::chrono::duration<double>(t2 - t1).count();
+        phase_s[2] += std::chrono::duration<double>(t3 - t2).count();
         pos_ = cut[T];
         if (final) {
             // the end of the stream, exactly as the reference sees it
@@ -773,18 +861,13 @@ bool load_unitig_file_parallel(const char* path, uint32_t k, unsigned threads, P
     const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads ? threads : 1, n / (min_slice ? min_slice : 1) + 1));
     WorkerPool pool(T - 1);
     // newline counts per slice -> start of record r (= right after newline number 2r)
-    std::vector<size_t> lo(T + 1), cnt(T + 1, 0);
-    for (unsigned t = 0; t <= T; ++t) lo[t] = (size_t)(n / T) * t;
-    lo[T] = n;
-    pool.run(T, [&](unsigned t) { cnt[t + 1] = count_newlines(d, lo[t], lo[t + 1]); });
-    for (unsigned t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
-    const size_t q = cnt[T] / 2;        // whole newline-terminated records
+    LineIndex li;
+    li.build(d, 0, n, T, pool);
+    const size_t q = li.total() / 2;    // whole newline-terminated records
     const size_t P = q ? q - 1 : 0;     // records the workers take; the rest is the sequential tail
     auto record_start = [&](size_t r) -> size_t {
         if (r == 0) return 0;
-        const size_t j = 2 * r;
-        const unsigned t = (unsigned)(std::upper_bound(cnt.begin(), cnt.end(), j - 1) - cnt.begin()) - 1;
-        return after_newline(d, lo[t], j - cnt[t]);
+        return li.after(d, 2 * r);
     };
     std::vector<size_t> cut(T + 1), first_rec(T + 1);
     for (unsigned t = 0; t <= T; ++t) first_rec[t] = P / T * t;
@@ -792,7 +875,7 @@ bool load_unitig_file_parallel(const char* path, uint32_t k, unsigned threads, P
     pool.run(T, [&](unsigned t) { cut[t] = record_start(first_rec[t]); });
     cut[T] = record_start(P);
     // pass 1: sequence line of every record (view), up to the worker's first line shorter than k
-    struct Part {
+    struct alignas(128) Part {  // own cache lines: see Shard
         std::vector<std::pair<const char*, size_t>> recs;
         uint64_t chars = 0;
         bool stopped = false;

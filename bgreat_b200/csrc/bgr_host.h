@@ -212,7 +212,7 @@ class ParallelReader {
     bool done() const { return finished_; }
     // appends the records of the next range to `out` (which the caller has cleared)
     void next(ParsedBatch& out);
-    // wall time spent so far in the phases of next(): cutting, parsing, copying (FASTA; diagnostics)
+    // wall time spent so far in the phases of next(): cutting (FASTQ: counting lines), parsing, copying (diagnostics)
     double phase_s[3] = {0, 0, 0};
 
    private:
