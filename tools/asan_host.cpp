@@ -2,6 +2,9 @@
 // several thread counts, random batch and slice sizes) against the sequential parser, and the 2-bit packer.
 #include "bgr_host.h"
 #include <stdio.h>
+#include <stdlib.h>
+#include <unistd.h>
+#include <algorithm>
 #include <random>
 #include <string>
 #include <vector>
@@ -39,6 +42,39 @@ int main() {
         uint32_t n1 = pack_reads_2bit(rb.seqs.p ? rb.seqs.p : "", rb.soff.p, (uint32_t)rb.size(), 1, words.data(), bad.data());
         uint32_t n2 = pack_reads_2bit(rb.seqs.p ? rb.seqs.p : "", rb.soff.p, (uint32_t)rb.size(), 7, w2.data(), b2.data());
         if (n1 != n2 || bad != b2) { printf("PACK MISMATCH\n"); return 1; }
+    }
+    // unitig loader: parallel (line index, per-worker parts) against the sequential record loop
+    for (int iter = 0; iter < 40; ++iter) {
+        std::string text;
+        const size_t nrec = g() % 2000;
+        for (size_t i = 0; i < nrec; ++i) {
+            const size_t len = (g() % 400 == 0) ? g() % 31 : 31 + g() % 300;  // a short line stops the loading
+            text += ">" + std::to_string(i) + "\n" + rnd_seq(g, len, 0.0) + "\n";
+        }
+        if (g() % 4 == 0 && !text.empty()) text.pop_back();
+        if (g() % 7 == 0) text += ">dangling header";
+        char path[] = "/tmp/bgr_asan_unitigs_XXXXXX";
+        const int fd = mkstemp(path);
+        if (fd < 0) return 2;
+        FILE* f = fdopen(fd, "wb");
+        fwrite(text.data(), 1, text.size(), f);
+        fclose(f);
+        std::string s1;
+        std::vector<uint64_t> o1;
+        const bool ok1 = load_unitig_file(path, 31, s1, o1);
+        for (unsigned T : {1u, 3u, 8u}) {
+            PodBuf<char> s2;
+            PodBuf<uint64_t> o2;
+            const bool ok2 = load_unitig_file_parallel(path, 31, T, s2, o2, 1 + g() % 3000);
+            if (ok1 != ok2 || o2.n != o1.size() || std::string(s2.p ? s2.p : "", s2.n) != s1 ||
+                !std::equal(o1.begin(), o1.end(), o2.p)) {
+                printf("UNITIG LOADER MISMATCH iter %d T %u\n", iter, T);
+                remove(path);
+                return 1;
+            }
+            ++checks;
+        }
+        remove(path);
     }
     printf("ok %d checks\n", checks);
     return 0;
