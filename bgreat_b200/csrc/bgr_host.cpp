@@ -557,7 +557,7 @@ void parse_fasta_range(const char* d, size_t a, size_t b, uint32_t k, Shard& out
 
 // whole 4-line FASTQ records in [a, b), every line newline-terminated (aligner.cpp:49-67 away from
 // the end of the stream)
-void parse_fastq_range(const char* d, size_t a, size_t b, Shard& out) {
+void parse_fastq_range_scalar(const char* d, size_t a, size_t b, Shard& out) {
     size_t pos = a;
     while (pos < b) {
         const size_t h = pos;
@@ -615,7 +615,51 @@ __attribute__((target("avx2,popcnt"))) size_t after_newline_avx2(const char* d, 
         if (--j == 0) return pos;
     }
 }
+
+// parse_fastq_range with the newlines found 32 bytes at a time: a record is four lines whatever they hold, so
+// every fourth newline closes one; no search call per line (four memchr calls per record were 60 of its 80 ns)
+__attribute__((target("avx2"))) void parse_fastq_range_avx2(const char* d, size_t a, size_t b, Shard& out) {
+    size_t start = a;       // first byte of the current line
+    size_t h = a, hn = 0, s = 0, sn = 0;
+    unsigned li = 0;        // line of the record the next newline ends: 0 header, 1 sequence, 2 '+', 3 quality
+    uint64_t chars = 0;
+    auto newline_at = [&](size_t nl) {
+        if (li == 0) {
+            h = start;
+            hn = nl - start;
+        } else if (li == 1) {
+            s = start;
+            sn = nl - start;
+        } else if (li == 3) {
+            if (sn > 2 && sn <= 0xFFFFFFFFull && acgtn_only(d + s, sn)) {
+                out.recs.push_back(Rec{d + h, d + s, (uint32_t)hn, (uint32_t)sn});
+                chars += sn;
+            }
+        }
+        li = (li + 1) & 3;
+        start = nl + 1;
+    };
+    size_t pos = a;
+    for (; pos + 32 <= b; pos += 32) {
+        uint32_t m = newline_mask32(d + pos);
+        while (m) {
+            newline_at(pos + (size_t)__builtin_ctz(m));
+            m &= m - 1;
+        }
+    }
+    for (; pos < b; ++pos)
+        if (d[pos] == '\n') newline_at(pos);
+    out.chars += chars;
+}
 #endif
+
+void parse_fastq_range(const char* d, size_t a, size_t b, Shard& out) {
+#ifdef BGR_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return parse_fastq_range_avx2(d, a, b, out);
+#endif
+    parse_fastq_range_scalar(d, a, b, out);
+}
 
 // newlines in [a, b): the FASTQ reader and the unitig loader cut their input by line numbers, so this pass runs
 // over every byte of such a file; one 32-byte compare + popcount per step instead of a memchr call per line
