@@ -178,3 +178,23 @@ def test_emulated_packed_upload_long_reads_with_n(k, rl):
         got, cnt, _, _ = E.emu_map(unitigs, k, reads, 0, 2, 2, scratch_ints=4096, how=how)
         assert got == ref and cnt == cref
     assert sum(1 for _, _, p in ref if p) > 20
+
+
+@pytest.mark.parametrize("seed", range(7000, 7060))
+def test_emulated_long_k_family_fuzz(seed):
+    """k around the compiled-in k-1 = 30 (31, and its neighbours 30 / 32 which take the run-time form), reads of
+    k-1 .. 300 bases with and without N, every upload / scan form, against the oracle"""
+    rng = random.Random(seed)
+    k = rng.choice([31, 31, 31, 32, 30, 21, 17])
+    unitigs, haps = S.make_graph(rng, k, genome_len=rng.choice([3000, 8000]), mean_unitig=rng.choice([2 * k, 70, 150]),
+                                 n_variants=rng.choice([0, 20, 60]))
+    reads = S.make_reads(rng, haps, rng.choice([50, 200]), rng.choice([k - 1, k, 60, 150, 151, 300]),
+                         sub_rate=rng.choice([0, 0.01, 0.03]), n_rate=rng.choice([0, 0.001, 0.01]))
+    m, e = rng.choice([0, 1, 2, 5]), rng.choice([0, 1, 2, 3])
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        o = O.Oracle(k, m, e)
+        o.index_unitigs(unitigs)
+        want = [o.align(r, mode) for r in reads]
+        for how in (0, 1, 3):
+            got, _, _, ovf = E.emu_map(unitigs, k, reads, mode, m, e, scratch_ints=4096, how=how)
+            assert not ovf and got == want, (k, mode, how)
