@@ -117,3 +117,25 @@ def test_packed_and_character_uploads_agree_on_the_same_slot(bg):
         b = al.align_batch(reads, O.GREEDY).as_tuples()
         assert a == b
     al.close()
+
+
+@pytest.mark.parametrize("seed", range(7100, 7112))
+def test_long_k_family_fuzz_both_upload_forms(bg, seed):
+    """k around the compiled-in k-1 = 30 and its neighbours (run-time form of the scan), reads of k-1 .. 300 bases
+    with and without N: character and packed upload against the oracle"""
+    rng = random.Random(seed)
+    k = rng.choice([31, 31, 32, 30, 21, 17])
+    unitigs, haps = S.make_graph(rng, k, genome_len=rng.choice([3000, 8000]), mean_unitig=rng.choice([2 * k, 70, 150]),
+                                 n_variants=rng.choice([0, 20, 60]))
+    reads = S.make_reads(rng, haps, rng.choice([300, 1500]), rng.choice([k - 1, k, 60, 150, 151, 300]),
+                         sub_rate=rng.choice([0, 0.01, 0.03]), n_rate=rng.choice([0, 0.001, 0.01]))
+    m, e = rng.choice([0, 1, 2, 5]), rng.choice([0, 1, 2, 3])
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        o = O.Oracle(k, m, e)
+        o.index_unitigs(unitigs)
+        want = [o.align(r, mode) for r in reads]
+        al = bg.Aligner(k, m, e)
+        al.index_unitigs(unitigs)
+        assert al.align_batch(reads, mode).as_tuples() == want, (k, mode, "characters")
+        assert al.align_batch_packed(reads, mode, threads=3).as_tuples() == want, (k, mode, "packed")
+        al.close()
