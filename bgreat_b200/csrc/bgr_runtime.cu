@@ -538,6 +538,8 @@ int bgr_index_query(const bgr_ctx* cctx, uint64_t kmer_code, int want_end, int32
 namespace {
 // per-read and per-word device buffers every upload form needs; the offsets go up with it
 int upload_common(bgr_ctx* ctx, Slot& s, const uint64_t* off, uint32_t n) {
+    // the kernels index reads, tiles and list entries with 32-bit numbers
+    if (n > (1u << 30)) return fail(ctx, BGR_ERR_LIMIT, "more than 2^30 reads in one batch: split it");
     const u64 chars = off[n];
     const u64 words = batch_words(chars, n);
     int rc;

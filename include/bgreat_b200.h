@@ -139,6 +139,8 @@ int bgr_index_query(const bgr_ctx* ctx, uint64_t kmer_code, int want_end, int32_
  * reference. The batch replaces n calls of Aligner::alignRead* (mode) plus the counter updates
  * of alignPartGreedy / alignPartExhaustive (alignerGreedy.cpp:382, alignerExhaustive.cpp:48-56).
  *
+ * A batch holds at most 2^30 reads (BGR_ERR_LIMIT beyond).
+ *
  * bgr_map_batch = upload + run + download + wait on slot 0, for callers that do not pipeline.
  * results: n records. path_pool: caller buffer of pool_cap ints; *pool_used receives the ints
  * written. If the paths do not fit, BGR_ERR_LIMIT is returned and *pool_used holds the size needed. */
