@@ -20,7 +20,7 @@ BGREAT = os.path.join(ROOT, "bgreat_b200", "bin", "bgreat")
 
 @pytest.fixture(scope="module")
 def workload():
-    g = synth.Graph(5_000_000, 31, seed=1)
+    g = synth.Graph(5_000_000, 31, seed=1, repeat_frac=0.005)
     n = 200_000
     seqs, off = g.make_reads(n, 150, 0.01)
     return g, seqs, off, n

@@ -18,18 +18,17 @@ def lib():
         if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
             subprocess.check_call(["make", "-s", "-C", HERE])
         L = C.CDLL(LIB)
-        L.bgs_make_graph.restype = C.c_void_p
-        L.bgs_make_graph.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_double]
+        L.bgs_make_graph2.restype = C.c_void_p
+        L.bgs_make_graph2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int]
         L.bgs_free_graph.argtypes = [C.c_void_p]
-        for f in ("bgs_n_unitigs", "bgs_n_snps", "bgs_unitig_bases", "bgs_genome_len"):
+        for f in ("bgs_n_unitigs", "bgs_n_snps", "bgs_n_repeat_copies", "bgs_unitig_bases", "bgs_genome_len"):
             getattr(L, f).restype = C.c_uint64
             getattr(L, f).argtypes = [C.c_void_p]
         L.bgs_unitig_seqs.restype = C.c_void_p
         L.bgs_unitig_seqs.argtypes = [C.c_void_p]
         L.bgs_unitig_off.restype = C.c_void_p
         L.bgs_unitig_off.argtypes = [C.c_void_p]
-        L.bgs_haplotype.restype = C.c_void_p
-        L.bgs_haplotype.argtypes = [C.c_void_p, C.c_int]
+        L.bgs_fill.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
         L.bgs_write_unitigs.argtypes = [C.c_void_p, C.c_char_p]
         L.bgs_make_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_double,
                                      C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
@@ -39,14 +38,18 @@ def lib():
 
 
 class Graph:
-    """Simulated diploid genome and its k-mer unitigs."""
+    """Simulated diploid genome and its k-mer unitigs. repeat_frac: fraction of the genome covered by repeat
+    families (2..6 identical copies: borders with more than two candidates). unitigs=False builds only what
+    make_reads needs (a rank that does not build the index): nothing of genome size is stored."""
 
-    def __init__(self, genome_len, k=31, seed=1, snp_rate=1.0 / 150):
+    def __init__(self, genome_len, k=31, seed=1, snp_rate=1.0 / 150, repeat_frac=0.0, unitigs=True, threads=0):
         self.L = lib()
         self.k = k
-        self.h = self.L.bgs_make_graph(genome_len, k, seed, snp_rate)
+        threads = threads or min(32, os.cpu_count() or 1)
+        self.h = self.L.bgs_make_graph2(genome_len, k, seed, snp_rate, repeat_frac, int(unitigs), threads)
         self.n_unitigs = self.L.bgs_n_unitigs(self.h)
         self.n_snps = self.L.bgs_n_snps(self.h)
+        self.n_repeat_copies = self.L.bgs_n_repeat_copies(self.h)
         self.unitig_bases = self.L.bgs_unitig_bases(self.h)
         self.genome_len = self.L.bgs_genome_len(self.h)
 
@@ -68,8 +71,13 @@ class Graph:
         b = seqs.tobytes()
         return [b[int(off[i]):int(off[i + 1])].decode() for i in range(self.n_unitigs)]
 
-    def haplotype(self, h):
-        return C.string_at(self.L.bgs_haplotype(self.h, h), self.genome_len).decode()
+    def haplotype(self, h, pos=0, length=None):
+        """bases [pos, pos+length) of haplotype h (regenerated: the genome is not stored)"""
+        length = self.genome_len - pos if length is None else length
+        buf = C.create_string_buffer(length)
+        if self.L.bgs_fill(self.h, h, pos, length, buf) != 0:
+            raise ValueError("range outside the genome")
+        return buf.raw.decode()
 
     def write_unitigs(self, path):
         if self.L.bgs_write_unitigs(self.h, os.fsencode(path)) != 0:
