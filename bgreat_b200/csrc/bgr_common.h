@@ -7,9 +7,13 @@
 //   keys    : u64[n_buckets * 4]      bucketed open addressing, one bucket = 4 keys = one 32-byte
 //                                     DRAM sector; EMPTY_KEY marks a free slot; a key lives in the
 //                                     first bucket at or after hash(key) that had room
-//   payload : Payload[n_buckets * 4]  per key slot: left[4] + right[4] unitig slots (32 bytes),
-//                                     the reference's two unitigIndices tables merged
-//                                     (reference aligner.h:49-55, aligner.cpp:463-533)
+//   entries : Entry[n_buckets * 4]    per key slot, one 128-byte line: left[4] + right[4] unitig slots, the
+//                                     reference's two unitigIndices tables merged (reference aligner.h:49-55,
+//                                     aligner.cpp:463-533). A slot is 16 bytes and carries everything a walk
+//                                     needs to go on without another dependent load: where the unitig lies in
+//                                     `pool` and how long it is, its id and orientation flags, and the key slot
+//                                     of the (k-1)-mer at its FAR end (the next level's entry). One side of an
+//                                     entry = 64 bytes = two sectors = one request.
 //   bloom   : u32[n_bloom]            negative filter in front of `keys` for the seed scan: a blocked Bloom
 //                                     filter whose block is ONE 32-bit word; every key sets 3 bits of its
 //                                     word. "Some bit clear" proves absence; a window that passes is
@@ -51,9 +55,27 @@ static const u32 SLOT_ID_MASK = 0x3FFFFFFFu;  // unitig ids < 2^30
 static const u32 SLOT_FWD_CANON = 1u << 30;
 static const u32 SLOT_FWD_RC = 1u << 31;
 
-struct Payload {
-    u32 left[4];
-    u32 right[4];
+// One candidate of a border: 16 bytes.
+//   start_len : first base of the (forward) unitig in `pool`, bits 0..35; its length in bases, bits 36..63
+//   id_flags  : unitig id (1-based, < 2^30) | SLOT_FWD_CANON | SLOT_FWD_RC; 0 = empty slot
+//   next      : key slot of the canonical (k-1)-mer at the unitig's other end, bits 0..29 -- the entry the
+//               walk queries after stepping through this unitig, whichever way it was entered (entered through
+//               the canonical key the next code is some c, entered through its reverse complement it is rc(c):
+//               both have the same canonical key). SLOT_NEXT_CANON: c <= rc(c); SLOT_NEXT_PAL: c == rc(c).
+struct USlot {
+    u64 start_len;
+    u32 id_flags;
+    u32 next;
+};
+static const u32 SLOT_START_BITS = 36, SLOT_LEN_BITS = 28;
+static const u64 SLOT_START_MASK = (1ull << SLOT_START_BITS) - 1;
+static const u32 SLOT_NEXT_MASK = 0x3FFFFFFFu;
+static const u32 SLOT_NEXT_CANON = 1u << 30;
+static const u32 SLOT_NEXT_PAL = 1u << 31;
+
+struct Entry {
+    USlot left[4];
+    USlot right[4];
 };
 
 struct UnitigMeta {
@@ -70,7 +92,7 @@ struct BlobHeader {
     u64 n_keys;
     u64 n_buckets;
     u64 pool_words;
-    u64 off_keys, off_payload, off_meta, off_pool;  // byte offsets from the blob start
+    u64 off_keys, off_entries, off_meta, off_pool;  // byte offsets from the blob start
     u64 total_bytes;
     u64 n_bloom;  // words of the Bloom filter
     u64 off_bloom;
@@ -78,6 +100,7 @@ struct BlobHeader {
     u32 pad;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
+static const u32 BLOB_VERSION = 5;
 
 // 2-bit code of a base character, A0 C1 G2 T3 (utils.cpp:117-129). Returns 4 for anything else.
 BGR_HD u32 base_code(unsigned char c) {
@@ -110,6 +133,27 @@ BGR_HD u64 rev2(u64 x) { return rc64(~x); }
 
 // rcb(x, n) of the reference (utils.cpp:182-192): reverse complement of an n-base code
 BGR_HD u64 rcb(u64 x, u32 n) { return rc64(x) >> (64 - 2 * n); }
+
+// n (1..32) bases of the 2-bit stream W starting at base p, right aligned (str2num's value). W[p/32 + 1] must
+// be readable.
+BGR_HD u64 bases_at(const u64* W, u64 p, u32 n) {
+    const u64 w = p >> 5;
+    const u32 s = (u32)(p & 31) * 2;
+    const u64 x = (W[w] << s) | ((W[w + 1] >> 1) >> (63 - s));
+    return x >> (64 - 2 * n);
+}
+
+// The code a walk continues with after stepping through the unitig of a slot that it entered through the
+// CANONICAL key (entered through the key's reverse complement it is the reverse complement of this):
+//   left table  = getBegin(key): the unitig oriented to begin with key -> its last k-1 bases
+//   right table = getEnd(key):   the unitig oriented to end with key   -> its first k-1 bases
+// (aligner.cpp:147-267 orient by the forward test only; alignerGreedy.cpp:200,246 take the other end).
+BGR_HD u64 slot_far_code(const u64* pool, u64 start, u64 len, u32 km1, u32 id_flags, bool right_table) {
+    const bool rc = (id_flags & SLOT_FWD_CANON) == 0;
+    const u64 ubeg = bases_at(pool, start, km1), uend = bases_at(pool, start + len - km1, km1);
+    if (!right_table) return rc ? rcb(ubeg, km1) : uend;
+    return rc ? rcb(uend, km1) : ubeg;
+}
 
 // hash of a canonical (k-1)-mer -> bucket. Kept to 32-bit integer ops on purpose: the seed-scan
 // kernel is instruction-issue bound (profiles/r01_ncu_k_pack_scan_v1.txt) and computes one per window.

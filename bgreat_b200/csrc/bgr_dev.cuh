@@ -21,7 +21,7 @@ namespace bgr {
 
 struct DevIndex {
     const u64* keys;
-    const Payload* payload;
+    const Entry* entries;
     const UnitigMeta* meta;
     const u64* pool;
     u64 n_buckets;

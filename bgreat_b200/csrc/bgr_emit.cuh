@@ -123,11 +123,35 @@ __device__ __forceinline__ void count_classes(const BatchArgs& a, u32 n_al, u32 
 
 static const int EXT_THREADS = 128;
 
-// Persistent warps: every lane walks one read with GreedyState::step; lanes that finish hand in their
-// result and take the next read of the hit list (a warp draws 32 list entries per atomic), so the
-// warp stays full until the list runs dry.
+// ---- greedy extension: lane per read for the walk's state, the whole warp for its comparisons.
+//
+// Every lane owns one read and runs GreedyState's stages (bgr_extend.cuh). What differs from lane to lane is how
+// much comparing a level needs -- 1..4 candidates of 1..5 (or, for long reads, hundreds of) 32-base chunks -- and
+// run lane by lane that left 9 of 32 threads active per instruction (profiles/r01_ncu_k_extend_greedy_v11_5Mbp.txt).
+// So a turn of the warp is:
+//   1. every walking lane reads its level's entry side (64 bytes) and lays out <= 4 comparison jobs in shared
+//      memory, at job slots 4*lane .. 4*lane+3, with an exclusive prefix sum of their chunk counts;
+//   2. the chunks of ALL jobs are dealt round-robin to the 32 lanes: chunk j finds its job by binary search in the
+//      prefix sums, loads two pool words and two read words, XOR + popc, and adds to the job's counter;
+//   3. every walking lane reads its counters and settles the level (GreedyState::level_settle).
+// The loads of step 2 are all independent and issued together: a level is two dependent round trips.
+struct ExtJob {   // 32 bytes
+    u64 ua;       // first unitig base, forward pool coordinates
+    u64 wofs;     // the read's first data word in BatchArgs::F / NM
+    i32 sa, n;    // first read base (stored coordinates), bases
+    u32 flags;    // bit0 flip, bit1 read has N, bit2 pass
+    u32 pad;
+};
+struct ExtWarpShared {
+    ExtJob job[128];
+    u32 start[128];  // first chunk of job q among the warp's chunks of this turn
+    u32 miss[128];
+};
+
 template <int MINB>
 __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix, BatchArgs a) {
+    __shared__ __align__(16) ExtWarpShared wsh_all[EXT_THREADS / 32];
+    ExtWarpShared& W = wsh_all[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31;
     const u32 list_n = a.scnt->list_n;
     GreedyState g;
@@ -139,13 +163,11 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
     bool dry = false;                    // the list has no more chunks
     u32 n_al = 0, n_na = 0, n_no = 0;
     bool any_overflow = false;
-    // Hand-in, refill and seed selection are needed once or twice per read while a walk has several
-    // levels: run per lane as soon as it is due, every turn pays for them with a handful of lanes
-    // active (profiles/r01_ncu_k_extend_greedy_v5_5Mbp.txt: 8 of 32 threads per instruction). They are
-    // therefore serviced together, once `lazy` lanes wait for them (or nobody can walk).
+    // Hand-in, refill and seed selection are needed once or twice per read while a walk has several levels:
+    // they are serviced together, once `lazy` lanes wait for them (or nobody can walk).
     const u32 lazy = a.ext_lazy ? a.ext_lazy : 1;
     for (;;) {
-        const bool walking = have && g.phase != GP_DONE && g.phase != GP_SEED;
+        const bool walking = have && g.walking();
         const u32 waiting = __ballot_sync(0xFFFFFFFFu, !walking);
         if ((u32)__popc(waiting) >= lazy || waiting == 0xFFFFFFFFu) {
             if (have && g.done()) {  // hand in
@@ -186,7 +208,76 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
             }
             if (have && g.phase == GP_SEED) g.pick_seed(ix, a);
         }
-        if (have && g.phase != GP_DONE && g.phase != GP_SEED) g.step_level(ix, a);
+        // ---- 1. entry side -> comparison jobs
+        const bool q = have && g.walking() && g.level_begin(ix, a);
+        USlot sl[4];
+        int nc = 0;
+        GreedyLevel lv;
+        lv.n = 0;
+        lv.ends = 0;
+        if (q) {
+            if (const USlot* side = g.level_side(ix)) {
+                load_side(side, sl);
+                nc = count_slots(sl);
+            }
+            g.level_jobs(ix, sl, nc, lv);
+        }
+        u32 cnt[4], mine = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            cnt[c] = (q && c < nc) ? (u32)(lv.job[c].n + 31) >> 5 : 0u;
+            mine += cnt[c];
+        }
+        u32 incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (u32)d) incl += x;
+        }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        {
+            u32 at = incl - mine;
+            const u32 jf = (g.s.v.hasN ? 2u : 0u) | (g.s.v.pass ? 4u : 0u);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const u32 qi = 4 * lane + c;
+                W.start[qi] = at;
+                W.miss[qi] = 0;
+                if (cnt[c]) {
+                    ExtJob j;
+                    j.ua = lv.job[c].ua;
+                    j.wofs = g.s.wb + 1;
+                    j.sa = lv.job[c].sa;
+                    j.n = lv.job[c].n;
+                    j.flags = (lv.job[c].flip ? 1u : 0u) | jf;
+                    j.pad = 0;
+                    W.job[qi] = j;
+                }
+                at += cnt[c];
+            }
+        }
+        __syncwarp();
+        // ---- 2. all chunks of all jobs, dealt to the 32 lanes
+        for (u32 j = lane; j < total; j += 32) {
+            u32 qi = 0;
+#pragma unroll
+            for (u32 sft = 64; sft; sft >>= 1)
+                if (W.start[qi + sft] <= j) qi += sft;
+            const ExtJob job = W.job[qi];
+            const i32 done = (i32)(j - W.start[qi]) * 32;
+            const u32 m = job_chunk_miss(ix.pool, a.F + job.wofs, a.NM + job.wofs, (job.flags & 2u) != 0, (job.flags & 4u) != 0,
+                                         job.ua, job.sa, job.n, (job.flags & 1u) != 0, done);
+            if (m) atomicAdd(&W.miss[qi], m);
+        }
+        __syncwarp();
+        // ---- 3. settle
+        if (q) {
+            u32 miss[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) miss[c] = W.miss[4 * lane + c];
+            g.level_settle(a, sl, lv, miss);
+        }
+        __syncwarp();
     }
     if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
     count_classes(a, n_al, n_na, n_no);

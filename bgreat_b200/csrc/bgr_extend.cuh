@@ -29,77 +29,86 @@ struct Oriented {
     bool rc;
 };
 
+// The candidates of one border: the <= 4 slots of one side of a key's entry (bgr_common.h), scanned in order up
+// to the first empty one (aligner.cpp:172-203).
 struct Cands {
-    u32 raw[4];
+    USlot s[4];
     int n;
     u32 fwd_bit;
+    bool canon;  // the query's code was the canonical form of its key
 };
 
-// getBegin / getEnd (aligner.cpp:147-267). The key's bucket and the payloads of that bucket's four slots
-// (one 128-byte line) are requested together: a key sits in its home bucket nearly always, and the walk
-// is a chain of dependent round trips, so the extra sectors are cheaper than a second trip.
-BGR_HD Cands index_query(const DevIndex& ix, u64 bin, bool want_end) {
-    Cands c;
-    c.n = 0;
-    c.fwd_bit = 0;
-    u64 rc = rcb(bin, ix.k - 1);
-    bool canon = bin <= rc;
-    const u64 key = canon ? bin : rc;
-    // getEnd: canonical -> right table, else left; getBegin: canonical -> left, else right
-    bool right = (want_end == canon);
-    const u64 b0 = bucket_of(key, ix.n_buckets);
-    const u64x4 v = ld_bucket(ix.keys + b0 * 4);
-    const u32* line = right ? ix.payload[b0 * 4].right : ix.payload[b0 * 4].left;
-    i64 slot;
+static const u32 NO_SLOT = 0xFFFFFFFFu;
+
+// one side of an entry: 64 bytes, two sectors of one line, one request
+BGR_HD void load_side(const USlot* side, USlot out[4]) {
 #if defined(__CUDA_ARCH__)
-    const uint4 p0 = __ldg((const uint4*)line), p1 = __ldg((const uint4*)(line + 8)), p2 = __ldg((const uint4*)(line + 16)),
-                p3 = __ldg((const uint4*)(line + 24));
-    uint4 p;
-    if (v.a == key) p = p0, slot = 0;
-    else if (v.b == key) p = p1, slot = 1;
-    else if (v.c == key) p = p2, slot = 2;
-    else if (v.d == key) p = p3, slot = 3;
-    else if (v.d == EMPTY_KEY) return c;
-    else {
-        slot = index_find(ix, key);  // overflowed into a later bucket
-        if (slot < 0) return c;
-        const u32* q = right ? ix.payload[slot].right : ix.payload[slot].left;
-        p = __ldg((const uint4*)q);
-    }
-    c.raw[0] = p.x;
-    c.raw[1] = p.y;
-    c.raw[2] = p.z;
-    c.raw[3] = p.w;
+    const u64x4 a = ld_bucket((const u64*)side), b = ld_bucket((const u64*)side + 4);
+    out[0].start_len = a.a;
+    out[0].id_flags = (u32)a.b;
+    out[0].next = (u32)(a.b >> 32);
+    out[1].start_len = a.c;
+    out[1].id_flags = (u32)a.d;
+    out[1].next = (u32)(a.d >> 32);
+    out[2].start_len = b.a;
+    out[2].id_flags = (u32)b.b;
+    out[2].next = (u32)(b.b >> 32);
+    out[3].start_len = b.c;
+    out[3].id_flags = (u32)b.d;
+    out[3].next = (u32)(b.d >> 32);
 #else
-    (void)v;
-    (void)line;
-    slot = index_find(ix, key);
-    if (slot < 0) return c;
-    const u32* q = right ? ix.payload[slot].right : ix.payload[slot].left;
-    for (int j = 0; j < 4; ++j) c.raw[j] = q[j];
+    for (int j = 0; j < 4; ++j) out[j] = side[j];
 #endif
-    c.fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
-    // slots are scanned in order up to the first empty one (aligner.cpp:172-203)
-    const bool s0 = (c.raw[0] & SLOT_ID_MASK) != 0, s1 = s0 && (c.raw[1] & SLOT_ID_MASK) != 0,
-               s2 = s1 && (c.raw[2] & SLOT_ID_MASK) != 0, s3 = s2 && (c.raw[3] & SLOT_ID_MASK) != 0;
-    c.n = (int)s0 + (int)s1 + (int)s2 + (int)s3;
-    return c;
 }
 
-BGR_HD Oriented orient(const DevIndex& ix, const Cands& c, int i) {
+BGR_HD int count_slots(const USlot s[4]) {
+    const bool s0 = (s[0].id_flags & SLOT_ID_MASK) != 0, s1 = s0 && (s[1].id_flags & SLOT_ID_MASK) != 0,
+               s2 = s1 && (s[2].id_flags & SLOT_ID_MASK) != 0, s3 = s2 && (s[3].id_flags & SLOT_ID_MASK) != 0;
+    return (int)s0 + (int)s1 + (int)s2 + (int)s3;
+}
+
+// getBegin / getEnd for the key in key slot `slot`, queried through its canonical form (canon) or through the
+// reverse complement of that: getEnd takes the right table for a canonical code, else the left one; getBegin the
+// other way round (aligner.cpp:147-267).
+BGR_HD const USlot* entry_side(const DevIndex& ix, u32 slot, bool canon, bool want_end) {
+    const bool right = (want_end == canon);
+    return right ? ix.entries[slot].right : ix.entries[slot].left;
+}
+BGR_HD Cands index_query_at(const DevIndex& ix, u32 slot, bool canon, bool want_end) {
+    Cands c;
+    c.n = 0;
+    c.canon = canon;
+    c.fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+    if (slot == NO_SLOT) return c;
+    load_side(entry_side(ix, slot, canon, want_end), c.s);
+    c.n = count_slots(c.s);
+    return c;
+}
+// the same for a (k-1)-mer code: canonical form -> key table -> entry
+BGR_HD Cands index_query(const DevIndex& ix, u64 bin, bool want_end) {
+    const u64 rc = rcb(bin, ix.k - 1);
+    const bool canon = bin <= rc;
+    const i64 slot = index_find(ix, canon ? bin : rc);
+    return index_query_at(ix, slot < 0 ? NO_SLOT : (u32)slot, canon, want_end);
+}
+
+BGR_HD Oriented orient_slot(const USlot& s, u32 fwd_bit) {
     Oriented u;
-    u32 id = c.raw[i] & SLOT_ID_MASK;
-#if defined(__CUDA_ARCH__)
-    const ulonglong2 m = __ldg((const ulonglong2*)&ix.meta[id]);
-    u.start = m.x;
-    u.len = (i64)(u32)m.y;
-#else
-    u.start = ix.meta[id].start;
-    u.len = ix.meta[id].len;
-#endif
-    u.rc = (c.raw[i] & c.fwd_bit) == 0;
+    const u32 id = s.id_flags & SLOT_ID_MASK;
+    u.start = s.start_len & SLOT_START_MASK;
+    u.len = (i64)(s.start_len >> SLOT_START_BITS);
+    u.rc = (s.id_flags & fwd_bit) == 0;
     u.sid = u.rc ? -(i32)id : (i32)id;
     return u;
+}
+BGR_HD Oriented orient(const DevIndex&, const Cands& c, int i) { return orient_slot(c.s[i], c.fwd_bit); }
+
+// where a walk goes on after stepping through slot s, which it reached by a query of form `canon`: the key
+// slot of the unitig's other end, and the form of the next query (bgr_common.h, USlot::next)
+BGR_HD void next_query(const USlot& s, bool canon, u32& slot, bool& next_canon) {
+    slot = s.next & SLOT_NEXT_MASK;
+    const bool c1 = (s.next & SLOT_NEXT_CANON) != 0, pal = (s.next & SLOT_NEXT_PAL) != 0;
+    next_canon = canon ? c1 : (!c1 || pal);
 }
 
 // str2num of the first / last k-1 bases of the oriented unitig
@@ -175,6 +184,47 @@ BGR_HD u32 mismatches(const DevIndex& ix, const ReadView& v, const Oriented& u, 
 // the greedy walk's call site: N-free reads take a loop without any mask handling
 BGR_HD u32 mismatches_split(const DevIndex& ix, const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n, u32 cap) {
     return v.hasN ? mismatches_t<1>(ix, v, u, upos, rpos, n, cap) : mismatches_t<0>(ix, v, u, upos, rpos, n, cap);
+}
+
+// One missmatchNumber call laid out for chunk-wise evaluation: n bases of the oriented unitig from upos against
+// n bases of the pass's read from rpos, in forward pool coordinates and stored read coordinates. The greedy
+// kernel spreads the 32-base chunks of all the comparisons a warp has pending over its lanes (k_extend_greedy);
+// the sum of the chunk counts, capped at cap+1, is what mismatches() returns.
+struct CmpJob {
+    u64 ua;     // first unitig base, forward pool coordinates
+    i32 sa;     // first read base, stored coordinates
+    i32 n;      // bases
+    bool flip;  // the read segment is reverse-complemented before comparing
+};
+BGR_HD CmpJob make_job(const ReadView& v, const Oriented& u, i64 upos, i32 rpos, i32 n) {
+    CmpJob j;
+    j.ua = (u64)((i64)u.start + (u.rc ? u.len - upos - n : upos));
+    j.sa = v.pass ? v.len - rpos - n : rpos;
+    j.n = n;
+    j.flip = u.rc != v.pass;
+    return j;
+}
+// mismatches among bases [done, done+32) of the job (fewer at its end)
+BGR_HD u32 job_chunk_miss(const u64* pool, const u64* D, const u64* ND, bool hasN, bool pass, u64 ua, i32 sa, i32 n,
+                          bool flip, i32 done) {
+    const i32 left = n - done;
+    const i32 m = left < 32 ? left : 32;
+    const i32 rp = flip ? sa + n - done - m : sa + done;
+    const u64 xu = ld_bases(pool, (i64)ua + done);
+    u64 y = ld_bases(D, rp), nm = 0;
+    if (hasN) {
+        const u64 ymask = ld_bases(ND, rp);
+        if (pass) y |= ymask;  // pass 1 sequence is F0|NM, without a mask
+        else nm = ymask;       // pass 0 carries the N mask
+    }
+    if (flip) {
+        y = rc64(y) << ((64 - 2 * m) & 63);
+        nm = rev2(nm) << ((64 - 2 * m) & 63);
+    }
+    u64 d = xu ^ y;
+    d = (d | (d >> 1) | nm) & 0x5555555555555555ull;
+    if (m < 32) d &= ~(~0ull >> (2 * m));
+    return (u32)BGR_POPCLL(d);
 }
 
 // forward code of window i of the pass's read, as the seed scans store it
@@ -420,25 +470,40 @@ BGR_HD ReadSetup setup_read(const DevIndex& ix, const BatchArgs& a, u32 r) {
 // alignReadGreedy (alignerGreedy.cpp:35-57) for read r. The path is left in scratch as
 // [0, nl) = pathBegin in push order (to be reversed) followed by [nl, n) = pathEnd.
 //
-// Written as ONE loop whose body is "settle the current level / pick the next seed / query the index"
-// followed by "compare one candidate unitig": threads of a warp work on different reads and are at
-// different points of their walks, but they all execute this same body, so the warp stays converged
-// (the first version, a call tree of walkers, ran with 1.65 of 32 lanes active:
-// profiles/r01_ncu_k_extend_greedy_v1.txt). The walkers greedy_left / greedy_right above are the
-// readable statement of the same procedure and are kept for the emulator's cross-check.
+// A resumable state machine whose turn is one LEVEL of a walk, cut into three stages so that the kernel can run
+// the middle one cooperatively:
+//   level_begin : ends of walks that need no index query; says which entry side the level reads
+//   level_jobs  : the <= 4 candidates of that side -> one comparison job each (geometry only, no memory access
+//                 beyond the 64 bytes of the side: a slot carries its unitig's position and length)
+//   level_settle: given the mismatch counts, the reference's choice -- a zero-miss candidate is taken at once,
+//                 otherwise the first strictly smallest within the budget (quirk 9) -- and the next level's key
+//                 slot straight from the chosen slot (USlot::next): no hashing, no load of the overlap code
+// A level therefore costs two dependent round trips (entry side, then the words of all its comparisons at once)
+// where the first form of this walk took four (bucket + payload, unitig meta, words, next overlap code).
+// The walkers greedy_left / greedy_right above are the readable statement of the same procedure (they go through
+// the key table at every level, which also cross-checks the next-slot links) and are kept for the emulator.
 enum { GP_SEED = 0, GP_LEFT = 1, GP_RIGHT_FIRST = 2, GP_RIGHT_MORE = 3, GP_DONE = 4 };
+
+struct GreedyLevel {
+    CmpJob job[4];
+    i32 L[4];         // bases of the candidate beyond the overlap
+    u32 ends;         // bit i: candidate i covers the rest of the read
+    int n;
+};
 
 struct GreedyState {
     ReadSetup s;
     Scratch sc;
     SeedIter it;
     u32 flags, n, nl, tried, phase;
-    // walk state
-    u64 code, seed_c;
+    // walk state: the key slot and query form of the current level, and of the seed
+    u32 slot, seed_slot;
+    bool canon, seed_canon;
     i32 pos, seed_pos;
     u32 budget, acc, eb;
 
     BGR_HD bool done() const { return phase == GP_DONE; }
+    BGR_HD bool walking() const { return phase == GP_LEFT || phase == GP_RIGHT_FIRST || phase == GP_RIGHT_MORE; }
 
     BGR_HD void start(const DevIndex& ix, const BatchArgs& a, u32 r, i32* scratch_row) {
         s = setup_read(ix, a, r);
@@ -452,7 +517,8 @@ struct GreedyState {
         phase = GP_SEED;
         // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
         it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, a.effort ? s.nwin : 1);
-        code = seed_c = 0;
+        slot = seed_slot = NO_SLOT;
+        canon = seed_canon = false;
         pos = seed_pos = 0;
         budget = acc = eb = 0;
     }
@@ -466,12 +532,14 @@ struct GreedyState {
         phase = GP_RIGHT_FIRST;
         budget = a.errors - eb;
         acc = 0;
-        code = seed_c;
+        slot = seed_slot;
+        canon = seed_canon;
         pos = seed_pos;
     }
 
     // Seed selection, possibly switching to the reverse-complement pass: needed once per seed, i.e. rarely
     // compared with the levels of a walk, so the kernel runs it for several lanes at once (see k_extend_greedy).
+    // The seed's (k-1)-mer is looked up in the key table here; every later level follows the slots' links.
     BGR_HD void pick_seed(const DevIndex& ix, const BatchArgs& a) {
         ReadView& v = s.v;
         const u32 max_seeds = a.effort ? a.effort : 1;
@@ -479,7 +547,13 @@ struct GreedyState {
             i32 p = tried < max_seeds ? it.next() : -1;
             if (p >= 0) {
                 ++tried;
-                seed_c = code = seed_code(ix, v, p);
+                const u64 code = seed_code(ix, v, p);
+                const u64 rc = rcb(code, ix.k - 1);
+                seed_canon = canon = code <= rc;
+                // (a read with N can name a window whose code, canonicalised the way getBegin / getEnd do it, is
+                // no key: the walk then finds no candidate, like the reference's)
+                const i64 sl = index_find(ix, canon ? code : rc);
+                seed_slot = slot = sl < 0 ? NO_SLOT : (u32)sl;
                 seed_pos = pos = p;
                 budget = a.errors;
                 acc = 0;
@@ -502,37 +576,37 @@ struct GreedyState {
         }
     }
 
-    // One turn of the loop = one level of a walk: query the index -> compare the <= 4 candidates ->
-    // settle. Every lane of a warp that holds a seed runs these same stages every turn.
-    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
-        if (phase == GP_SEED) pick_seed(ix, a);
-        if (phase != GP_SEED && phase != GP_DONE) step_level(ix, a);
-    }
-
-    BGR_HD void step_level(const DevIndex& ix, const BatchArgs& a) {
-        ReadView& v = s.v;
-        const i64 km1 = ix.k - 1;
-        // ---- ends of walks that need no index query
+    // ---- stage 1: ends of walks that need no index query. Returns true when the level goes on to a query.
+    BGR_HD bool level_begin(const DevIndex& ix, const BatchArgs& a) {
+        const i32 km1 = (i32)ix.k - 1;
         if (phase == GP_LEFT && pos == 0) {  // checkBeginGreedy:269 / mapOnLeftEndGreedy:168
             sc.set(n++, 0);
             eb = acc;
             go_right(a);
         }
-        if (phase == GP_RIGHT_FIRST && v.len - (pos + (i32)km1) == 0) succeed();  // checkEndGreedy:324
-        if (phase == GP_RIGHT_MORE && v.len - pos < (i32)ix.k) succeed();         // mapOnRightEndGreedy:223
-        if (phase == GP_DONE) return;
-        // ---- candidates of this level: getEnd on the way left, getBegin on the way right
-        const Cands c = index_query(ix, code, phase == GP_LEFT);
-        u32 best = budget + 1;
-        i32 best_sid = 0, offset = 0;
-        i64 next_L = 0;
-        u64 next_code = 0;
-        bool ended = false, accepted = false;
+        if (phase == GP_RIGHT_FIRST && s.v.len - (pos + km1) == 0) succeed();  // checkEndGreedy:324
+        if (phase == GP_RIGHT_MORE && s.v.len - pos < (i32)ix.k) succeed();    // mapOnRightEndGreedy:223
+        return phase != GP_DONE;
+    }
+    // the 64 bytes this level reads: getEnd on the way left, getBegin on the way right (null: no such key)
+    BGR_HD const USlot* level_side(const DevIndex& ix) const {
+        return slot == NO_SLOT ? nullptr : entry_side(ix, slot, canon, phase == GP_LEFT);
+    }
+
+    // ---- stage 2: comparison geometry of the level's candidates
+    BGR_HD void level_jobs(const DevIndex& ix, const USlot sl[4], int nc, GreedyLevel& lv) const {
+        const ReadView& v = s.v;
+        const i32 km1 = (i32)ix.k - 1;
+        const u32 fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+        lv.n = nc;
+        lv.ends = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (i < c.n && !accepted) {
-                const Oriented u = orient(ix, c, i);
-                const i64 L = u.len - km1;
+            lv.job[i].n = 0;
+            lv.L[i] = 0;
+            if (i < nc) {
+                const Oriented u = orient_slot(sl[i], fwd_bit);
+                const i32 L = (i32)(u.len - km1);
                 bool ends_here;
                 i64 upos;
                 i32 rpos, nn;
@@ -540,15 +614,15 @@ struct GreedyState {
                     // unitig covers the rest: unitig[L-pos, L) vs read[0,pos); else unitig[0,L) vs read[pos-L,pos)
                     ends_here = L >= pos;
                     upos = ends_here ? L - pos : 0;
-                    rpos = ends_here ? 0 : pos - (i32)L;
-                    nn = ends_here ? pos : (i32)L;
+                    rpos = ends_here ? 0 : pos - L;
+                    nn = ends_here ? pos : L;
                 } else if (phase == GP_RIGHT_FIRST) {
                     // comparisons start after the anchor overlap
-                    const i32 rstart = pos + (i32)km1, rl = v.len - rstart;
+                    const i32 rstart = pos + km1, rl = v.len - rstart;
                     ends_here = L >= rl;
                     upos = km1;
                     rpos = rstart;
-                    nn = ends_here ? rl : (i32)L;
+                    nn = ends_here ? rl : L;
                 } else {
                     // the remaining read starts AT the overlap; whole unitig compared, cut at the read end
                     const i32 rl = v.len - pos;
@@ -557,31 +631,50 @@ struct GreedyState {
                     rpos = pos;
                     nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
                 }
-                const u32 miss = mismatches_split(ix, v, u, upos, rpos, nn, budget);
-                if (miss < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
-                    best = miss;
-                    best_sid = u.sid;
-                    ended = ends_here;
-                    offset = (i32)(L - pos);
-                    next_L = L;
-                    // (asking for this code together with the comparison's words, for every candidate, was
-                    // measured and lost: 3.91 vs 3.66 ms at 5 Mbp, 6.65 vs 5.35 ms at 1 Gbp -- the extra
-                    // random sectors cost more than the saved round trip)
-                    if (!ends_here) next_code = (phase == GP_LEFT) ? first_code(ix, u) : last_code(ix, u);
-                    accepted = miss == 0;
+                lv.job[i] = make_job(v, u, upos, rpos, nn);
+                lv.L[i] = L;
+                lv.ends |= (ends_here ? 1u : 0u) << i;
+            }
+        }
+    }
+
+    // ---- stage 3: settle the level. miss[i] = mismatches of candidate i (any value above the budget counts as
+    // budget+1, the cap of missmatchNumber)
+    BGR_HD void level_settle(const BatchArgs& a, const USlot sl[4], const GreedyLevel& lv, const u32 miss[4]) {
+        u32 best = budget + 1;
+        int bi = -1;
+        bool accepted = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < lv.n && !accepted) {
+                const u32 m = miss[i] < budget + 1 ? miss[i] : budget + 1;
+                if (m < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
+                    best = m;
+                    bi = i;
+                    accepted = m == 0;
                 }
             }
         }
-        // ---- settle the level
-        if (best > budget) {
+        if (bi < 0) {
             phase = GP_SEED;  // this seed failed
             return;
         }
-        sc.set(n++, best_sid);
+        const u32 fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+        USlot bs = sl[0];
+        i32 bL = lv.L[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i)
+            if (bi == i) {
+                bs = sl[i];
+                bL = lv.L[i];
+            }
+        const Oriented u = orient_slot(bs, fwd_bit);
+        const bool ended = (lv.ends >> bi) & 1u;
+        sc.set(n++, u.sid);
         // an exact candidate leaves the budget untouched, an inexact one pays for its mismatches
         if (ended) {
             if (phase == GP_LEFT) {
-                sc.set(n++, offset);
+                sc.set(n++, bL - pos);
                 eb = acc + best;
                 go_right(a);
             } else {
@@ -590,13 +683,33 @@ struct GreedyState {
         } else {
             acc += best;
             budget -= best;
-            code = next_code;
-            if (phase == GP_LEFT) pos -= (i32)next_L;
+            next_query(bs, canon, slot, canon);
+            if (phase == GP_LEFT) pos -= bL;
             else {
-                pos += (i32)next_L;
+                pos += bL;
                 phase = GP_RIGHT_MORE;
             }
         }
+    }
+
+    // One turn, start to finish, by one thread (emulator; the kernel runs the stages itself).
+    BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {
+        if (phase == GP_SEED) pick_seed(ix, a);
+        if (!walking() || !level_begin(ix, a)) return;
+        USlot sl[4];
+        int nc = 0;
+        if (const USlot* side = level_side(ix)) {
+            load_side(side, sl);
+            nc = count_slots(sl);
+        }
+        GreedyLevel lv;
+        level_jobs(ix, sl, nc, lv);
+        u32 miss[4] = {0, 0, 0, 0};
+        for (int i = 0; i < nc; ++i)
+            for (i32 d = 0; d < lv.job[i].n; d += 32)
+                miss[i] += job_chunk_miss(ix.pool, s.v.D, s.v.ND, s.v.hasN, s.v.pass, lv.job[i].ua, lv.job[i].sa, lv.job[i].n,
+                                          lv.job[i].flip, d);
+        level_settle(a, sl, lv, miss);
     }
 
     // Path in final order in scratch [0, plen): pathBegin is reversed in place (alignerGreedy.cpp:48).

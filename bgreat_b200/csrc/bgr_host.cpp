@@ -172,14 +172,18 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     for (; nu < n; ++nu) {
         u64 len = off[nu + 1] - off[nu];
         if (len < k) break;
-        if (len > 0xFFFFFFFFull) {
-            err = "unitig longer than 2^32-1 bases";
+        if (len >> SLOT_LEN_BITS) {
+            err = "unitig longer than 2^28-1 bases";
             return BGR_ERR_LIMIT;
         }
         total_bases += len;
     }
     if (nu >= SLOT_ID_MASK) {
         err = "more than 2^30-1 unitigs";
+        return BGR_ERR_LIMIT;
+    }
+    if (total_bases >> SLOT_START_BITS) {
+        err = "more than 2^36 unitig bases";
         return BGR_ERR_LIMIT;
     }
     const u64 pool_words = (total_bases + 31) / 32 + 2;  // + lookahead padding
@@ -243,8 +247,8 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     const u64 n_keys = keys.size();
     const u64 n_buckets = std::max<u64>(4, (n_keys + 1) / 2);  // <= 50% load: 2 of 4 slots on average
-    if (n_buckets >= 0xFFFFFFFFull) {
-        err = "too many distinct border k-mers for the 32-bit bucket hash";
+    if (n_buckets * 4 > SLOT_NEXT_MASK) {
+        err = "too many distinct border k-mers for 30-bit key slots";
         return BGR_ERR_LIMIT;
     }
 
@@ -252,7 +256,7 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     BlobHeader h;
     memset(&h, 0, sizeof h);
     h.magic = BLOB_MAGIC;
-    h.version = 4;
+    h.version = BLOB_VERSION;
     h.k = k;
     h.n_unitigs = nu;
     h.n_keys = n_keys;
@@ -260,8 +264,8 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     h.pool_words = pool_words;
     auto align_up = [](u64 x) { return (x + 255) & ~255ull; };
     h.off_keys = align_up(sizeof(BlobHeader));
-    h.off_payload = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
-    h.off_meta = align_up(h.off_payload + n_buckets * 4 * sizeof(Payload));
+    h.off_entries = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
+    h.off_meta = align_up(h.off_entries + n_buckets * 4 * sizeof(Entry));
     h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
     bool two_hashes = false;
     h.n_bloom = bloom_words_for(n_keys, two_hashes);
@@ -282,7 +286,7 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     char* B = (char*)blob.data();
     memcpy(B, &h, sizeof h);
     u64* tkeys = (u64*)(B + h.off_keys);
-    Payload* tpay = (Payload*)(B + h.off_payload);
+    Entry* tent = (Entry*)(B + h.off_entries);
     memcpy(B + h.off_meta, meta.data(), (nu + 1) * sizeof(UnitigMeta));
     memcpy(B + h.off_pool, pool.data(), pool_words * sizeof(u64));
     for (u64 i = 0; i < n_buckets * 4; ++i) tkeys[i] = EMPTY_KEY;
@@ -319,11 +323,18 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     // (aligner.cpp:481-489)
     for (size_t i = 0; i < refs.size(); ++i) {
         u64 slot = find_or_insert(refs[i].key, false);
-        u32* s = (refs[i].side_flg & 1u) ? tpay[slot].right : tpay[slot].left;
-        u32 v = refs[i].id | (refs[i].side_flg & (SLOT_FWD_CANON | SLOT_FWD_RC));
-        if (s[0] == 0) s[0] = v;
-        else if (s[1] == 0) s[1] = v;
-        else if (s[2] == 0) s[2] = v;
+        const bool right = (refs[i].side_flg & 1u) != 0;
+        USlot* s = right ? tent[slot].right : tent[slot].left;
+        USlot v;
+        v.start_len = meta[refs[i].id].start | ((u64)meta[refs[i].id].len << SLOT_START_BITS);
+        v.id_flags = refs[i].id | (refs[i].side_flg & (SLOT_FWD_CANON | SLOT_FWD_RC));
+        // the entry the walk goes on with: the key slot of the (k-1)-mer at the unitig's other end
+        const u64 c = slot_far_code(pool.data(), meta[refs[i].id].start, meta[refs[i].id].len, k - 1, v.id_flags, right);
+        const u64 rc = rcb(c, k - 1);
+        v.next = (u32)find_or_insert(c <= rc ? c : rc, false) | (c <= rc ? SLOT_NEXT_CANON : 0u) | (c == rc ? SLOT_NEXT_PAL : 0u);
+        if (s[0].id_flags == 0) s[0] = v;
+        else if (s[1].id_flags == 0) s[1] = v;
+        else if (s[2].id_flags == 0) s[2] = v;
         else s[3] = v;
     }
     return BGR_OK;

@@ -9,9 +9,10 @@
 //        equal keys keep FILE ORDER, which is what the reference's slot rules depend on
 //     -> k_mark_runs / exclusive sum / k_run_starts : distinct keys and their runs
 //     -> k_insert_keys : bucketed open addressing by atomicCAS, slots of a bucket fill in order; Bloom bits
-//     -> k_fill_payload: per key, left/right slots in file order, the 5th and later arrivals overwrite
-//                        slot 4 (aligner.cpp:481-489)
 //     -> k_pack_pool / k_unitig_meta : 2-bit pool, ACGT validation, per-unitig (start, length)
+//     -> k_fill_entries: per key, left/right slots in file order, the 5th and later arrivals overwrite
+//                        slot 4 (aligner.cpp:481-489); every slot also gets where its unitig lies and the key
+//                        slot of the unitig's other end (the next level of a walk)
 //
 // The blob it leaves in HBM has the layout of bgr_common.h and answers every query exactly like the
 // host-built one (tests/test_gpu_parity.py compares the two); only the slot a key occupies inside its
@@ -122,26 +123,51 @@ __global__ void k_insert_keys(const u64* skeys, const u32* run_start, u32 n_keys
     atomicOr(&bloom[word], pattern);
 }
 
-__global__ void k_fill_payload(const u32* sidx, const u32* flags, const u32* run_start, const u32* slot_of, u32 n_keys,
-                               Payload* payload) {
+// slot of an existing key (every border of an accepted unitig is one)
+__device__ __forceinline__ u32 find_key_slot(const u64* tkeys, u64 n_buckets, u64 key) {
+    u64 b = bucket_of(key, n_buckets);
+    for (u64 tries = 0; tries < n_buckets; ++tries) {
+        for (int j = 0; j < 4; ++j)
+            if (tkeys[b * 4 + j] == key) return (u32)(b * 4 + j);
+        if (++b == n_buckets) b = 0;
+    }
+    return 0;  // unreachable for a well-formed table
+}
+
+__global__ void k_fill_entries(const u32* sidx, const u32* flags, const u32* run_start, const u32* slot_of, u32 n_keys,
+                               const u64* off, const u64* pool, const u64* tkeys, u64 n_buckets, u32 km1, Entry* entries) {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_keys) return;
-    Payload p;
-    for (int j = 0; j < 4; ++j) p.left[j] = p.right[j] = 0;
+    Entry e;
+    for (int j = 0; j < 4; ++j) {
+        e.left[j].start_len = e.right[j].start_len = 0;
+        e.left[j].id_flags = e.right[j].id_flags = 0;
+        e.left[j].next = e.right[j].next = 0;
+    }
     u32 nl = 0, nr = 0;
     for (u32 j = run_start[r]; j < run_start[r + 1]; ++j) {  // file order (the sort is stable)
         const u32 ix = sidx[j];
         const u32 f = flags[ix];
-        const u32 v = (ix / 2 + 1) | (f & (SLOT_FWD_CANON | SLOT_FWD_RC));
-        if (f & 1u) {
-            p.right[nr < 3 ? nr : 3] = v;  // first free of 4; the 5th and later overwrite slot 4
+        const u32 id = ix / 2 + 1;
+        const u64 start = off[id - 1] - off[0], len = off[id] - off[id - 1];
+        const bool right = (f & 1u) != 0;
+        USlot v;
+        v.start_len = start | (len << SLOT_START_BITS);
+        v.id_flags = id | (f & (SLOT_FWD_CANON | SLOT_FWD_RC));
+        // the entry the walk goes on with: the key slot of the (k-1)-mer at the unitig's other end
+        const u64 c = slot_far_code(pool, start, len, km1, v.id_flags, right);
+        const u64 rc = rcb(c, km1);
+        v.next = find_key_slot(tkeys, n_buckets, c <= rc ? c : rc) | (c <= rc ? SLOT_NEXT_CANON : 0u) |
+                 (c == rc ? SLOT_NEXT_PAL : 0u);
+        if (right) {
+            e.right[nr < 3 ? nr : 3] = v;  // first free of 4; the 5th and later overwrite slot 4
             ++nr;
         } else {
-            p.left[nl < 3 ? nl : 3] = v;
+            e.left[nl < 3 ? nl : 3] = v;
             ++nl;
         }
     }
-    payload[slot_of[r]] = p;
+    entries[slot_of[r]] = e;
 }
 
 // pool word w = characters [32w, 32w+32) of the accepted text, first base most significant
@@ -219,8 +245,8 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     for (; nu < n; ++nu) {
         const u64 len = off[nu + 1] - off[nu];
         if (len < k) break;
-        if (len > 0xFFFFFFFFull) {
-            err = "unitig longer than 2^32-1 bases";
+        if (len >> SLOT_LEN_BITS) {
+            err = "unitig longer than 2^28-1 bases";
             return BGR_ERR_LIMIT;
         }
     }
@@ -229,6 +255,10 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
         return BGR_ERR_LIMIT;
     }
     const u64 total_bases = nu ? off[nu] - off[0] : 0;
+    if (total_bases >> SLOT_START_BITS) {
+        err = "more than 2^36 unitig bases";
+        return BGR_ERR_LIMIT;
+    }
     const u64 pool_words = (total_bases + 31) / 32 + 2;
     const u64 n_refs = 2 * nu;
     if (n_refs >= 0xFFFFFFFFull) {
@@ -284,8 +314,8 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
         ++*launches;
     }
     const u64 n_buckets = std::max<u64>(4, ((u64)n_keys + 1) / 2);  // <= 50 % load
-    if (n_buckets >= 0xFFFFFFFFull) {
-        err = "too many distinct border k-mers for the 32-bit bucket hash";
+    if (n_buckets * 4 > SLOT_NEXT_MASK) {
+        err = "too many distinct border k-mers for 30-bit key slots";
         return BGR_ERR_LIMIT;
     }
 
@@ -293,7 +323,7 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     BlobHeader h;
     memset(&h, 0, sizeof h);
     h.magic = BLOB_MAGIC;
-    h.version = 4;
+    h.version = BLOB_VERSION;
     h.k = k;
     h.n_unitigs = nu;
     h.n_keys = n_keys;
@@ -301,8 +331,8 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     h.pool_words = pool_words;
     auto align_up = [](u64 x) { return (x + 255) & ~255ull; };
     h.off_keys = align_up(sizeof(BlobHeader));
-    h.off_payload = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
-    h.off_meta = align_up(h.off_payload + n_buckets * 4 * sizeof(Payload));
+    h.off_entries = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
+    h.off_meta = align_up(h.off_entries + n_buckets * 4 * sizeof(Entry));
     h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
     bool two_hashes = false;
     h.n_bloom = bloom_words_for(n_keys, two_hashes);
@@ -330,14 +360,19 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
         k_insert_keys<<<grid_for(n_keys, B), B>>>(d_skeys.as<u64>(), d_runstart.as<u32>(), n_keys, (u64*)(Bp + h.off_keys),
                                                    n_buckets, (u32*)(Bp + h.off_bloom), (u32)h.n_bloom, h.bloom_two_hashes,
                                                    k - 1, d_slot.as<u32>());
-        k_fill_payload<<<grid_for(n_keys, B), B>>>(d_sidx.as<u32>(), d_flags.as<u32>(), d_runstart.as<u32>(),
-                                                    d_slot.as<u32>(), n_keys, (Payload*)(Bp + h.off_payload));
-        *launches += 2;
+        ++*launches;
     }
     k_pack_pool<<<grid_for(pool_words, B), B>>>(d_seq.as<char>(), total_bases, (u64*)(Bp + h.off_pool), pool_words,
                                                  d_st.as<BuildStatus>());
     k_unitig_meta<<<grid_for(nu + 1, B), B>>>(d_off.as<u64>(), (u32)nu, (UnitigMeta*)(Bp + h.off_meta));
     *launches += 2;
+    if (n_keys) {  // needs the finished key table and the packed pool (far-end codes)
+        k_fill_entries<<<grid_for(n_keys, B), B>>>(d_sidx.as<u32>(), d_flags.as<u32>(), d_runstart.as<u32>(),
+                                                    d_slot.as<u32>(), n_keys, d_off.as<u64>(), (const u64*)(Bp + h.off_pool),
+                                                    (const u64*)(Bp + h.off_keys), n_buckets, k - 1,
+                                                    (Entry*)(Bp + h.off_entries));
+        ++*launches;
+    }
     GCK(cudaGetLastError());
     BuildStatus st;
     GCK(cudaMemcpy(&st, d_st.p, sizeof st, cudaMemcpyDeviceToHost));  // synchronises with the kernels

@@ -131,10 +131,10 @@ int grow(bgr_ctx* ctx, T*& p, size_t& cap, size_t need, size_t slack_num = 5, si
 int set_index_from_device_blob(bgr_ctx* ctx) {
     CK(cudaMemcpy(&ctx->hdr, ctx->d_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost));
     const BlobHeader& h = ctx->hdr;
-    if (h.magic != BLOB_MAGIC || h.version != 4) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
+    if (h.magic != BLOB_MAGIC || h.version != BLOB_VERSION) return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version");
     char* B = (char*)ctx->d_blob;
     ctx->ix.keys = (const u64*)(B + h.off_keys);
-    ctx->ix.payload = (const Payload*)(B + h.off_payload);
+    ctx->ix.entries = (const Entry*)(B + h.off_entries);
     ctx->ix.meta = (const UnitigMeta*)(B + h.off_meta);
     ctx->ix.pool = (const u64*)(B + h.off_pool);
     ctx->ix.n_buckets = h.n_buckets;
@@ -159,7 +159,7 @@ int install_host_blob(bgr_ctx* ctx, const void* blob, u64 bytes) {
     if (bytes < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index blob too small");
     BlobHeader h;
     memcpy(&h, blob, sizeof h);
-    if (h.magic != BLOB_MAGIC || h.version != 4 || h.total_bytes != bytes)
+    if (h.magic != BLOB_MAGIC || h.version != BLOB_VERSION || h.total_bytes != bytes)
         return fail(ctx, BGR_ERR_FORMAT, "index blob: bad magic/version/size");
     CK(cudaSetDevice(ctx->device));
     int rc = drop_index(ctx);
@@ -508,7 +508,7 @@ int bgr_index_load_file(bgr_ctx* ctx, const char* path, uint32_t k) {
     if (mf.size < sizeof(BlobHeader)) return fail(ctx, BGR_ERR_FORMAT, "index file too small");
     BlobHeader h;
     memcpy(&h, mf.data, sizeof h);
-    if (h.magic != BLOB_MAGIC || h.version != 4 || h.total_bytes != mf.size)
+    if (h.magic != BLOB_MAGIC || h.version != BLOB_VERSION || h.total_bytes != mf.size)
         return fail(ctx, BGR_ERR_FORMAT, "index file: bad magic/version/size");
     if (h.k != k) return fail(ctx, BGR_ERR_FORMAT, "index file was built for another k");
     return install_host_blob(ctx, mf.data, mf.size);

@@ -33,7 +33,7 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     char* B = (char*)blob.data();
     DevIndex ix;
     ix.keys = (const u64*)(B + h.off_keys);
-    ix.payload = (const Payload*)(B + h.off_payload);
+    ix.entries = (const Entry*)(B + h.off_entries);
     ix.meta = (const UnitigMeta*)(B + h.off_meta);
     ix.pool = (const u64*)(B + h.off_pool);
     ix.n_buckets = h.n_buckets;

@@ -60,7 +60,7 @@ def test_packed_upload_golden_vectors_of_the_reference(bg, case):
 @pytest.mark.parametrize("seed", range(2000, 2040))
 def test_packed_upload_fuzz_against_oracle(bg, seed):
     c = S.fuzz_case(seed)
-    _check(bg, c["k"], c["m"], c["effort"], c["unitigs"], c["reads"], (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH))
+    _check(bg, c["k"], c["m"], c["effort"], c["unitigs"], c["reads"], (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH, O.EXHAUSTIVE_PATH))
 
 
 def test_packed_upload_many_tiles_mixed_lengths_and_n(bg):

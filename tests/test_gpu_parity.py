@@ -53,7 +53,7 @@ def test_golden_vectors_of_the_reference(bg, case):
 @pytest.mark.parametrize("seed", range(2000, 2060))
 def test_fuzz_against_oracle(bg, seed):
     c = S.fuzz_case(seed)
-    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH):
+    for mode in (O.GREEDY, O.EXHAUSTIVE, O.GREEDY_PATH, O.EXHAUSTIVE_PATH):
         want, wc = oracle_results(c["k"], c["m"], c["effort"], c["unitigs"], c["reads"], mode)
         al = bg.Aligner(c["k"], c["m"], c["effort"])
         al.index_unitigs(c["unitigs"])
@@ -250,22 +250,38 @@ def test_effort_and_mismatch_sweep_properties(bg):
 # content; only the slot a key occupies inside its probe sequence may differ
 
 def _blob_view(blob):
-    """-> (header dict, {key: payload bytes}, meta bytes, pool bytes, bloom bytes)"""
-    names = ["magic", "vk", "n_unitigs", "n_keys", "n_buckets", "pool_words", "off_keys", "off_payload", "off_meta",
+    """-> (header dict, {key: entry}, meta bytes, pool bytes, bloom bytes, invariants hold). An entry is the key's
+    8 slots as (start_len, id_flags, KEY of the next-level slot, next flags): the slot a key occupies inside its
+    probe sequence may differ between the builders, so the links are compared by the key they lead to."""
+    names = ["magic", "vk", "n_unitigs", "n_keys", "n_buckets", "pool_words", "off_keys", "off_entries", "off_meta",
              "off_pool", "total_bytes", "n_bloom", "off_bloom", "two"]
     h = dict(zip(names, np.frombuffer(blob[:8 * len(names)].tobytes(), dtype=np.uint64).tolist()))
     nslots = h["n_buckets"] * 4
     keys = np.frombuffer(blob[h["off_keys"]:h["off_keys"] + 8 * nslots].tobytes(), dtype=np.uint64)
-    pay = np.frombuffer(blob[h["off_payload"]:h["off_payload"] + 32 * nslots].tobytes(), dtype=np.uint8).reshape(nslots, 32)
-    table = {int(k): pay[i].tobytes() for i, k in enumerate(keys) if k != 0xFFFFFFFFFFFFFFFF}
-    empty_payload_ok = all(not pay[i].any() for i, k in enumerate(keys) if k == 0xFFFFFFFFFFFFFFFF)
+    ent = np.frombuffer(blob[h["off_entries"]:h["off_entries"] + 128 * nslots].tobytes(), dtype=np.uint32).reshape(nslots, 8, 4)
+    EMPTY = 0xFFFFFFFFFFFFFFFF
+    table, links_ok = {}, True
+    for i, k in enumerate(keys):
+        if k == EMPTY:
+            continue
+        slots = []
+        for lo, hi, idf, nxt in ent[i].tolist():
+            if idf == 0:
+                slots.append((0, 0, 0, 0))
+                links_ok &= (lo | hi | nxt) == 0
+            else:
+                nk = int(keys[nxt & 0x3FFFFFFF])
+                links_ok &= nk != EMPTY
+                slots.append((lo | (hi << 32), idf, nk, nxt >> 30))
+        table[int(k)] = tuple(slots)
+    empty_ok = all(not ent[i].any() for i, k in enumerate(keys) if k == EMPTY)
     meta = blob[h["off_meta"]:h["off_meta"] + 16 * (h["n_unitigs"] + 1)].tobytes()
     pool = blob[h["off_pool"]:h["off_pool"] + 8 * h["pool_words"]].tobytes()
     bloom = blob[h["off_bloom"]:h["off_bloom"] + 4 * h["n_bloom"]].tobytes()
     # probe-sequence invariant: slots of a bucket fill in order
-    kb = keys.reshape(-1, 4) != 0xFFFFFFFFFFFFFFFF
+    kb = keys.reshape(-1, 4) != EMPTY
     in_order = bool((kb[:, :-1] >= kb[:, 1:]).all())
-    return h, table, meta, pool, bloom, empty_payload_ok and in_order
+    return h, table, meta, pool, bloom, empty_ok and in_order and links_ok
 
 
 def _build_both(bg, k, unitigs):
