@@ -135,6 +135,11 @@ static const int EXT_THREADS = 128;
 //      prefix sums, loads two pool words and two read words, XOR + popc, and adds to the job's counter;
 //   3. every walking lane reads its counters and settles the level (GreedyState::level_settle).
 // The loads of step 2 are all independent and issued together: a level is two dependent round trips.
+// Measured (10 M reads, 6.4 M of them listed): 15 of 32 threads per instruction, 3.48 ms at 5 Mbp, 4.68 ms at
+// 3 Gbp against 3.49 / 5.9 ms for thread-per-read (profiles/r02_ncu_k_extend_greedy_a_warp_*.txt). A CTA-wide
+// form of the same stages -- read states in shared memory, per-round lists of the reads at each stage, so that
+// every stage runs on dense warps -- reached 21.6 of 32 threads but lost the time to its seven barriers per
+// round and to moving state in and out of shared memory: 5.0 / 6.6 ms (profiles/r02_ncu_k_extend_greedy_b_cta_*.txt).
 struct ExtJob {   // 32 bytes
     u64 ua;       // first unitig base, forward pool coordinates
     u64 wofs;     // the read's first data word in BatchArgs::F / NM

@@ -179,6 +179,7 @@ int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
             switch (ctx->ext_blocks_per_sm) {
                 case 8: k_extend_greedy<8><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
                 case 6: k_extend_greedy<6><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+                case 4: k_extend_greedy<4><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
                 default: k_extend_greedy<5><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
             }
             break;
@@ -319,7 +320,7 @@ int bgr_ctx_create(int device, int n_slots, bgr_ctx** out) {
     if (const char* e = getenv("BGR_SCAN")) ctx->scan_ws = strcmp(e, "classic") != 0;
     if (const char* e = getenv("BGR_EXT_MINB")) {
         int v = atoi(e);
-        if (v == 5 || v == 6 || v == 8) ctx->ext_blocks_per_sm = (u32)v;
+        if (v == 4 || v == 5 || v == 6 || v == 8) ctx->ext_blocks_per_sm = (u32)v;
     }
     for (int i = 0; i < n_slots; ++i) {
         Slot& s = ctx->slots[i];
