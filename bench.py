@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the read-to-de-Bruijn-graph mapping path on B200 (BASELINE.json metric).
 
-A "step" is one pass of the hot path (pack + seed scan/index probe + greedy extension) over one batch
-set of synthetic reads: BASELINE.json configs[1] -- simulated 5 Mbp diploid genome, its k=31 unitigs,
-10 M 150 bp reads at 1 % substitution error, -m 2, greedy mode, effort 2 -- per GPU (weak scaling).
+Default workload = BASELINE.json configs[4], one GPU's shard: synthetic 3 Gbp diploid genome (SNP 1/150, 0.1 % of the
+sequence in 2..6-copy repeat families), its k=31 unitigs (60 M unitigs, 40 M border keys, 13 GB index replicated in
+HBM), 150 bp reads at 1 % substitution error, -m 2 -e 2, greedy mode, 10 M reads per GPU and pass (weak scaling).
+A "step" is PASSES passes of the hot path (pack + seed scan / index probe + greedy extension + path compaction) over
+the batch, so that the timed region of the default run lasts more than a second. The other configs are selected
+with --genome / --errors / --mode / --sub-rate and are named in `config.workload`.
 
-  value : whole-job reads/s with the reads already resident in HBM (device time, CUDA events on the
-          launching stream, max over ranks)
-  e2e   : the same metric through the C ABI with HOST (pinned) buffers: every step moves the reads host->device
-          and the result records + paths device->host. Three forms of the public API are timed -- read
-          characters over PCIe (bgr_slot_upload), reads packed to 2 bits per base by the host cores inside the
-          timed region (bgr_pack_reads + bgr_slot_upload_packed), and a mix of both -- the fastest is the
-          headline, all three are reported under e2e.forms
-  roofline     : the seed-scan / index-probe kernel (k_scan_tiles_ws) against the measured HBM peak
+  value : whole-job reads/s with the reads already resident in HBM (device time, CUDA events on the launching
+          stream, max over ranks)
+  e2e   : the same metric through the C ABI with HOST (pinned) buffers, every pass moving the reads host->device
+          and the result records + paths device->host. The headline is the form the reference's own API has --
+          read CHARACTERS (bgr_slot_upload); the two other upload forms of the public API (reads packed to 2 bits
+          per base by the host cores inside the timed region, and a mix of both) are reported beside it
+  roofline     : the kernel that takes the most device time, and under `kernels` both hot kernels, each with the
+                 bytes this design has to move (inputs once, outputs once), the DRAM bytes ncu measured for this
+                 graph size, the resource that binds it, and -- separately, as model_frac -- SURVEY 8(d)'s model
   cpu_baseline : the reference `bgreat -t <all cores>` on a bounded sample of the same reads
 
-`--impl reference` times the reference's own CPU implementation instead (oracle/_ref/bgreat, built from
-the unmodified sources; falls back to the oracle port if that binary cannot run on this host).
+`--impl reference` times the reference's own CPU implementation instead (oracle/_ref/bgreat, built from the
+unmodified sources; falls back to the oracle port if that binary cannot run on this host): ONE process that
+indexes the graph once and maps warm-up + steps copies of the sample file (`-r f,f,...,f`, aligner.cpp:554-586);
+a step's time is the time between two file names appearing on its stdout.
 """
 import argparse
 import ctypes as C
@@ -41,31 +47,35 @@ EFFORT = 2
 READ_LEN = 150
 SUB_RATE = 0.01
 EXHAUSTIVE = False
-WORKLOAD = "configs[1]: synthetic 5 Mbp diploid genome (SNP 1/150), k=31 unitigs, 150 bp reads at 1% substitutions, -m 2 -e 2, greedy"
-
-
-ROOFLINE_NOTE = ("achieved = SURVEY 8(d) algorithmic bytes (one 32-byte index sector per (k-1)-mer window the reference "
-                 "examines + 40 B of packed read) / measured kernel time. The kernel answers most windows from a Bloom "
-                 "filter (shared memory for small indexes, L2 for large ones) and only verifies survivors in the key "
-                 "table, so it moves far fewer DRAM bytes than that model (see traffic) and frac can exceed 1: with the "
-                 "filter in shared memory it is bound by the integer ALU pipe (80 %% of peak, issue slots 68 %% busy: "
-                 "profiles/r01_ncu_k_scan_tiles_v9_5Mbp.txt), with the filter in L2 by L2 sector throughput (one random "
-                 "sector per window, 1.6 G sectors in 5.8 ms: profiles/r01_ncu_k_scan_tiles_v9_1Gbp.txt). "
-                 "Index blob: %.1f MB.")
+REPEAT_FRAC = 0.001
+PASSES = 8
+DEFAULT_GENOME = 3_000_000_000
+WORKLOAD = ""
 
 
 def configure(args):
-    """The default run is BASELINE.json configs[1] (the configuration the metric is quoted on). The other
-    configs (larger graphs, -m sweep, exhaustive mode) are selected with flags and named in `workload`."""
-    global ERRORS, EFFORT, SUB_RATE, EXHAUSTIVE, WORKLOAD
+    """The default run is BASELINE.json configs[4] (the 3 Gbp graph the metric's HBM target is defined on), one
+    10 M-read shard per GPU and pass. The other configs (smaller graphs, -m sweep, exhaustive mode) are selected
+    with flags and named in `workload`."""
+    global ERRORS, EFFORT, SUB_RATE, EXHAUSTIVE, WORKLOAD, REPEAT_FRAC, PASSES
     ERRORS, EFFORT, SUB_RATE, EXHAUSTIVE = args.errors, args.effort, args.sub_rate, args.mode == "exhaustive"
-    default = (args.genome == 5_000_000 and ERRORS == 2 and EFFORT == 2 and SUB_RATE == 0.01 and not EXHAUSTIVE)
-    if not default:
-        g = args.genome
-        gs = "%g Gbp" % (g / 1e9) if g >= 1e9 else "%g Mbp" % (g / 1e6)
-        WORKLOAD = ("%ssynthetic %s diploid genome (SNP 1/150), k=31 unitigs, 150 bp reads at %g%% substitutions, "
-                    "-m %d -e %d, %s" % ((args.label + ": ") if args.label else "", gs, 100 * SUB_RATE, ERRORS, EFFORT,
-                                         args.mode))
+    REPEAT_FRAC, PASSES = args.repeat_frac, max(1, args.passes)
+    g = args.genome
+    gs = "%g Gbp" % (g / 1e9) if g >= 1e9 else "%g Mbp" % (g / 1e6)
+    default = (g == DEFAULT_GENOME and ERRORS == 2 and EFFORT == 2 and SUB_RATE == 0.01 and not EXHAUSTIVE)
+    label = args.label or ("configs[4], one shard of the 1 B reads per GPU" if default else "")
+    WORKLOAD = ("%ssynthetic %s diploid genome (SNP 1/150, %g%% repeats), k=31 unitigs, 150 bp reads at %g%% "
+                "substitutions, -m %d -e %d, %s" % ((label + ": ") if label else "", gs, 100 * REPEAT_FRAC, 100 * SUB_RATE,
+                                                    ERRORS, EFFORT, args.mode))
+
+
+def workload_config(args):
+    """`config` of the JSON line: the workload, the same in both arms."""
+    return {"workload": WORKLOAD, "genome_bp": args.genome, "repeat_frac": REPEAT_FRAC, "k": K, "errors": ERRORS,
+            "effort": EFFORT, "read_len": READ_LEN, "sub_rate": SUB_RATE, "mode": args.mode,
+            "reads_per_gpu_per_pass": args.reads, "passes_per_step": PASSES,
+            "parallelism": "reads sharded across GPUs, index replicated",
+            "l2": "inputs (1.5 GB of read characters per pass) exceed L2; no flush needed"}
 
 
 def parse_args():
@@ -74,8 +84,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--genome", type=int, default=5_000_000)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per pass")
+    ap.add_argument("--passes", type=int, default=8, help="passes over the batch per step")
+    ap.add_argument("--genome", type=int, default=DEFAULT_GENOME)
+    ap.add_argument("--repeat-frac", type=float, default=0.001, help="fraction of the genome in repeat families")
     ap.add_argument("--batch", type=int, default=1 << 20, help="reads per batch on the end-to-end leg")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -169,7 +181,10 @@ def scratch_dir():
 
 
 class CpuReference:
-    """The reference's own CPU implementation of the path, on this box's host cores."""
+    """The reference's own CPU implementation of the path, on this box's host cores: ONE `bgreat` process that
+    indexes the graph once and then maps the sample file as many times as asked (-r f,f,...,f). The reference
+    prints each read file's name when it opens it and "The End" after the last one (aligner.cpp:556-588), so the
+    time between two of those lines is the mapping time of one file: no index-only run to subtract."""
 
     def __init__(self, graph, n_sample, seed_first=0):
         from oracle import oracle as O
@@ -180,9 +195,7 @@ class CpuReference:
         self.cores = min(host_cores(), 255)  # -t is kept in an unsigned char (reference aligner.h:80)
         self.unitigs = os.path.join(self.dir, "unitigs.fa")
         self.reads = os.path.join(self.dir, "reads.fa")
-        self.empty = os.path.join(self.dir, "empty.fa")
         graph.write_unitigs(self.unitigs)
-        open(self.empty, "w").close()
         self.kind = "reference"
         self.index_s = None
         if not os.access(O.REF_BGREAT, os.X_OK) or not self._binary_runs():
@@ -191,66 +204,76 @@ class CpuReference:
             self.n = n_sample = min(n_sample, 300_000)
         seqs, off = graph.make_reads(n_sample, READ_LEN, SUB_RATE, first=seed_first)
         synth.write_reads(self.reads, seqs, off, n_sample, first=seed_first)
-        self.sample_seqs, self.sample_off = seqs, off
-
-    def _run_binary(self, reads_file):
-        t0 = time.perf_counter()
-        out = subprocess.run([self.O.REF_BGREAT, "-r", reads_file, "-g", self.unitigs, "-k", str(K), "-m", str(ERRORS),
-                              "-e", str(EFFORT), "-t", str(self.cores), "-f", os.path.join(self.dir, "paths.ref"),
-                              "-a", os.path.join(self.dir, "na.ref")] + (["-b"] if EXHAUSTIVE else []), capture_output=True, text=True, cwd=self.dir,
-                             timeout=3600)
-        dt = time.perf_counter() - t0
-        if out.returncode != 0:
-            raise RuntimeError("reference bgreat failed: rc=%d %s" % (out.returncode, out.stderr[-200:]))
-        reads = 0
-        for l in out.stdout.splitlines():
-            if l.startswith("Reads : "):
-                reads = int(l.split(":")[1])
-        return dt, reads
+        del seqs, off
 
     def _binary_runs(self):
-        try:
-            # index-only run (empty read file): its wall time is subtracted from every step, which
-            # matches the scope of the reference's own "Mapping in seconds" (aligner.cpp:551,594)
-            a, _ = self._run_binary(self.empty)
-            b, _ = self._run_binary(self.empty)
-            self.index_s = min(a, b)
-            return True
-        except Exception as e:  # e.g. SIGILL on a host without AVX2
+        try:  # e.g. SIGILL on a host without AVX2
+            return subprocess.run([self.O.REF_BGREAT], capture_output=True, timeout=60).returncode == 0
+        except Exception as e:
             sys.stderr.write("bench: reference binary unusable here (%s); using the oracle port\n" % e)
             return False
 
-    def step(self):
-        """-> (reads mapped, seconds of mapping)"""
-        if self.kind == "reference":
-            dt, reads = self._run_binary(self.reads)
-            return reads, max(dt - self.index_s, 1e-6)
-        o = self.O.Oracle(K, ERRORS, EFFORT)
-        o.index_file(self.unitigs)
+    def run(self, n_files):
+        """-> per-file mapping seconds (n_files of them), reads per file"""
+        if self.kind == "port":
+            o = self.O.Oracle(K, ERRORS, EFFORT)
+            o.index_file(self.unitigs)
+            out = []
+            for _ in range(n_files):
+                t0 = time.perf_counter()
+                o.run(self.O.EXHAUSTIVE if EXHAUSTIVE else self.O.GREEDY, self.reads, False,
+                      os.path.join(self.dir, "paths.port"), os.path.join(self.dir, "na.port"))
+                out.append(time.perf_counter() - t0)
+            return out, self.n
+        cmd = [self.O.REF_BGREAT, "-r", ",".join(["reads.fa"] * n_files), "-g", "unitigs.fa", "-k", str(K), "-m", str(ERRORS),
+               "-e", str(EFFORT), "-t", str(self.cores), "-f", "paths.ref", "-a", "na.ref"] + (["-b"] if EXHAUSTIVE else [])
         t0 = time.perf_counter()
-        o.run(self.O.EXHAUSTIVE if EXHAUSTIVE else self.O.GREEDY, self.reads, False, os.path.join(self.dir, "paths.port"), os.path.join(self.dir, "na.port"))
-        return self.n, time.perf_counter() - t0
-
-    def windows_per_read(self, n=20000):
-        """W of SURVEY 8(d): (k-1)-mer windows the reference examines per read (incl. RC retries),
-        from the oracle's instrumentation on a prefix of the sample."""
-        o = self.O.Oracle(K, ERRORS, EFFORT)
-        o.index_file(self.unitigs)
-        b = self.sample_seqs.tobytes()
-        n = min(n, self.n)
-        for i in range(n):
-            o.align(b[int(self.sample_off[i]):int(self.sample_off[i + 1])],
-                    self.O.EXHAUSTIVE if EXHAUSTIVE else self.O.GREEDY)
-        c = o.counters()
-        return c["windows"] / float(n), c
+        p = subprocess.Popen(cmd, cwd=self.dir, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        marks, reads = [], 0
+        for line in p.stdout:
+            now = time.perf_counter()
+            line = line.strip()
+            if line == "reads.fa" or line == "The End":
+                marks.append(now)
+            elif line.startswith("Reads : "):
+                reads = int(line.split(":")[1])
+        rc = p.wait()
+        if rc != 0 or len(marks) != n_files + 1:
+            raise RuntimeError("reference bgreat failed: rc=%d, %d file marks" % (rc, len(marks)))
+        self.index_s = marks[0] - t0
+        return [marks[i + 1] - marks[i] for i in range(n_files)], reads // n_files
 
     def describe(self):
-        return "%d reads of the same synthetic set (%s), -t %d" % (self.n, "oracle/_ref/bgreat, index time subtracted"
-                                                                  if self.kind == "reference" else "oracle C port",
-                                                                  self.cores)
+        return "%d reads of the same synthetic set (%s), -t %d; one process, index built once (%s s), time per file " \
+               "from its stdout" % (self.n, "oracle/_ref/bgreat" if self.kind == "reference" else "oracle C port",
+                                    self.cores, "%.0f" % self.index_s if self.index_s else "-")
 
     def cleanup(self):
         shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def reference_model(n=20000):
+    """What the reference does per read on this workload -- windows it examines, index queries, comparisons and
+    compared bases -- from the oracle's instrumentation (these figures come from the spec model, not
+    from the GPU implementation). They are properties of the reads and of the graph's local shape, not of the
+    genome's length, so they are taken on a 5 Mbp graph of the same generator (the oracle would need minutes and
+    tens of GB to index the 3 Gbp one)."""
+    from oracle import oracle as O
+    from tools import synth
+    g = synth.Graph(5_000_000, K, seed=1, repeat_frac=REPEAT_FRAC)
+    o = O.Oracle(K, ERRORS, EFFORT)
+    o.index_unitigs(g.unitig_list())
+    seqs, off = g.make_reads(n, READ_LEN, SUB_RATE)
+    b = seqs.tobytes()
+    for i in range(n):
+        o.align(b[int(off[i]):int(off[i + 1])], O.EXHAUSTIVE if EXHAUSTIVE else O.GREEDY)
+    c = o.counters()
+    return {k_: c[k_] / float(n) for k_ in ("windows", "queries", "compares", "cmp_bases")}
+
+
+def cpu_cache_path(args):
+    key = "%d_%g_%d_%d_%g_%s_%d" % (args.genome, REPEAT_FRAC, ERRORS, EFFORT, SUB_RATE, args.mode, min(host_cores(), 255))
+    return os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), "bgr_cpu_baseline_%s.json" % key)
 
 
 def cli_leg(graph, n_reads):
@@ -296,8 +319,9 @@ def cli_leg(graph, n_reads):
 def auto_cpu_sample(args):
     if args.cpu_sample:
         return min(args.cpu_sample, args.reads)
-    # ~25 k reads/s/thread measured for the reference -> about 8 s of work
-    return int(min(args.reads, 200_000 * min(host_cores(), 255)))
+    # ~25 k reads/s/thread measured for the reference on the small graphs, about half that on the 3 Gbp one
+    #  -> a few seconds of work per file
+    return int(min(args.reads, 100_000 * min(host_cores(), 255)))
 
 
 def run_reference_arm(args):
@@ -305,29 +329,27 @@ def run_reference_arm(args):
     if rank != 0:
         return
     from tools import synth
-    graph = synth.Graph(args.genome, K, seed=1)
+    graph = synth.Graph(args.genome, K, seed=1, repeat_frac=REPEAT_FRAC)
     n = auto_cpu_sample(args)
     ref = CpuReference(graph, n)
+    del graph
     try:
-        for _ in range(args.warmup):
-            ref.step()
-        t, reads = 0.0, 0
-        for _ in range(args.steps):
-            r, dt = ref.step()
-            reads += r
-            t += dt
-        v = reads / t
+        secs, per_file = ref.run(args.warmup + args.steps)
+        timed = secs[args.warmup:]
+        v = per_file * len(timed) / sum(timed)
+        cpu = {"value": v, "unit": "reads/s", "cores": ref.cores, "kind": ref.kind, "sample": ref.describe()}
         line = {
             "impl": "reference", "metric": "reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(timed) / max(len(timed), 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "char", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "genome_bp": args.genome, "k": K, "errors": ERRORS, "effort": EFFORT,
-                       "read_len": READ_LEN, "reads_per_step": n},
-            "bases_per_s": v * READ_LEN,
-            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ref.cores, "kind": ref.kind,
-                             "sample": ref.describe()},
+            "config": workload_config(args), "bases_per_s": v * READ_LEN, "reads_per_step": per_file,
+            "index_s": ref.index_s, "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
+        try:  # the B200 arm that follows on this box reports this measurement instead of indexing the graph again
+            json.dump(dict(cpu, when=time.time()), open(cpu_cache_path(args), "w"))
+        except Exception:
+            pass
         print(json.dumps(line), flush=True)
     finally:
         ref.cleanup()
@@ -389,7 +411,9 @@ def run_b200_arm(args):
     n_reads = args.reads
 
     # ---- graph + index: built once on rank 0, replicated by one NCCL broadcast of the flat blob
-    graph = synth.Graph(args.genome, K, seed=1)
+    # only the rank that builds the index needs the unitigs; the others regenerate the stretches of genome their
+    # reads come from (tools/bgr_synth.cpp: nothing of genome size is stored)
+    graph = synth.Graph(args.genome, K, seed=1, repeat_frac=REPEAT_FRAC, unitigs=(rank == 0))
     al = bgreat_b200.Aligner(K, ERRORS, EFFORT, device=local, n_slots=1 + E2E_DEPTH)
     from bgreat_b200 import shard
     t0 = time.perf_counter()
@@ -425,10 +449,13 @@ def run_b200_arm(args):
     ms = (C.c_float * 3)()
 
     def resident_step():
-        ck(L.bgr_slot_run(ctx, 0, C.byref(params)))
-        ck(L.bgr_slot_wait(ctx, 0, None))
-        ck(L.bgr_slot_kernel_ms(ctx, 0, ms))
-        return ms[0], ms[1], ms[2]
+        tot = np.zeros(3)
+        for _ in range(PASSES):
+            ck(L.bgr_slot_run(ctx, 0, C.byref(params)))
+            ck(L.bgr_slot_wait(ctx, 0, None))
+            ck(L.bgr_slot_kernel_ms(ctx, 0, ms))
+            tot += (ms[0], ms[1], ms[2])
+        return tot
 
     for _ in range(args.warmup):
         resident_step()
@@ -448,7 +475,7 @@ def run_b200_arm(args):
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
     dev_ms = dev_ms.cpu().numpy()
     steps = max(args.steps, 1)
-    value = world * n_reads * steps / (dev_ms[2] / 1e3)
+    value = world * n_reads * PASSES * steps / (dev_ms[2] / 1e3)
 
     # the same leg with the reads resident as the 2-bit stream the packed / mixed end-to-end forms upload
     # (extra information: `value` above stays on the character form)
@@ -537,7 +564,7 @@ def run_b200_arm(args):
             e2e_step(form)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(args.steps * PASSES):
             e2e_step(form)
         barrier()
         t1 = time.perf_counter()
@@ -546,7 +573,7 @@ def run_b200_arm(args):
             dist.all_reduce(sec, op=dist.ReduceOp.MAX)
         return float(sec.item()), t1, int((res_np[:, 0] & 1).sum()), d2h[0], h2d_packed[0]
 
-    # both upload forms of the public API are timed; the headline is the faster one, the other is reported beside it
+    # all upload forms of the public API are timed; the headline is the character form
     what = {"characters": "bgr_slot_upload: read characters + offsets cross PCIe (8 bits per base)",
             "packed": "bgr_pack_reads (host cores, inside the timed region) + bgr_slot_upload_packed: 2 bits per base "
                       "+ offsets + flag bitmap cross PCIe",
@@ -556,11 +583,12 @@ def run_b200_arm(args):
     for form in ("characters", "packed", "mixed"):
         sec, t_e1, m, d2h_f, h2d_f = time_e2e(form)
         mapped.add(m)
-        e2e_forms[form] = {"value": world * n_reads * steps / sec, "unit": "reads/s", "ms_per_step": 1e3 * sec / steps,
-                           "h2d_bytes_per_step": int(h2d_f), "d2h_bytes_per_step": int(d2h_f), "what": what[form]}
+        e2e_forms[form] = {"value": world * n_reads * PASSES * steps / sec, "unit": "reads/s", "ms_per_step": 1e3 * sec / steps,
+                           "h2d_bytes_per_step": int(h2d_f) * PASSES, "d2h_bytes_per_step": int(d2h_f) * PASSES,
+                           "what": what[form]}
         if form != "characters":
             e2e_forms[form]["host_pack_threads"] = pack_threads
-    e2e_best = max(e2e_forms, key=lambda f: e2e_forms[f]["value"])
+    e2e_best = "characters"  # the headline is the reference API's own shape; the other forms are reported beside it
     e2e_s_best = e2e_forms[e2e_best]["ms_per_step"] * steps / 1e3
     e2e_value = e2e_forms[e2e_best]["value"]
     clocks.stop()
@@ -575,69 +603,124 @@ def run_b200_arm(args):
             dist.destroy_process_group()
         return
 
-    # ================= roofline of the probe kernel + CPU baseline (rank 0) =================
+    # ================= rooflines of the two hot kernels + CPU baseline (rank 0) =================
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof):
-        try:
-            # measured DRAM bytes of one 10 M-read launch of the scan kernel on a graph of this size
-            # (ncu --set full, tools/gpu_profile.sh), scaled to this run's reads per launch
-            t10 = json.load(open(prof)).get("k_scan_tiles@%d" % args.genome)
-            traffic = None if t10 is None else t10 * n_reads / 1e7
-        except Exception:
-            traffic = None
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        pass
+
+    def measured_traffic(kernel):
+        """DRAM bytes of one 10 M-read launch of `kernel` on a graph of this size (ncu --set full,
+        tools/gpu_profile.sh -> profiles/roofline_traffic.json), scaled to this run's reads per launch"""
+        t10 = prof.get("%s@%d" % (kernel, args.genome))
+        return None if t10 is None else t10 * n_reads / 1e7
 
     cpu = None
-    w_per_read, w_src = 121.5, "SURVEY.md 8(d) figure"
-    if not args.no_cpu_baseline:
-        ref = CpuReference(graph, auto_cpu_sample(args))
+    if not args.no_cpu_baseline and world == 1:
+        cache = cpu_cache_path(args)
         try:
-            if world == 1:
-                r, dt = ref.step()
-                cpu = {"value": r / dt, "unit": "reads/s", "cores": ref.cores, "kind": ref.kind,
+            c = json.load(open(cache))
+            if time.time() - c.pop("when") < 3 * 3600:
+                cpu = c
+                cpu["sample"] += "; measured by `bench.py --impl reference` on this box %d min before this run" % (
+                    (time.time() - os.path.getmtime(cache)) / 60)
+        except Exception:
+            cpu = None
+        if cpu is None:
+            ref = CpuReference(graph, auto_cpu_sample(args))
+            try:
+                secs, per_file = ref.run(3)  # one warm-up file, two timed
+                cpu = {"value": 2 * per_file / sum(secs[1:]), "unit": "reads/s", "cores": ref.cores, "kind": ref.kind,
                        "sample": ref.describe()}
-            w_per_read, _ = ref.windows_per_read()
-            w_src = "oracle instrumentation, 20000 reads of this set"
-        finally:
-            ref.cleanup()
-    algo_bytes = n_reads * (w_per_read * 32.0 + 40.0)
-    scan_ms = dev_ms[0] / steps
-    achieved = algo_bytes / (scan_ms / 1e3) / 1e9
+            finally:
+                ref.cleanup()
+    model = {"windows": 119.1, "queries": 2.853, "compares": 3.747, "cmp_bases": 155.1}
+    model_src = "SURVEY.md 8(d) / round-1 oracle instrumentation"
+    if not args.no_cpu_baseline:
+        try:
+            model = reference_model()
+            model_src = "oracle instrumentation, 20000 reads on a 5 Mbp graph of the same generator"
+        except Exception as e:
+            sys.stderr.write("bench: oracle instrumentation skipped (%s)\n" % e)
+
+    per_pass = steps * PASSES
+    scan_ms, ext_ms = dev_ms[0] / per_pass, dev_ms[1] / per_pass
+    listed = counters["aligned"] + counters["not_aligned"]  # reads the extension kernel looked at (greedy mode)
+    listed_per_read = listed / max(counters["reads"], 1)
+    verified_per_read = counters["verified"] / max(counters["reads"], 1)
+    # ---- the bytes this design has to move per read, inputs once and outputs once
+    #   scan: characters + offset in; packed words (40 B) + hit mask (16 B) + info (4 B) + result or list entry (8 B)
+    #         out; one 8-byte filter block per run of windows sharing a minimizer (~W/8; one 4-byte word per window
+    #         on indexes with the word filters... counted as W/8 blocks of 8 B here only for the minimizer tier) and
+    #         one 32-byte key bucket per window that passes the filter (counter `verified`)
+    #   extension (per read the scan lists): list entry, offsets, info, hit mask, packed words in (4+16+4+16+40);
+    #         per seed a key bucket (32 B); per index query one entry side (64 B); per comparison the unitig words
+    #         under it (cmp_bases/4 bytes, at least one 32-byte sector); path ints + result record out
+    large = stats["keys"] > 131072
+    filt = (model["windows"] / 8.0) * 8.0 if large else 0.0
+    scan_bytes = READ_LEN + 8 + 40 + 16 + 4 + 8 + filt + 32.0 * verified_per_read
+    lm = 1.0 / max(listed_per_read, 1e-9)  # the model's per-read figures are over all reads: per listed read
+    cmp_b = max(32.0, model["cmp_bases"] / max(model["compares"], 1e-9) / 4.0)
+    ext_bytes = listed_per_read * (80 + 32 * 1.15 + lm * (64.0 * model["queries"] + cmp_b * model["compares"]) + 4 * 6 + 8)
+    # SURVEY 8(d)'s model of the same two kernels (what the reference's algorithm would move)
+    model_scan = model["windows"] * 32.0 + 40.0
+    model_ext = 32.0 * model["queries"] + model["compares"] * (16 + 32.0) + 17
+
+    def roof(name, kernel_key, ms_, need, model_b, bound_note):
+        ach = need * n_reads / (ms_ / 1e3) / 1e9
+        tr = measured_traffic(kernel_key)
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": tr, "traffic_achieved_gbs": None if tr is None else tr / (ms_ / 1e3) / 1e9,
+                "necessary_bytes_per_read": need, "necessary_bytes_per_launch": need * n_reads, "kernel_ms": ms_,
+                "model_bytes_per_read": model_b, "model_frac": model_b * n_reads / (ms_ / 1e3) / 1e9 / peak,
+                "binding": bound_note, "peak_source": peak_src}
+
+    tier = "L2/HBM (minimizer-addressed filter)" if large else "shared memory (filter copied into every CTA)"
+    k_scan = roof("k_scan_tiles_ws (pack + seed scan / index probe)", "k_scan_tiles", scan_ms, scan_bytes, model_scan,
+                  "filter tier: %s. With the filter in shared memory the kernel is bound by the integer ALU pipe (80 %% busy, "
+                  "profiles/r01_ncu_k_scan_tiles_v11_5Mbp.txt); with it in L2/HBM by the latency of the block and key-bucket "
+                  "loads (long scoreboard, profiles/r02_ncu_k_scan_tiles_*_3Gbp.txt)" % tier)
+    k_ext = roof("k_extend_greedy (overlap extension)" if not EXHAUSTIVE else "k_extend_exhaustive_nodes (overlap extension)",
+                 "k_extend_greedy" if not EXHAUSTIVE else "k_extend_exhaustive", ext_ms, ext_bytes, model_ext,
+                 "dependent round trips (entry side, then unitig words) at 20 warps per SM and 15 of 32 threads per "
+                 "instruction (profiles/r02_ncu_k_extend_greedy_*.txt): latency and issue bound, not bandwidth bound")
+    dominant = k_scan if scan_ms >= ext_ms else k_ext
+    roofline = dict(dominant)
+    roofline["note"] = ("frac = necessary bytes of THIS design / kernel time / measured HBM peak; model_frac = the same with "
+                        "SURVEY 8(d)'s bytes (one 32-byte index sector per window the reference examines), which the "
+                        "filter makes unnecessary to move; traffic = DRAM bytes ncu measured for this kernel and graph size")
+    roofline["kernels"] = {"scan": k_scan, "extend": k_ext}
+    roofline["reference_model_per_read"] = model
+    roofline["reference_model_source"] = model_src
+    cfg = workload_config(args)
     line = {
         "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms[2] / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "genome_bp": args.genome, "k": K, "errors": ERRORS, "effort": EFFORT,
-                   "read_len": READ_LEN, "reads_per_gpu_per_step": n_reads, "unitigs": stats["unitigs"],
-                   "border_keys": stats["keys"], "index_bytes": stats["device_bytes"],
-                   "l2": "inputs (1.5 GB of read characters per step) exceed L2; no flush needed",
-                   "e2e_batch_reads": B, "parallelism": "reads sharded across GPUs, index replicated",
-                   "rank0_numa_binding": numa},
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": cfg,
+        "index": {"unitigs": stats["unitigs"], "border_keys": stats["keys"], "bytes": stats["device_bytes"],
+                  "build_s": index_build_s, "repeat_copies": int(graph.n_repeat_copies)},
+        "e2e_batch_reads": B, "rank0_numa_binding": numa,
         "bases_per_s": value * READ_LEN,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": e2e_forms[e2e_best]["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": e2e_forms[e2e_best]["d2h_bytes_per_step"], "ms_per_step": 1e3 * e2e_s_best / steps,
                 "upload": e2e_best, "forms": e2e_forms},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_scan_tiles_ws (pack + seed scan / index probe)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                     "windows_per_read": w_per_read, "windows_source": w_src, "kernel_ms": scan_ms,
-                     "note": ROOFLINE_NOTE % (stats["device_bytes"] / 1e6)},
-        "kernel_ms": {"pack_scan": scan_ms, "extend": dev_ms[1] / steps},
-        "packed_input": {"value": world * n_reads * steps / (dev_pk[2] / 1e3), "unit": "reads/s",
-                         "kernel_ms": {"scan": dev_pk[0] / steps, "extend": dev_pk[1] / steps},
+        "roofline": roofline,
+        "kernel_ms_per_pass": {"pack_scan": scan_ms, "extend": ext_ms, "whole": dev_ms[2] / per_pass},
+        "timed_region_s": {"resident_wall": t_res1 - t_res0, "resident_device": dev_ms[2] / 1e3},
+        "packed_input": {"value": world * n_reads * per_pass / (dev_pk[2] / 1e3), "unit": "reads/s",
+                         "kernel_ms_per_pass": {"scan": dev_pk[0] / per_pass, "extend": dev_pk[1] / per_pass},
                          "what": "same resident leg with the reads in HBM as the 2-bit stream of a packed upload"},
-        "wall_ms_per_step_resident": 1e3 * (t_res1 - t_res0) / steps,
-        "outcome": {"scope": "all ranks, per step", "reads": counters["reads"] // steps, "aligned": counters["aligned"] // steps,
-                    "not_aligned": counters["not_aligned"] // steps, "no_overlap": counters["no_overlap"] // steps,
-                    "mapped_e2e_last_step": mapped_e2e},
-        "index_build_s": index_build_s,
+        "outcome": {"scope": "all ranks, per pass", "reads": counters["reads"] // per_pass, "aligned": counters["aligned"] // per_pass,
+                    "not_aligned": counters["not_aligned"] // per_pass, "no_overlap": counters["no_overlap"] // per_pass,
+                    "filter_passes_per_read": verified_per_read, "mapped_e2e_last_pass": mapped_e2e},
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libbgreat_b200.so")
 
 BGR_C_COUNT = 8
-COUNTER_NAMES = ["reads", "aligned", "not_aligned", "no_overlap", "overlaps", "windows"]
+COUNTER_NAMES = ["reads", "aligned", "not_aligned", "no_overlap", "overlaps", "windows", "verified"]
 
 MODE_GREEDY, MODE_EXHAUSTIVE, MODE_GREEDY_PATH, MODE_EXHAUSTIVE_PATH = 0, 1, 2, 3
 F_MAPPED, F_OVERLAP_FOUND, F_RC = 0x01, 0x02, 0x04

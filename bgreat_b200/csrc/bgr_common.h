@@ -96,7 +96,7 @@ struct BlobHeader {
     u64 total_bytes;
     u64 n_bloom;  // words of the Bloom filter
     u64 off_bloom;
-    u32 bloom_two_hashes;  // 0: word and bit positions from one 32-bit hash, 1: from two
+    u32 bloom_mode;  // BLOOM_SMEM_1HASH / BLOOM_WORDS_2HASH / BLOOM_MINIMIZER
     u32 pad;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
@@ -221,29 +221,92 @@ BGR_HD u32 bloom_word_of(u32 h1, u32 n_bloom) {
     return (u32)(((u64)h1 * (u64)n_bloom) >> 32);
 #endif
 }
-// word index and bit pattern of a canonical key (the index builders; km1 = k-1)
+// Filter modes (BlobHeader::bloom_mode):
+//   BLOOM_SMEM_1HASH  small indexes: <= 32768 words, copied into shared memory by every CTA of the scan; word and
+//                     bit pattern from one hash
+//   BLOOM_WORDS_2HASH large indexes, any k: one 32-bit word per probe somewhere in a filter of up to 64 MB, word
+//                     from one hash, pattern from another: one random L2 sector per WINDOW
+//   BLOOM_MINIMIZER   large indexes, k = 31: the filter is an array of 64-bit blocks and a (k-1)-mer's block is
+//                     chosen by its MINIMIZER -- the smallest hash among its 15 16-mers (hash symmetric in a
+//                     16-mer and its reverse complement). Consecutive windows of a read mostly share their
+//                     minimizer, so the scan fetches a block once per run of ~8 windows instead of once per window
+//                     (the L2 sector rate was what bound the scan on large indexes: 1.6 G sectors per 10 M reads,
+//                     profiles/r01_ncu_k_scan_tiles_v9_1Gbp.txt). Inside the block a key sets 3 of 64 bits, chosen
+//                     by bloom_h2 of the whole (k-1)-mer.
+enum { BLOOM_SMEM_1HASH = 0, BLOOM_WORDS_2HASH = 1, BLOOM_MINIMIZER = 2 };
+static const u32 MM_M = 16;       // minimizer length: a 16-mer is one 32-bit word
+static const u32 MM_KM1 = 30;     // the (k-1) the minimizer mode is built for
+static const u32 MM_W = MM_KM1 - MM_M + 1;  // 16-mers per (k-1)-mer
+// hash of a 16-mer s and its reverse complement r (symmetric: both strands of a (k-1)-mer see the same values).
+// Multiply-adds only (the scan's integer ALU pipe is the busy one). The product term matters: s + r alone takes
+// few distinct values for a word and its reversed complement, and a filter addressed by it had a third of its
+// blocks empty and 31 % false positives.
+BGR_HD u32 mm_hash(u32 s, u32 r) { return (s * r) * 0x9E3779B1u + s * 0x85EBCA77u + r * 0x85EBCA77u; }
+// block of a (k-1)-mer whose smallest 16-mer hash is hmin (the multiplication spreads the small values a
+// minimum takes over the whole range)
+BGR_HD u32 mm_block(u32 hmin, u32 n_blocks) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(hmin * 0x85EBCA77u, n_blocks);
+#else
+    return (u32)(((u64)(u32)(hmin * 0x85EBCA77u) * (u64)n_blocks) >> 32);
+#endif
+}
+// pattern i: three distinct bits of a 64-bit block
+BGR_HD u64 bloom_pattern64(u32 i) {
+    u32 r = (i + 1) * 0x9E3779B1u;
+    r ^= r >> 16;
+    r *= 0x85EBCA6Bu;
+    r ^= r >> 13;
+    const u32 b0 = r & 63;
+    const u32 b1 = (b0 + 1 + ((r >> 6) & 1023) % 63) & 63;
+    const u32 lo = b0 < b1 ? b0 : b1, hi = b0 < b1 ? b1 : b0;
+    u32 b2 = ((r >> 16) & 1023) % 62;
+    if (b2 >= lo) ++b2;
+    if (b2 >= hi) ++b2;
+    return (1ull << b0) | (1ull << b1) | (1ull << b2);
+}
+// smallest 16-mer hash of a 30-mer code
+BGR_HD u32 mm_min_hash(u64 key) {
+    u32 best = 0xFFFFFFFFu;
+    for (u32 i = 0; i < MM_W; ++i) {
+        const u32 sft = 2 * (MM_W - 1 - i);
+        const u32 s = (u32)(key >> sft);
+        const u32 r = (u32)rcb((u64)s, MM_M);
+        const u32 h = mm_hash(s, r);
+        best = h < best ? h : best;
+    }
+    return best;
+}
+
+// word index and bit pattern of a canonical key (the index builders; km1 = k-1): word modes
 BGR_HD void bloom_slot(u64 key, u32 km1, bool two_hashes, u32 n_bloom, u32& word, u32& pattern) {
     const u64 r = rcb(key, km1);
     const u32 h1 = bloom_h1(key, r);
     word = bloom_word_of(h1, n_bloom);
     pattern = bloom_pattern(bloom_pidx(two_hashes ? bloom_h2(key, r) : h1));
 }
-// number of filter words for n_keys keys (power of two not required)
-inline u64 bloom_words_for(u64 n_keys, bool& two_hashes) {
-    if (n_keys <= 4ull * BLOOM_SMEM_WORDS) {  // shared-memory tier: <= 4 keys per word
-        two_hashes = false;
+// block index and bit pattern of a canonical 30-mer: minimizer mode (n_blocks = n_bloom / 2)
+BGR_HD void bloom_slot_mm(u64 key, u32 n_blocks, u32& block, u64& pattern) {
+    block = mm_block(mm_min_hash(key), n_blocks);
+    pattern = bloom_pattern64(bloom_pidx(bloom_h2(key, rcb(key, MM_KM1))));
+}
+// filter layout for n_keys keys of k-mers: mode and number of 32-bit words (power of two not required)
+inline u64 bloom_layout(u64 n_keys, u32 k, u32& mode) {
+    bool force_global = false;
+    if (const char* e = getenv("BGR_BLOOM")) force_global = e[0] == 'g';  // test hook: "global" = the large-index tier
+    if (n_keys <= 4ull * BLOOM_SMEM_WORDS && !force_global) {  // shared-memory tier: <= 4 keys per word
+        mode = BLOOM_SMEM_1HASH;
         u64 w = 4 * n_keys;
         if (w < 1024) w = 1024;
         if (w > BLOOM_SMEM_WORDS) w = BLOOM_SMEM_WORDS;
         return w;
     }
-    // global tier: 16 bytes per key while that stays within the cap, never below 2/3 byte per key (about 8 %
-    // false positives). The cap is what stays L2-resident next to the read stream: the B200's 126 MB L2
-    // is two partitions that each hold their own copy of read-shared lines, so a 64 MB filter already
-    // misses 40 % of its probes (profiles/r01_ncu_k_scan_tiles_v5_1Gbp.txt) while 32 MB does not.
-    two_hashes = true;
+    // global tier: 16 bytes per key while that stays within the cap, never below 2/3 byte per key. The cap is
+    // what stays L2-resident next to the read stream: the B200's 126 MB L2 is two partitions that each hold
+    // their own copy of read-shared lines (profiles/r01_ncu_k_scan_tiles_v5_1Gbp.txt).
+    mode = (k - 1 == MM_KM1) ? BLOOM_MINIMIZER : BLOOM_WORDS_2HASH;
     u64 cap_mb = 32;  // BGR_BLOOM_MB: experiment hook
-    if (n_keys > (20ull << 20)) cap_mb = 64;  // beyond ~20 M keys the false positives cost more than the misses (3 Gbp: 64 MB wins)
+    if (n_keys > (20ull << 20)) cap_mb = 64;  // beyond ~20 M keys the false positives cost more than the misses
     if (const char* e = getenv("BGR_BLOOM_MB")) {
         const long v = atol(e);
         if (v > 0) cap_mb = (u64)v;
@@ -252,7 +315,8 @@ inline u64 bloom_words_for(u64 n_keys, bool& two_hashes) {
     const u64 cap_words = cap_mb << 18;
     if (w > cap_words) w = cap_words;
     if (w < n_keys / 6) w = n_keys / 6;
-    return w;
+    if (w < 1024) w = 1024;
+    return (w + 1) & ~1ull;  // whole 64-bit blocks
 }
 
 // word offset of read r's packed words inside a batch whose reads are concatenated characters:

@@ -27,7 +27,7 @@ struct DevIndex {
     u64 n_buckets;
     const u32* bloom;
     u32 n_bloom;
-    u32 bloom_two_hashes;
+    u32 bloom_mode;  // BLOOM_* (bgr_common.h)
     u32 k;
 };
 

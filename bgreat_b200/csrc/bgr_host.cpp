@@ -267,15 +267,9 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
     h.off_entries = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
     h.off_meta = align_up(h.off_entries + n_buckets * 4 * sizeof(Entry));
     h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
-    bool two_hashes = false;
-    h.n_bloom = bloom_words_for(n_keys, two_hashes);
-    if (const char* e = getenv("BGR_BLOOM")) {  // test hook: force the large-index (global, two-hash) tier
-        if (!strcmp(e, "global")) {
-            two_hashes = true;
-            h.n_bloom = std::max<u64>(1024, 4 * n_keys);
-        }
-    }
-    h.bloom_two_hashes = two_hashes ? 1u : 0u;
+    u32 bloom_mode = 0;
+    h.n_bloom = bloom_layout(n_keys, k, bloom_mode);
+    h.bloom_mode = bloom_mode;
     if (h.n_bloom >= 0xFFFFFFFFull) {
         err = "too many distinct border k-mers for the 32-bit filter hash";
         return BGR_ERR_LIMIT;
@@ -313,9 +307,16 @@ int build_index_blob(const char* seqs, const uint64_t* off, uint32_t n, uint32_t
         memcpy(B, &h, sizeof h);
         u32* bloom = (u32*)(B + h.off_bloom);
         for (u64 i = 0; i < n_keys; ++i) {
-            u32 word, pattern;
-            bloom_slot(keys[i], k - 1, two_hashes, (u32)h.n_bloom, word, pattern);
-            bloom[word] |= pattern;
+            if (bloom_mode == BLOOM_MINIMIZER) {
+                u32 block;
+                u64 pattern;
+                bloom_slot_mm(keys[i], (u32)(h.n_bloom / 2), block, pattern);
+                ((u64*)bloom)[block] |= pattern;
+            } else {
+                u32 word, pattern;
+                bloom_slot(keys[i], k - 1, bloom_mode == BLOOM_WORDS_2HASH, (u32)h.n_bloom, word, pattern);
+                bloom[word] |= pattern;
+            }
         }
     }
 

@@ -99,7 +99,7 @@ __global__ void k_run_starts(const u32* head, const u32* run_id, u64 n, u32 n_ke
 }
 
 __global__ void k_insert_keys(const u64* skeys, const u32* run_start, u32 n_keys, u64* tkeys, u64 n_buckets, u32* bloom,
-                              u32 n_bloom, u32 two_hashes, u32 km1, u32* slot_of) {
+                              u32 n_bloom, u32 bloom_mode, u32 km1, u32* slot_of) {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_keys) return;
     const u64 key = skeys[run_start[r]];
@@ -118,9 +118,16 @@ __global__ void k_insert_keys(const u64* skeys, const u32* run_start, u32 n_keys
         if (placed) break;
         if (++b == n_buckets) b = 0;
     }
-    u32 word, pattern;
-    bloom_slot(key, km1, two_hashes != 0, n_bloom, word, pattern);
-    atomicOr(&bloom[word], pattern);
+    if (bloom_mode == BLOOM_MINIMIZER) {
+        u32 block;
+        u64 pattern;
+        bloom_slot_mm(key, n_bloom / 2, block, pattern);
+        atomicOr((unsigned long long*)bloom + block, (unsigned long long)pattern);
+    } else {
+        u32 word, pattern;
+        bloom_slot(key, km1, bloom_mode == BLOOM_WORDS_2HASH, n_bloom, word, pattern);
+        atomicOr(&bloom[word], pattern);
+    }
 }
 
 // slot of an existing key (every border of an accepted unitig is one)
@@ -334,15 +341,9 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     h.off_entries = align_up(h.off_keys + n_buckets * 4 * sizeof(u64));
     h.off_meta = align_up(h.off_entries + n_buckets * 4 * sizeof(Entry));
     h.off_pool = align_up(h.off_meta + (nu + 1) * sizeof(UnitigMeta));
-    bool two_hashes = false;
-    h.n_bloom = bloom_words_for(n_keys, two_hashes);
-    if (const char* e = getenv("BGR_BLOOM")) {  // test hook: force the large-index (global, two-hash) tier
-        if (!strcmp(e, "global")) {
-            two_hashes = true;
-            h.n_bloom = std::max<u64>(1024, 4 * (u64)n_keys);
-        }
-    }
-    h.bloom_two_hashes = two_hashes ? 1u : 0u;
+    u32 bloom_mode = 0;
+    h.n_bloom = bloom_layout(n_keys, k, bloom_mode);
+    h.bloom_mode = bloom_mode;
     if (h.n_bloom >= 0xFFFFFFFFull) {
         err = "too many distinct border k-mers for the 32-bit filter hash";
         return BGR_ERR_LIMIT;
@@ -358,7 +359,7 @@ int build_index_on_device(const char* seqs, const uint64_t* off, uint32_t n, uin
     GCK(cudaMemcpy(Bp, &h, sizeof h, cudaMemcpyHostToDevice));
     if (n_keys) {
         k_insert_keys<<<grid_for(n_keys, B), B>>>(d_skeys.as<u64>(), d_runstart.as<u32>(), n_keys, (u64*)(Bp + h.off_keys),
-                                                   n_buckets, (u32*)(Bp + h.off_bloom), (u32)h.n_bloom, h.bloom_two_hashes,
+                                                   n_buckets, (u32*)(Bp + h.off_bloom), (u32)h.n_bloom, h.bloom_mode,
                                                    k - 1, d_slot.as<u32>());
         ++*launches;
     }

@@ -140,9 +140,11 @@ int set_index_from_device_blob(bgr_ctx* ctx) {
     ctx->ix.n_buckets = h.n_buckets;
     ctx->ix.bloom = (const u32*)(B + h.off_bloom);
     ctx->ix.n_bloom = (u32)h.n_bloom;
-    ctx->ix.bloom_two_hashes = h.bloom_two_hashes;
-    if (!h.bloom_two_hashes && h.n_bloom > BLOOM_SMEM_WORDS)
+    ctx->ix.bloom_mode = h.bloom_mode;
+    if (h.bloom_mode == BLOOM_SMEM_1HASH && h.n_bloom > BLOOM_SMEM_WORDS)
         return fail(ctx, BGR_ERR_FORMAT, "index blob: single-hash filter larger than the shared-memory tier");
+    if (h.bloom_mode > BLOOM_MINIMIZER || (h.bloom_mode == BLOOM_MINIMIZER) != (h.bloom_mode != BLOOM_SMEM_1HASH && h.k - 1 == MM_KM1))
+        return fail(ctx, BGR_ERR_FORMAT, "index blob: filter mode does not match k");
     ctx->ix.k = h.k;
     ctx->has_index = true;
     return BGR_OK;
@@ -699,7 +701,7 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
         BatchArgs a = make_args(s);
         if (s.tile_r >= 2) {
             // tile scan: one persistent CTA per SM; the Bloom filter rides in shared memory when it is small
-            const bool bloom_smem = !ctx->ix.bloom_two_hashes;
+            const bool bloom_smem = ctx->ix.bloom_mode == BLOOM_SMEM_1HASH;
             const size_t smem = ctx->scan_ws ? tile_ws_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB)
                                              : tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
             const u32 ntiles = (s.n + s.tile_r - 1) / s.tile_r;

@@ -428,16 +428,108 @@ BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, const u32* pat, u32 km1_rt,
     return count >= 32 ? hits : hits & ((1u << count) - 1);
 }
 
-// The windows that passed the filter, checked against the key table: the returned mask is exact.
+// The same test against the minimizer-addressed filter (BLOOM_MINIMIZER, bgr_common.h; k-1 = 30): the block of a
+// window is chosen by the smallest hash among its 15 16-mers, and is looked at only when it differs from the
+// previous window's (a run of ~8 windows shares it). The hash of the 16-mer that enters with a window is a few
+// multiply-adds on words the rolling codes already hold (its code = the low word of the forward code, its reverse
+// complement = the top word of the reverse-complement code); the minimum over the window comes from the van Herk
+// scheme over blocks of 15 offsets -- suffix minima of the block a window starts in, a running prefix minimum of
+// the block it ends in: three min operations per window. Everything is unrolled, the arrays live in registers.
+// Measured, 10 M reads: 3.7 ms at 100 Mbp and 4.4 ms at 1 Gbp against 5.7 / 5.9 ms for the word filter (one L2 sector
+// per window); at 3 Gbp (40 M keys, 64 MB of blocks, more than L2 keeps) 6.2 against 6.0 ms: there the loads of a
+// chunk -- four or five blocks, one or two key buckets -- are HBM round trips (profiles/r02_ncu_k_scan_tiles_d_3Gbp.txt).
+// Two variants were measured at 3 Gbp and lost: requesting a chunk's blocks ahead of the test (a first pass that only
+// computes the minimizers, prefetches and lists the block numbers: 6.8 ms, twice the L2 sectors), and a bit map over
+// a sparser block array so that only occupied blocks are fetched (8.8 ms: two dependent loads per run of windows).
+// blocks: the filter as 64-bit blocks; pat: bloom_pattern64 table.
+BGR_HD u32 scan_chunk_mm(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0, u64 w1, u32 count) {
+    const u32 sh = 64 - 2 * MM_KM1, top = 2 * (MM_KM1 - 1);
+    const u64 mask = ~0ull >> sh;
+    u64 num = w0 >> sh;
+    u64 rc = rcb(num, MM_KM1);
+    const u64 inc = (w0 << (2 * MM_KM1)) | (w1 >> sh);  // the bases that follow the first window
+    // 16-mers at offsets 0..13 lie inside w0: codes are slices of w0, their reverse complements slices of rc64(w0)
+    const u64 R = rc64(w0);
+    u32 S[MM_W], hb[MM_W];
+#pragma unroll
+    for (u32 i = 0; i + 1 < MM_W; ++i) S[i] = mm_hash((u32)(w0 >> (32 - 2 * i)), (u32)(R >> (2 * i)));
+    u32 P = 0, Q = 0xFFFFFFFFu, hits = 0, cur = 0xFFFFFFFFu;
+    u64 blk = 0;
+#pragma unroll
+    for (u32 j = 0; j < 32; ++j) {
+        const u32 h = mm_hash((u32)num, (u32)(rc >> (2 * (MM_KM1 - MM_M))));  // the 16-mer at offset j + 14
+        u32 wmin;
+        if (j == 0) {
+            S[MM_W - 1] = h;
+#pragma unroll
+            for (int i = (int)MM_W - 2; i >= 0; --i) S[i] = S[i] < S[i + 1] ? S[i] : S[i + 1];
+            wmin = S[0];
+        } else if (j <= MM_W) {  // offsets 15..29
+            hb[j - 1] = h;
+            P = (j == 1 || h < P) ? h : P;
+            wmin = (j < MM_W) ? (S[j] < P ? S[j] : P) : P;
+            if (j == MM_W) {  // the block is complete: its suffix minima replace the first block's
+                S[MM_W - 1] = hb[MM_W - 1];
+#pragma unroll
+                for (int i = (int)MM_W - 2; i >= 0; --i) S[i] = hb[i] < S[i + 1] ? hb[i] : S[i + 1];
+            }
+        } else {  // offsets 30..45
+            if (j <= 2 * MM_W) P = (j == MM_W + 1 || h < P) ? h : P;
+            if (j >= MM_W + 2) Q = h < Q ? h : Q;  // offsets 31..: the last window starts one past a block start
+            wmin = (j < 2 * MM_W) ? (S[j - MM_W] < P ? S[j - MM_W] : P) : (j == 2 * MM_W ? P : Q);
+        }
+        const u32 b = mm_block(wmin, n_blocks);
+        if (b != cur) {
+            cur = b;
+#if defined(__CUDA_ARCH__)
+            blk = __ldg((const unsigned long long*)blocks + b);
+#else
+            blk = blocks[b];
+#endif
+        }
+        const u64 m = pat[bloom_pidx(bloom_h2(num, rc))];
+        hits |= ((blk & m) == m ? 1u : 0u) << j;
+        const u64 nb = (inc >> (62 - 2 * j)) & 3;
+        num = ((num << 2) | nb) & mask;
+        rc = (rc >> 2) | ((3 - nb) << top);
+    }
+    return count >= 32 ? hits : hits & ((1u << count) - 1);
+}
+
+// The windows that passed the filter, checked against the key table: the returned mask is exact. The home
+// buckets of up to NB survivors are requested together (a chunk has one or two on average, and on a large index
+// each is a random sector in HBM: waiting for them one after the other costs a round trip each).
+template <int NB>
 BGR_HD u32 verify_chunk(const DevIndex& ix, u64 w0, u64 w1, u32 hits) {
     const u32 km1 = ix.k - 1, sh = 64 - 2 * km1;
     u32 m = hits;
     while (m) {
-        const u32 j = (u32)BGR_FFS(m) - 1;
-        m &= m - 1;
-        const u64 x = (j ? ((w0 << (2 * j)) | (w1 >> (64 - 2 * j))) : w0) >> sh;
-        const u64 rc = rcb(x, km1);
-        if (!index_has(ix, x < rc ? x : rc)) hits &= ~(1u << j);
+        u32 jj[NB];
+        u64 key[NB];
+        u64x4 v[NB];
+        int n = 0;
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            if (m) {
+                const u32 j = (u32)BGR_FFS(m) - 1;
+                m &= m - 1;
+                const u64 x = (j ? ((w0 << (2 * j)) | (w1 >> (64 - 2 * j))) : w0) >> sh;
+                const u64 rc = rcb(x, km1);
+                jj[t] = j;
+                key[t] = x < rc ? x : rc;
+                v[t] = ld_bucket(ix.keys + bucket_of(key[t], ix.n_buckets) * 4);
+                n = t + 1;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            if (t < n) {
+                bool found = v[t].a == key[t] || v[t].b == key[t] || v[t].c == key[t] || v[t].d == key[t];
+                // a full home bucket: the key may have overflowed into a later one
+                if (!found && v[t].d != EMPTY_KEY) found = index_has(ix, key[t]);
+                if (!found) hits &= ~(1u << jj[t]);
+            }
+        }
     }
     return hits;
 }
@@ -482,7 +574,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, 
 
 struct TileSmem {
     u32* bloom;
-    u32* pat;  // BLOOM_PATTERNS filter bit patterns
+    u32* pat;  // BLOOM_PATTERNS filter bit patterns (64-bit ones in minimizer mode)
     unsigned char* chars[2];
     u64* off;     // ST_MAX_R + 2
     u32* prefix;  // ST_MAX_R + 2
@@ -492,7 +584,7 @@ struct TileSmem {
 };
 __host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb) {
     size_t b = ((size_t)bloom_words_in_smem * 4 + 127) & ~(size_t)127;
-    b += BLOOM_PATTERNS * 4;
+    b += BLOOM_PATTERNS * 8;
     b += 2 * ((size_t)tile_cb + ST_CHAR_SLACK);
     b += (ST_MAX_R + 2) * 8 + 2 * (ST_MAX_R + 2) * 4 + 2 * 8 + 32 * 4;
     return b + 128;
@@ -536,10 +628,13 @@ __device__ __forceinline__ u32 tile_chunk(const DevIndex& ix, const BatchArgs& a
         gF[nw + 2] = 0;
     }
     const u32 count = min(32u, rnwin - 32 * l);
-    // the shared-memory tier is the single-hash tier (bloom_words_for)
-    u32 hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, pat, km1, w0, w1, count);
+    // the shared-memory tier is the single-hash tier; large indexes of 31-mers have the minimizer filter, other
+    // k the two-hash word filter (bloom_layout)
+    u32 hits;
+    if (!BLOOM_SMEM && KM1S == MM_KM1) hits = scan_chunk_mm((const u64*)bloom, ix.n_bloom / 2, (const u64*)pat, w0, w1, count);
+    else hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, pat, km1, w0, w1, count);
     const u32 passed = (u32)__popc(hits);
-    hits = verify_chunk(ix, w0, w1, hits);
+    hits = verify_chunk<1>(ix, w0, w1, hits);
     a.H1[wb + l] = hits;
     const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
     if (fl) atomicOr(&s_flags[rd], fl);
@@ -559,7 +654,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
         S.bloom = (u32*)q;
         q += BLOOM_SMEM ? (((size_t)ix.n_bloom * 4 + 127) & ~(size_t)127) : 0;
         S.pat = (u32*)q;
-        q += BLOOM_PATTERNS * 4;
+        q += BLOOM_PATTERNS * 8;
         S.chars[0] = q;
         q += a.tile_cb + ST_CHAR_SLACK;
         S.chars[1] = q;
@@ -580,7 +675,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles(DevIndex ix, Batch
     const u32 km1 = KM1S ? KM1S : ix.k - 1;
     const bool exhaustive = a.mode != BGR_MODE_GREEDY;
     const u32* bloom = BLOOM_SMEM ? S.bloom : ix.bloom;
-    for (u32 i = threadIdx.x; i < BLOOM_PATTERNS; i += ST_THREADS) S.pat[i] = bloom_pattern(i);
+    for (u32 i = threadIdx.x; i < BLOOM_PATTERNS; i += ST_THREADS) {
+        if (!BLOOM_SMEM && KM1S == MM_KM1) ((u64*)S.pat)[i] = bloom_pattern64(i);
+        else S.pat[i] = bloom_pattern(i);
+    }
 
     u64 policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -783,7 +881,7 @@ static const u32 WS_WORKERS = ST_THREADS - 32;
 
 __host__ __device__ inline size_t tile_ws_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb) {
     size_t b = ((size_t)bloom_words_in_smem * 4 + 127) & ~(size_t)127;
-    b += BLOOM_PATTERNS * 4;
+    b += BLOOM_PATTERNS * 8;
     b += 2 * ((size_t)tile_cb + ST_CHAR_SLACK);
     b += 2 * ((sizeof(TileMeta) + 15) & ~(size_t)15) + 6 * 8;
     return b + 128;
@@ -805,7 +903,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, Ba
         s_bloom = (u32*)q;
         q += BLOOM_SMEM ? (((size_t)ix.n_bloom * 4 + 127) & ~(size_t)127) : 0;
         s_pat = (u32*)q;
-        q += BLOOM_PATTERNS * 4;
+        q += BLOOM_PATTERNS * 8;
         s_chars[0] = q;
         q += a.tile_cb + ST_CHAR_SLACK;
         s_chars[1] = q;
@@ -823,7 +921,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, Ba
     const u32 km1 = KM1S ? KM1S : ix.k - 1;
     const bool exhaustive = a.mode != BGR_MODE_GREEDY;
     const u32* bloom = BLOOM_SMEM ? s_bloom : ix.bloom;
-    for (u32 i = tid; i < BLOOM_PATTERNS; i += ST_THREADS) s_pat[i] = bloom_pattern(i);
+    for (u32 i = tid; i < BLOOM_PATTERNS; i += ST_THREADS) {
+        if (!BLOOM_SMEM && KM1S == MM_KM1) ((u64*)s_pat)[i] = bloom_pattern64(i);
+        else s_pat[i] = bloom_pattern(i);
+    }
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bar_tma[b], 1);

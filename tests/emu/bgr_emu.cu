@@ -40,7 +40,7 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     ix.k = h.k;
     ix.bloom = (const u32*)(B + h.off_bloom);
     ix.n_bloom = (u32)h.n_bloom;
-    ix.bloom_two_hashes = h.bloom_two_hashes;
+    ix.bloom_mode = h.bloom_mode;
 
     const u64 chars = off[n];
     const u64 words = batch_words(chars, n);
@@ -92,6 +92,8 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     a.pk = packed ? pk.data() : nullptr;
     std::vector<u32> pat(BLOOM_PATTERNS);
     for (u32 i = 0; i < BLOOM_PATTERNS; ++i) pat[i] = bloom_pattern(i);
+    std::vector<u64> pat64(BLOOM_PATTERNS);
+    for (u32 i = 0; i < BLOOM_PATTERNS; ++i) pat64[i] = bloom_pattern64(i);
     for (u32 r = 0; r < n; ++r) {
         const u64 o = off[r];
         const u32 len = (u32)(off[r + 1] - o);
@@ -123,19 +125,37 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
             const u32 count = nwin_t - 32 * l < 32u ? nwin_t - 32 * l : 32u;
             // both the k-1 = 30 specialisation and the run-time form, like the kernel's dispatch
             u32 hits;
-            if (ix.bloom_two_hashes)
+            if (ix.bloom_mode == BLOOM_MINIMIZER) {
+                hits = scan_chunk_mm((const u64*)ix.bloom, ix.n_bloom / 2, pat64.data(), w0, w1, count);
+                // window by window from the definition (bloom_slot_mm of the window's canonical code)
+                u32 want = 0;
+                for (u32 j = 0; j < count; ++j) {
+                    const u64 x = (j ? ((w0 << (2 * j)) | (w1 >> (64 - 2 * j))) : w0) >> (64 - 2 * km1);
+                    const u64 rcx = rcb(x, km1);
+                    u32 block;
+                    u64 pattern;
+                    bloom_slot_mm(x < rcx ? x : rcx, ix.n_bloom / 2, block, pattern);
+                    u32 block2;
+                    u64 pattern2;
+                    bloom_slot_mm(x < rcx ? rcx : x, ix.n_bloom / 2, block2, pattern2);  // strand symmetry
+                    if (block2 != block || pattern2 != pattern) return 1004;
+                    if ((((const u64*)ix.bloom)[block] & pattern) == pattern) want |= 1u << j;
+                }
+                if (want != hits) return 1003;
+            } else if (ix.bloom_mode == BLOOM_WORDS_2HASH)
                 hits = km1 == 30 ? scan_chunk<true, 30>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
                                  : scan_chunk<true, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
             else
                 hits = km1 == 30 ? scan_chunk<false, 30>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
                                  : scan_chunk<false, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
-            if (km1 == 30) {  // the two forms must agree
-                const u32 h0 = ix.bloom_two_hashes ? scan_chunk<true, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
-                                                   : scan_chunk<false, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
+            if (km1 == 30 && ix.bloom_mode != BLOOM_MINIMIZER) {  // the two forms must agree
+                const u32 h0 = ix.bloom_mode == BLOOM_WORDS_2HASH
+                                   ? scan_chunk<true, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count)
+                                   : scan_chunk<false, 0>(ix.bloom, ix.n_bloom, pat.data(), km1, w0, w1, count);
                 if (h0 != hits) return 1003;
             }
             scnt.c[BGR_C_VERIFIED] += (u64)__builtin_popcount(hits);
-            hits = verify_chunk(ix, w0, w1, hits);
+            hits = (r & 1) ? verify_chunk<1>(ix, w0, w1, hits) : verify_chunk<2>(ix, w0, w1, hits);
             a.H1[wb + l] = hits;
             tile_bad |= bad != 0;
             tile_hit |= hits != 0;

@@ -86,8 +86,8 @@ def emu_map(unitigs, k, reads, mode, errors, effort, scratch_ints=64, how=0):
         o = int(res[i, 1])
         out.append((bool(fl & 2), bool(fl & 4), [int(x) for x in pool[o:o + ln]]))
         flags.append(fl)
-    names = ["reads", "aligned", "not_aligned", "no_overlap", "overlaps", "windows"]
-    return out, dict(zip(names, [int(c) for c in counters[:6]])), flags, bool(ovf.value)
+    names = ["reads", "aligned", "not_aligned", "no_overlap", "overlaps", "windows", "verified"]
+    return out, dict(zip(names, [int(c) for c in counters[:7]])), flags, bool(ovf.value)
 
 
 def parse_reads(path, k, fastq=False, chunk=10000, threads=0, range_bytes=1 << 20, min_slice=4096):

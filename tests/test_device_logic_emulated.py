@@ -49,6 +49,29 @@ def test_emulated_device_code_matches_oracle_fuzz(seed):
             assert counters[name] == wc[name]
 
 
+@pytest.mark.parametrize("k,seed", [(31, 1), (31, 2), (31, 3), (21, 4), (17, 5), (12, 6)])
+def test_emulated_large_index_filter_tiers(k, seed, monkeypatch):
+    """The filter of large indexes (forced here on a small graph): minimizer-addressed 64-bit blocks for k = 31,
+    two-hash words for any other k. The emulator also checks every chunk's filter answer against the filter's
+    definition, window by window (return code 1003 / 1004 otherwise)."""
+    monkeypatch.setenv("BGR_BLOOM", "global")
+    rng = random.Random(seed)
+    unitigs, haps = S.make_graph(rng, k, genome_len=30000, mean_unitig=70, n_variants=200)
+    reads = S.make_reads(rng, haps, 1500, 150, sub_rate=0.01, n_rate=0.0005)
+    reads += S.make_reads(rng, haps, 60, 40, sub_rate=0.02) + S.make_reads(rng, haps, 40, 333, sub_rate=0.01)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        o = O.Oracle(k, 2, 2)
+        o.index_unitigs(unitigs)
+        want = [o.align(r, mode) for r in reads]
+        for how in (0, 1):  # character and packed upload forms of the tile scan
+            got, counters, _, ovf = E.emu_map(unitigs, k, reads, mode, 2, 2, scratch_ints=4096, how=how)
+            assert not ovf
+            assert got == want
+            # the filter does filter: the windows it lets through are the true borders (a few per cent of all
+            # windows in this graph) plus a small share of false positives
+            assert counters["verified"] < 0.15 * counters["windows"]
+
+
 def test_scratch_overflow_is_flagged_not_truncated():
     rng = random.Random(5)
     unitigs, haps = S.make_graph(rng, 10, genome_len=600, mean_unitig=2, n_variants=0)
@@ -176,6 +199,7 @@ def test_emulated_packed_upload_long_reads_with_n(k, rl):
     ref, cref, _, _ = E.emu_map(unitigs, k, reads, 0, 2, 2, scratch_ints=4096, how=0)
     for how in (1, 3):
         got, cnt, _, _ = E.emu_map(unitigs, k, reads, 0, 2, 2, scratch_ints=4096, how=how)
+        cnt["verified"] = cref["verified"]  # instrumentation of the filter: the general scan form has none
         assert got == ref and cnt == cref
     assert sum(1 for _, _, p in ref if p) > 20
 

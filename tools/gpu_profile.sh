@@ -9,5 +9,5 @@ ncu --set full --clock-control none --import-source on -k regex:$scan -s 3 -c 1 
 ncu --set full --clock-control none --import-source on -k regex:$ext -s 3 -c 1 -f -o $out/prof_ext_$tag \
     python tools/tune.py 10000000 $genome $mode > $out/prof_ext_$tag.log 2>&1
 python tools/ncu_summary.py $out/prof_scan_$tag.ncu-rep $out/ncu_${scan}_$tag.txt --traffic-key "k_scan_tiles@$genome" --traffic-json $out/roofline_traffic.json
-python tools/ncu_summary.py $out/prof_ext_$tag.ncu-rep $out/ncu_${ext}_$tag.txt
+python tools/ncu_summary.py $out/prof_ext_$tag.ncu-rep $out/ncu_${ext}_$tag.txt --traffic-key "$ext@$genome" --traffic-json $out/roofline_traffic.json
 tail -2 $out/prof_scan_$tag.log
