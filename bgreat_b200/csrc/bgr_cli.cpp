@@ -56,6 +56,7 @@ struct Batch {
     PodBuf<uint64_t> corr;  // -c: corrected reads, 2 bits per base (layout: BGR_CORRECTED_BASE)
     uint64_t pool_used = 0;
     int slot = -1;
+    uint64_t seq = 0;  // position in the input: the writer emits batches in this order
     Batch() {
         pb.set_allocator(pinned_alloc, pinned_free);
         res.alloc = pool.alloc = corr.alloc = pinned_alloc;
@@ -381,11 +382,21 @@ int main(int argc, char** argv) {
                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
     };
     const int n_slots = 2;
-    bgr_ctx* ctx = nullptr;
-    if (bgr_ctx_create(0, n_slots, &ctx) != BGR_OK) {
-        fprintf(stderr, "bgreat: %s\n", bgr_last_error(nullptr));
+    // one context per visible device (reads shard across the GPUs of a box, the index is replicated)
+    int n_dev = 0;
+    if (bgr_device_count(&n_dev) != BGR_OK || n_dev < 1) {
+        fprintf(stderr, "bgreat: %s\n", n_dev < 1 && !*bgr_last_error(nullptr) ? "no CUDA device" : bgr_last_error(nullptr));
         return 1;
     }
+    int n_gpus = n_dev;
+    if (const char* e = getenv("BGR_GPUS")) n_gpus = std::max(1, std::min(16, atoi(e)));
+    std::vector<bgr_ctx*> ctxs((size_t)n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g)
+        if (bgr_ctx_create(g % n_dev, n_slots, &ctxs[g]) != BGR_OK) {
+            fprintf(stderr, "bgreat: %s\n", bgr_last_error(nullptr));
+            return 1;
+        }
+    bgr_ctx* ctx = ctxs[0];
 
     lap("context created");
     // Aligner ctor opens the outputs first (aligner.h:85-86)
@@ -411,6 +422,11 @@ int main(int argc, char** argv) {
             fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
         rc = BGR_OK;
     }
+    for (int g = 1; g < n_gpus; ++g)
+        if (bgr_index_replicate(ctxs[g], ctx) != BGR_OK) {
+            fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctxs[g]));
+            return 1;
+        }
     auto t1 = std::chrono::system_clock::now();
     std::cout << "Indexing in seconds : " << std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count()
               << std::endl;
@@ -424,7 +440,7 @@ int main(int argc, char** argv) {
     params.effort = (uint32_t)o.effort;
     params.flags = correction ? BGR_P_CORRECT : 0u;
 
-    const size_t n_batches = n_slots + 4;
+    const size_t n_batches = (size_t)n_gpus * (n_slots + 1) + 3;
     std::vector<Batch> batches(n_batches);
     Queue<Batch*> free_q, parsed_q, done_q;
     // text per batch: about 100 k reads of 150 bases (measured on 20 M reads: 16-32 MB beats 8 and 64 MB: the
@@ -458,6 +474,7 @@ int main(int argc, char** argv) {
     std::vector<std::unique_ptr<MappedFile>> mapped;
 
     std::thread parser([&] {
+        uint64_t seq = 0;
         for (const std::string& file : files) {
             mapped.emplace_back(new MappedFile());
             MappedFile& mf = *mapped.back();
@@ -475,15 +492,17 @@ int main(int argc, char** argv) {
                 const auto t = now();
                 b->pb.clear();
                 pr.next(b->pb);
+                b->seq = seq++;
                 parse_s += since(t);
                 parsed_q.push(b);  // possibly empty: still flows through so that order is kept
             } while (!pr.done());
             for (int i = 0; i < 3; ++i) reader_phase[i] += pr.phase_s[i];
         }
-        parsed_q.push(nullptr);
+        for (int g = 0; g < n_gpus; ++g) parsed_q.push(nullptr);
     });
 
-    std::thread gpu([&] {
+    std::mutex stat_m;
+    auto gpu_loop = [&](bgr_ctx* ctx) {
         std::deque<Batch*> inflight;
         int next_slot = 0;
         bool input_done = false;
@@ -501,7 +520,10 @@ int main(int argc, char** argv) {
                 exit(1);
             }
             b->pool_used = used;
-            gpu_wait_s += since(t);
+            {
+                std::lock_guard<std::mutex> l(stat_m);
+                gpu_wait_s += since(t);
+            }
             done_q.push(b);
         };
         while (!input_done || !inflight.empty()) {
@@ -546,18 +568,37 @@ int main(int argc, char** argv) {
             }
         }
         done_q.push(nullptr);
-    });
+    };
+    std::vector<std::thread> gpu_threads;
+    for (int g = 0; g < n_gpus; ++g) gpu_threads.emplace_back(gpu_loop, ctxs[g]);
 
-    // writer: this thread and its workers
+    // writer: this thread and its workers; batches leave in input order (a small reorder buffer: the devices
+    // finish in any order)
     bool write_error = false;
     {
         std::vector<size_t> sz(3 * (size_t)threads), at(3 * (size_t)threads);
         WorkerPool pool(threads - 1);
+        std::vector<Batch*> held;
+        uint64_t next_seq = 0;
+        int ended = 0;
         for (;;) {
-            const auto tw = now();
-            Batch* b = done_q.pop();
-            done_wait_s += since(tw);
-            if (!b) break;
+            Batch* b = nullptr;
+            for (size_t i = 0; i < held.size(); ++i)
+                if (held[i]->seq == next_seq) {
+                    b = held[i];
+                    held.erase(held.begin() + (long)i);
+                    break;
+                }
+            if (!b) {
+                if (ended == n_gpus) break;  // every device thread is through and nothing is held back
+                const auto tw = now();
+                Batch* x = done_q.pop();
+                done_wait_s += since(tw);
+                if (!x) ++ended;
+                else held.push_back(x);
+                continue;
+            }
+            ++next_seq;
             const auto t0w = now();
             const size_t n = b->pb.size();
             const unsigned T = (unsigned)std::min<size_t>(threads, n / 4096 + 1);
@@ -589,7 +630,7 @@ int main(int argc, char** argv) {
         }
     }
     parser.join();
-    gpu.join();
+    for (auto& t : gpu_threads) t.join();
     allocator.join();
     lap("mapping done");
     if (verbose) {
@@ -602,8 +643,12 @@ int main(int argc, char** argv) {
     }
     for (const std::string& file : files) std::cout << file << std::endl;
 
-    uint64_t cnt[BGR_C_COUNT];
-    bgr_counters(ctx, cnt);
+    uint64_t cnt[BGR_C_COUNT] = {0};
+    for (bgr_ctx* c : ctxs) {  // the reference's atomic counters (aligner.h:68), summed over the devices
+        uint64_t one[BGR_C_COUNT];
+        bgr_counters(c, one);
+        for (int i = 0; i < BGR_C_COUNT; ++i) cnt[i] += one[i];
+    }
     const unsigned readNumber = (unsigned)cnt[BGR_C_READS], noOverlapRead = (unsigned)cnt[BGR_C_NOOVERLAP],
                    alignedRead = (unsigned)cnt[BGR_C_ALIGNED], notAligned = (unsigned)cnt[BGR_C_NOTALIGNED];
     // aligner.cpp:588-596, same expressions (float arithmetic, -nan on 0/0 included)
@@ -635,7 +680,7 @@ int main(int argc, char** argv) {
     }
     batches.clear();
     mapped.clear();
-    bgr_ctx_destroy(ctx);
+    for (bgr_ctx* c : ctxs) bgr_ctx_destroy(c);
     lap("context destroyed");
     return status;
 }

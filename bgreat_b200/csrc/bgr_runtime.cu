@@ -380,10 +380,17 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
     delete ctx;
 }
 
+int bgr_device_count(int* n) {
+    bgr_ctx* ctx = nullptr;
+    if (!n) return fail(nullptr, BGR_ERR_ARG, "n is null");
+    CK(cudaGetDeviceCount(n));
+    return BGR_OK;
+}
+
 int bgr_host_alloc(size_t bytes, void** out) {
     bgr_ctx* ctx = nullptr;
     if (!out) return fail(nullptr, BGR_ERR_ARG, "out is null");
-    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
     return BGR_OK;
 }
 
@@ -468,6 +475,18 @@ int bgr_index_import_device(bgr_ctx* ctx, const void* dev_src, uint64_t bytes) {
         return fail(ctx, BGR_ERR_FORMAT, "index blob: size mismatch");
     }
     return rc;
+}
+
+int bgr_index_replicate(bgr_ctx* ctx, const bgr_ctx* src) {
+    if (!ctx || !src || ctx == src) return fail(ctx, BGR_ERR_ARG, "bad argument");
+    if (!src->has_index) return fail(ctx, BGR_ERR_NO_INDEX, "source context has no index");
+    const u64 bytes = src->hdr.total_bytes;
+    CK(cudaSetDevice(ctx->device));
+    int rc = drop_index(ctx);
+    if (rc) return rc;
+    CK(cudaMalloc(&ctx->d_blob, bytes));
+    CK(cudaMemcpyPeer(ctx->d_blob, ctx->device, src->d_blob, src->device, bytes));
+    return set_index_from_device_blob(ctx);
 }
 
 int bgr_index_export_host(const bgr_ctx* cctx, void* host_dst, uint64_t bytes) {

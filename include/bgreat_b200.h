@@ -96,7 +96,12 @@ void bgr_ctx_destroy(bgr_ctx* ctx);
 const char* bgr_last_error(const bgr_ctx* ctx);
 int bgr_abi_version(void);
 
-/* pinned host memory for asynchronous transfers (cudaHostAlloc / cudaFreeHost) */
+/* number of CUDA devices this process sees (the reference's parallelism is inside the binary -- coreNumber threads,
+ * aligner.cpp:560-586; here a caller makes one context per device and deals batches to them) */
+int bgr_device_count(int* n);
+
+/* pinned host memory for asynchronous transfers (cudaHostAlloc, portable: usable by the contexts of every device /
+ * cudaFreeHost) */
 int bgr_host_alloc(size_t bytes, void** out);
 void bgr_host_free(void* p);
 
@@ -121,6 +126,10 @@ int bgr_index_export_device(const bgr_ctx* ctx, void* dev_dst, uint64_t bytes);
 int bgr_index_import_device(bgr_ctx* ctx, const void* dev_src, uint64_t bytes);
 int bgr_index_export_host(const bgr_ctx* ctx, void* host_dst, uint64_t bytes);
 int bgr_index_import_host(bgr_ctx* ctx, const void* host_src, uint64_t bytes);
+
+/* The same replication inside one process: dst gets a copy of src's index, device to device (cudaMemcpyPeer: over
+ * NVLink where the devices are peers). dst and src may sit on the same device. */
+int bgr_index_replicate(bgr_ctx* dst, const bgr_ctx* src);
 
 /* On-disk index cache (cf. the reference's unused mphf::save / load, BooPHF.h:927-1005):
  * the flat blob as a file. bgr_index_load_file checks magic, version, size and that the blob was built for

@@ -178,6 +178,13 @@ bo_aligner* bo_new(uint32_t k, uint32_t errors, uint32_t effort) {
     return a;
 }
 
+/* The index does not depend on -m / -e (aligner.cpp:407-534 never looks at them): the same indexed graph can be
+ * asked with other settings (test convenience: one index, a sweep over -m). */
+void bo_set_params(bo_aligner* a, uint32_t errors, uint32_t effort) {
+    a->errors = errors;
+    a->effort = effort;
+}
+
 void bo_free(bo_aligner* a) {
     if (!a) return;
     for (uint32_t i = 0; i < a->n_unitigs; ++i) free(a->unitigs[i]);

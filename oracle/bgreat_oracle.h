@@ -42,6 +42,8 @@ enum {
 
 /* Aligner::Aligner (aligner.h:80): k, errorsMax (-m), tryNumber (-e). */
 bo_aligner* bo_new(uint32_t k, uint32_t errors, uint32_t effort);
+/* other -m / -e for the graph already indexed */
+void bo_set_params(bo_aligner* a, uint32_t errors, uint32_t effort);
 void bo_free(bo_aligner* a);
 
 /* indexUnitigsAux (aligner.cpp:407-534) on a unitig FASTA file. Returns the number of

@@ -37,6 +37,7 @@ def lib():
         L.bo_new.restype = C.c_void_p
         L.bo_new.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         L.bo_free.argtypes = [C.c_void_p]
+        L.bo_set_params.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.bo_index_file.restype = C.c_int64
         L.bo_index_file.argtypes = [C.c_void_p, C.c_char_p]
         L.bo_index_mem.restype = C.c_int64
@@ -96,6 +97,16 @@ class Oracle:
             t += len(s)
         off[len(seqs)] = t
         return self.L.bo_index_mem(self.h, b"".join(seqs), off, len(seqs))
+
+    def index_arrays(self, seqs, off):
+        """unitigs as one uint8 array of concatenated sequences + uint64 offsets[n+1] (no per-unitig objects:
+        graphs of millions of unitigs)"""
+        return self.L.bo_index_mem(self.h, seqs.ctypes.data_as(C.c_char_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                   len(off) - 1)
+
+    def set_params(self, errors, effort):
+        """other -m / -e on the graph already indexed (the index does not depend on them)"""
+        self.L.bo_set_params(self.h, errors, effort)
 
     def align(self, read, mode=GREEDY):
         """-> (overlap_found, rc, [path ints])"""

@@ -206,3 +206,58 @@ def test_cli_index_cache_file(tmp_path):
     args[ki] = str(int(args[ki]) + 1)
     rc, lines, err = run_cli(args, str(tmp_path), {"BGR_INDEX_CACHE": cache})
     assert "index cache not used" in err
+
+
+# ---- several devices inside the binary (reads shard across the GPUs of a box, the index is replicated device to
+# device, the writer restores input order). BGR_GPUS beyond the number of devices puts several contexts on one
+# device, which exercises the same pipeline on a single-GPU box.
+
+def _gpu_count():
+    import bgreat_b200
+    from bgreat_b200 import _abi as A
+    import ctypes as C
+    n = C.c_int(0)
+    assert A.lib().bgr_device_count(C.byref(n)) == 0
+    return n.value
+
+
+@pytest.mark.parametrize("gpus", ["2", "3", "all"])
+@pytest.mark.parametrize("name", ["K1_two_files", "K4_fastq_trailing_nl", "random_k7_e2"])
+def test_cli_golden_runs_on_several_contexts(name, gpus, tmp_path):
+    if gpus == "all" and _gpu_count() < 2:
+        pytest.skip("one GPU: the oversubscribed forms cover the pipeline")
+    case = next(c for c in CLI if c["name"] == name)
+    for fn, content in case["files"].items():
+        with open(tmp_path / fn, "w", newline="") as f:
+            f.write(content)
+    env = {"BGR_RANGE_BYTES": "60"}
+    if gpus != "all":
+        env["BGR_GPUS"] = gpus
+    rc, lines, err = run_cli(case["args"], str(tmp_path), env)
+    assert rc == 0, err
+    assert lines == case["stdout"]
+    for fn, want in case["outputs"].items():
+        if want is not None:
+            assert open(tmp_path / fn, newline="").read() == want, fn
+
+
+def test_cli_several_contexts_equal_one_on_a_larger_file(tmp_path):
+    """40 k reads cut into ~80 batches: outputs of 1, 2 and 4 contexts are byte-equal (input order is kept)."""
+    import random
+    rng = random.Random(9)
+    unitigs, haps = S.make_graph(rng, 31, genome_len=60000, mean_unitig=80, n_variants=400)
+    reads = S.make_reads(rng, haps, 40000, 150, sub_rate=0.01, n_rate=0.0003)
+    with open(tmp_path / "u.fa", "w") as f:
+        for i, u in enumerate(unitigs):
+            f.write(">%d\n%s\n" % (i + 1, u))
+    with open(tmp_path / "r.fa", "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">r%d\n%s\n" % (i, r))
+    outs = {}
+    for g in ("1", "2", "4"):
+        rc, lines, err = run_cli(["-r", "r.fa", "-g", "u.fa", "-k", 31, "-m", 2, "-t", 4, "-f", "p" + g, "-a", "n" + g],
+                                 str(tmp_path), {"BGR_GPUS": g, "BGR_RANGE_BYTES": "80000"})
+        assert rc == 0, err
+        outs[g] = (lines, open(tmp_path / ("p" + g)).read(), open(tmp_path / ("n" + g)).read())
+    assert outs["1"] == outs["2"] == outs["4"]
+    assert outs["1"][1].count("\n") > 20000
