@@ -92,7 +92,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the command-line leg (files in /dev/shm)")
-    ap.add_argument("--cli-reads", type=int, default=10_000_000, help="reads of the command-line leg")
+    ap.add_argument("--cli-reads", type=int, default=40_000_000, help="reads of the command-line leg")
     ap.add_argument("--errors", type=int, default=2, help="-m")
     ap.add_argument("--effort", type=int, default=2, help="-e")
     ap.add_argument("--sub-rate", type=float, default=0.01, help="substitution error rate of the reads")

@@ -23,7 +23,7 @@ SYMBOLS = ["bgr_abi_version", "bgr_ctx_create", "bgr_ctx_destroy", "bgr_last_err
            "bgr_index_query", "bgr_map_batch", "bgr_slot_upload", "bgr_slot_run", "bgr_slot_download",
            "bgr_slot_wait", "bgr_slot_download_corrected", "bgr_slot_kernel_ms", "bgr_counters", "bgr_counters_reset", "bgr_launch_count",
            "bgr_pack_reads", "bgr_slot_upload_packed", "bgr_index_save_file", "bgr_index_load_file", "bgr_device_count",
-           "bgr_index_replicate"]
+           "bgr_index_replicate", "bgr_slot_upload_text", "bgr_slot_format_text"]
 
 
 P_CORRECT = 1  # bgr_params.flags: correction mode (-c)
@@ -73,6 +73,8 @@ def lib():
     L.bgr_index_load_file.argtypes = [vp, C.c_char_p, C.c_uint32]
     L.bgr_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bgr_index_replicate.argtypes = [vp, vp]
+    L.bgr_slot_upload_text.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.bgr_slot_format_text.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.bgr_map_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint64, u64p]
     L.bgr_slot_upload.argtypes = [vp, C.c_int, vp, vp, C.c_uint32]
     L.bgr_slot_run.argtypes = [vp, C.c_int, C.POINTER(Params)]

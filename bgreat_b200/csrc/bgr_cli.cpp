@@ -22,6 +22,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -57,14 +58,29 @@ struct Batch {
     uint64_t pool_used = 0;
     int slot = -1;
     uint64_t seq = 0;  // position in the input: the writer emits batches in this order
+    // text mode (regular FASTA): the batch is a range of the input text, parsed and formatted on the device
+    // (bgr_slot_upload_text / bgr_slot_format_text); the host only copies text in and out
+    bool text_mode = false;
+    PodBuf<char> text;     // the range's text (pinned)
+    const char* src = nullptr;  // the mapped input and the range in it: parsed here if the device reports it irregular
+    size_t src_a = 0, src_b = 0;
+    PodBuf<char> otext[3];  // the three output streams (pinned)
+    uint64_t oused[3] = {0, 0, 0};
     Batch() {
         pb.set_allocator(pinned_alloc, pinned_free);
-        res.alloc = pool.alloc = corr.alloc = pinned_alloc;
-        res.dealloc = pool.dealloc = corr.dealloc = pinned_free;
+        res.alloc = pool.alloc = corr.alloc = text.alloc = pinned_alloc;
+        res.dealloc = pool.dealloc = corr.dealloc = text.dealloc = pinned_free;
+        for (auto& o : otext) o.alloc = pinned_alloc, o.dealloc = pinned_free;
     }
     // Buffers for a batch cut from `range_bytes` of text, sized once: pinning memory costs about as much per
     // byte as parsing it, and growing a pinned buffer pins it twice. Reads shorter than ~60 bases make the
     // per-read arrays grow later, which is only slower.
+    void prealloc_text(size_t range_bytes, bool split_no_overlap) {
+        text.reserve(range_bytes + 4096);
+        otext[0].reserve(range_bytes / 2 + 4096);  // paths are shorter than the reads they stand for
+        otext[1].reserve(range_bytes * 5 / 8 + 4096);
+        if (split_no_overlap) otext[2].reserve(range_bytes / 2 + 4096);
+    }
     void prealloc(size_t range_bytes) {
         const size_t reads = range_bytes / 96 + 1024;
         pb.seqs.reserve(range_bytes + 4096);
@@ -456,9 +472,12 @@ int main(int argc, char** argv) {
         else total_text += range_bytes;  // pipes: size unknown
     }
     const size_t batch_text = std::min(range_bytes, total_text + 4096);
+    // regular FASTA goes through the device's parser and formatter (BGR_TEXT=0: the host stages only)
+    const bool text_path = !o.fastq && !(getenv("BGR_TEXT") && !strcmp(getenv("BGR_TEXT"), "0"));
     std::thread allocator([&] {
         for (auto& b : batches) {
-            b.prealloc(batch_text);
+            if (text_path) b.prealloc_text(batch_text, o.have_o);
+            else b.prealloc(batch_text);
             free_q.push(&b);
         }
     });
@@ -473,8 +492,11 @@ int main(int argc, char** argv) {
     // the header lines of a batch are views into the mapped input: every file stays mapped until the end
     std::vector<std::unique_ptr<MappedFile>> mapped;
 
+    // cleared by the first range the device reports irregular: the rest of the input is then parsed on the host
+    std::atomic<bool> text_ok{true};
     std::thread parser([&] {
         uint64_t seq = 0;
+        WorkerPool copy_pool(threads - 1);
         for (const std::string& file : files) {
             mapped.emplace_back(new MappedFile());
             MappedFile& mf = *mapped.back();
@@ -491,7 +513,28 @@ int main(int argc, char** argv) {
                 free_wait_s += since(tw);
                 const auto t = now();
                 b->pb.clear();
-                pr.next(b->pb);
+                b->text_mode = false;
+                size_t ra = 0, rb = 0;
+                if (text_path && pr.fasta_next_range(ra, rb)) {
+                    if (text_ok.load()) {  // hand the text over as it is: copied into the pinned buffer by all workers
+                        b->text_mode = true;
+                        b->src = mf.data;
+                        b->src_a = ra;
+                        b->src_b = rb;
+                        const size_t nb = rb - ra;
+                        b->text.reserve(nb + 64);
+                        b->text.n = nb;
+                        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, nb / (1u << 20) + 1));
+                        copy_pool.run(T, [&](unsigned w) {
+                            const size_t lo = nb * w / T, hi = nb * (w + 1) / T;
+                            memcpy(b->text.p + lo, mf.data + ra + lo, hi - lo);
+                        });
+                    } else {
+                        pr.fasta_parse_range(ra, rb, b->pb);
+                    }
+                } else if (!text_path) {
+                    pr.next(b->pb);
+                }
                 b->seq = seq++;
                 parse_s += since(t);
                 parsed_q.push(b);  // possibly empty: still flows through so that order is kept
@@ -509,6 +552,29 @@ int main(int argc, char** argv) {
         auto finish = [&](Batch* b) {
             uint64_t used = 0;
             const auto t = now();
+            if (b->text_mode) {
+                char* outp[3] = {b->otext[0].p, b->otext[1].p, b->otext[2].p};
+                uint64_t cap[3] = {b->otext[0].cap, b->otext[1].cap, b->otext[2].cap};
+                int r = bgr_slot_format_text(ctx, b->slot, o.have_o ? 1 : 0, outp, cap, b->oused);
+                if (r == BGR_ERR_LIMIT) {  // an output buffer too small: come back with bigger ones
+                    for (int f = 0; f < 3; ++f) {
+                        if (b->oused[f] > b->otext[f].cap) b->otext[f].reserve(b->oused[f] + b->oused[f] / 8 + 4096);
+                        outp[f] = b->otext[f].p;
+                        cap[f] = b->otext[f].cap;
+                    }
+                    r = bgr_slot_format_text(ctx, b->slot, o.have_o ? 1 : 0, outp, cap, b->oused);
+                }
+                if (r != BGR_OK) {
+                    fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
+                    exit(1);
+                }
+                {
+                    std::lock_guard<std::mutex> l(stat_m);
+                    gpu_wait_s += since(t);
+                }
+                done_q.push(b);
+                return;
+            }
             int r = bgr_slot_wait(ctx, b->slot, &used);
             if (r == BGR_ERR_LIMIT) {  // pool buffer too small: come back with a bigger one
                 b->pool.reserve(used + 1024);
@@ -546,6 +612,26 @@ int main(int argc, char** argv) {
                 }
                 b->slot = next_slot;
                 next_slot = (next_slot + 1) % n_slots;
+                if (b->text_mode) {
+                    uint32_t n_reads = 0;
+                    int regular = 1;
+                    int r = bgr_slot_upload_text(ctx, b->slot, b->text.p, b->text.n, 0, &n_reads, &regular);
+                    if (r == BGR_OK && regular) r = bgr_slot_run(ctx, b->slot, &params);
+                    if (r != BGR_OK) {
+                        fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
+                        exit(1);
+                    }
+                    if (regular) {
+                        inflight.push_back(b);
+                        continue;
+                    }
+                    // continuation lines, a missing final newline ...: the host parser knows what the reference
+                    // does with those; this range here and now, the rest of the input in the reader
+                    text_ok.store(false);
+                    b->text_mode = false;
+                    b->pb.clear();
+                    parse_fasta_text_sequential(b->src, b->src_a, b->src_b, (uint32_t)o.k, b->pb);
+                }
                 size_t n = b->pb.size();
                 b->res.reserve(n + 1);
                 b->pool.reserve(n * 8 + 1024);
@@ -599,6 +685,30 @@ int main(int argc, char** argv) {
                 continue;
             }
             ++next_seq;
+            if (b->text_mode) {  // already text: the three streams are copied into the files by all workers
+                const auto t0w = now();
+                for (int f = 0; f < 3; ++f)
+                    if (!out[f].begin((size_t)b->oused[f])) write_error = true;
+                writer_phase[1] += since(t0w);
+                const auto t2w = now();
+                size_t total_b = (size_t)(b->oused[0] + b->oused[1] + b->oused[2]);
+                const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, total_b / (1u << 20) + 1));
+                pool.run(T, [&](unsigned t) {
+                    for (int f = 0; f < 3; ++f) {
+                        if (!out[f].base || !b->oused[f]) continue;
+                        const size_t lo = (size_t)b->oused[f] * t / T, hi = (size_t)b->oused[f] * (t + 1) / T;
+                        memcpy(out[f].base + lo, b->otext[f].p + lo, hi - lo);
+                    }
+                });
+                writer_phase[2] += since(t2w);
+                const auto t3w = now();
+                for (int f = 0; f < 3; ++f)
+                    if (!out[f].end((size_t)b->oused[f])) write_error = true;
+                writer_phase[3] += since(t3w);
+                write_s += since(t0w);
+                free_q.push(b);
+                continue;
+            }
             const auto t0w = now();
             const size_t n = b->pb.size();
             const unsigned T = (unsigned)std::min<size_t>(threads, n / 4096 + 1);

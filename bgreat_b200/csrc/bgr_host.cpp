@@ -812,10 +812,17 @@ void ParallelReader::next(ParsedBatch& out) {
     else next_fasta(out);
 }
 
-void ParallelReader::next_fasta(ParsedBatch& out) {
-    const size_t a = pos_;
+bool ParallelReader::fasta_next_range(size_t& a, size_t& b) {
+    if (finished_) return false;
+    a = pos_;
     const size_t want = a + range_;
-    const size_t b = (want >= n_ || want < a) ? n_ : fasta_boundary(want);
+    b = (want >= n_ || want < a) ? n_ : fasta_boundary(want);
+    pos_ = b;
+    if (pos_ >= n_) finished_ = true;
+    return true;
+}
+
+void ParallelReader::fasta_parse_range(size_t a, size_t b, ParsedBatch& out) {
     const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, (b - a) / min_slice_ + 1));
     std::vector<size_t> cut(T + 1);
     cut[0] = a;
@@ -836,8 +843,18 @@ void ParallelReader::next_fasta(ParsedBatch& out) {
     phase_s[0] += std::chrono::duration<double>(t1 - t0).count();
     phase_s[1] += std::chrono::duration<double>(t2 - t1).count();
     phase_s[2] += std::chrono::duration<double>(t3 - t2).count();
-    pos_ = b;
-    if (pos_ >= n_) finished_ = true;
+}
+
+void ParallelReader::next_fasta(ParsedBatch& out) {
+    size_t a, b;
+    if (fasta_next_range(a, b)) fasta_parse_range(a, b, out);
+}
+
+void parse_fasta_text_sequential(const char* d, size_t a, size_t b, uint32_t k, ParsedBatch& out) {
+    std::vector<Shard> sh(1);
+    if (a < b) parse_fasta_range(d, a, b, k, sh[0]);
+    WorkerPool pool(0);
+    gather(sh, 1, pool, out);
 }
 
 void ParallelReader::next_fastq(ParsedBatch& out) {

@@ -212,6 +212,10 @@ class ParallelReader {
     bool done() const { return finished_; }
     // appends the records of the next range to `out` (which the caller has cleared)
     void next(ParsedBatch& out);
+    // FASTA, in two steps, for a caller that may hand the range's text to the device instead of parsing it here
+    // (bgr_slot_upload_text): the next range [a, b) of whole records (false: the input is used up), and its parse
+    bool fasta_next_range(size_t& a, size_t& b);
+    void fasta_parse_range(size_t a, size_t b, ParsedBatch& out);
     // wall time spent so far in the phases of next(): cutting (FASTQ: counting lines), parsing, copying (diagnostics)
     double phase_s[3] = {0, 0, 0};
 
@@ -228,6 +232,9 @@ class ParallelReader {
     unsigned threads_;
     Impl* impl_;
 };
+
+// the FASTA records of d[a, b) (a a record start, b a record start or the end of the input) on the calling thread
+void parse_fasta_text_sequential(const char* d, size_t a, size_t b, uint32_t k, ParsedBatch& out);
 
 // load_unitig_file on `threads` workers: records are two lines whatever they contain, so newlines are
 // counted in parallel and every worker takes whole records; the last record goes through the sequential

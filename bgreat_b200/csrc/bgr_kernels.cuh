@@ -22,9 +22,11 @@
 // host: libbgreat_b200.so only ever launches the kernels.
 //
 // This header is the one to include; the code lives in bgr_dev.cuh (shared vocabulary), bgr_scan.cuh (seed scan),
-// bgr_extend.cuh (per-read aligners) and bgr_emit.cuh (extension kernels, compaction, correction).
+// bgr_extend.cuh (per-read aligners), bgr_emit.cuh (extension kernels, compaction, correction) and bgr_text.cuh
+// (record parsing and output formatting for text batches).
 #pragma once
 #include "bgr_dev.cuh"
 #include "bgr_scan.cuh"
 #include "bgr_extend.cuh"
 #include "bgr_emit.cuh"
+#include "bgr_text.cuh"

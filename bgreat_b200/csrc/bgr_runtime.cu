@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cub/device/device_scan.cuh>
 #include <string>
 #include <thread>
 #include <vector>
@@ -79,6 +80,30 @@ struct Slot {
     i32* h_pool = nullptr;
     u64 h_pool_cap = 0;
     bool want_download = false;
+    // text batches (bgr_slot_upload_text / bgr_slot_format_text): the raw text, its line and record tables
+    char* d_text = nullptr;
+    size_t cap_text = 0;
+    u64 text_bytes = 0;
+    bool is_text = false;
+    u32 n_rec = 0;
+    u32 *d_tcnt = nullptr, *d_tbase = nullptr;  // newlines per 16 bytes, and their exclusive scan
+    size_t cap_tcnt = 0;
+    u32* d_nl = nullptr;
+    size_t cap_nl = 0;
+    u32 *d_hoff = nullptr, *d_hlen = nullptr, *d_soff = nullptr, *d_slen = nullptr, *d_keep = nullptr, *d_ridx = nullptr;
+    unsigned long long *d_klen = nullptr, *d_roff = nullptr;
+    size_t cap_rec = 0;
+    u32* d_rec_of = nullptr;
+    size_t cap_rec_of = 0;
+    void* d_scan_tmp = nullptr;
+    size_t cap_scan_tmp = 0;
+    TextMeta* d_tmeta = nullptr;
+    TextMeta* h_tmeta = nullptr;  // pinned
+    unsigned long long *d_osz = nullptr, *d_oat = nullptr;  // [3][n] bytes per read and file, and their scans
+    size_t cap_osz = 0;
+    char* d_out[3] = {nullptr, nullptr, nullptr};
+    size_t cap_out[3] = {0, 0, 0};
+    unsigned long long* h_ototal = nullptr;  // pinned: [3] last offset + last size per file
 };
 
 }  // namespace
@@ -291,6 +316,22 @@ int enqueue_extension(bgr_ctx* ctx, Slot& s) {
 
 }  // namespace
 
+namespace {
+template <typename T>
+int scan_exclusive(bgr_ctx* ctx, Slot& s, const T* in, T* out, size_t n) {
+    size_t need = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, s.stream));
+    if (need > s.cap_scan_tmp) {
+        if (s.d_scan_tmp) CK(cudaFree(s.d_scan_tmp));
+        s.d_scan_tmp = nullptr;
+        CK(cudaMalloc(&s.d_scan_tmp, need * 2));
+        s.cap_scan_tmp = need * 2;
+    }
+    CK(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp, need, in, out, (int)n, s.stream));
+    return BGR_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int bgr_abi_version(void) { return BGR_ABI_VERSION; }
@@ -370,6 +411,26 @@ void bgr_ctx_destroy(bgr_ctx* ctx) {
         cudaFree(s.d_slow);
         cudaFree(s.d_bsum);
         cudaFree(s.d_corr);
+        cudaFree(s.d_text);
+        cudaFree(s.d_tcnt);
+        cudaFree(s.d_tbase);
+        cudaFree(s.d_nl);
+        cudaFree(s.d_hoff);
+        cudaFree(s.d_hlen);
+        cudaFree(s.d_soff);
+        cudaFree(s.d_slen);
+        cudaFree(s.d_keep);
+        cudaFree(s.d_ridx);
+        cudaFree(s.d_klen);
+        cudaFree(s.d_roff);
+        cudaFree(s.d_rec_of);
+        cudaFree(s.d_scan_tmp);
+        cudaFree(s.d_tmeta);
+        cudaFree(s.d_osz);
+        cudaFree(s.d_oat);
+        for (int f = 0; f < 3; ++f) cudaFree(s.d_out[f]);
+        if (s.h_tmeta) cudaFreeHost(s.h_tmeta);
+        if (s.h_ototal) cudaFreeHost(s.h_ototal);
         if (s.h_cnt) cudaFreeHost(s.h_cnt);
         if (s.h_scnt) cudaFreeHost(s.h_scnt);
         for (int j = 0; j < 3; ++j)
@@ -559,10 +620,11 @@ int bgr_index_query(const bgr_ctx* cctx, uint64_t kmer_code, int want_end, int32
 
 namespace {
 // per-read and per-word device buffers every upload form needs; the offsets go up with it
-int upload_common(bgr_ctx* ctx, Slot& s, const uint64_t* off, uint32_t n) {
+// off: the n+1 offsets on the host, or (off_on_host false) null with `chars_known` characters: the device fills d_off
+int upload_common(bgr_ctx* ctx, Slot& s, const uint64_t* off, uint32_t n, bool off_on_host = true, u64 chars_known = 0) {
     // the kernels index reads, tiles and list entries with 32-bit numbers
     if (n > (1u << 30)) return fail(ctx, BGR_ERR_LIMIT, "more than 2^30 reads in one batch: split it");
-    const u64 chars = off[n];
+    const u64 chars = off_on_host ? off[n] : chars_known;
     const u64 words = batch_words(chars, n);
     int rc;
     if (n + 1 > s.cap_reads || !s.d_off) {
@@ -582,7 +644,7 @@ int upload_common(bgr_ctx* ctx, Slot& s, const uint64_t* off, uint32_t n) {
         if ((rc = grow(ctx, s.d_H2, c3, (size_t)words))) return rc;
         s.cap_words = std::min(std::min(c0, c1), std::min(c2, c3));
     }
-    CK(cudaMemcpyAsync(s.d_off, off, ((size_t)n + 1) * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
+    if (off_on_host) CK(cudaMemcpyAsync(s.d_off, off, ((size_t)n + 1) * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
     s.n = n;
     s.chars = chars;
     s.words = words;
@@ -590,6 +652,7 @@ int upload_common(bgr_ctx* ctx, Slot& s, const uint64_t* off, uint32_t n) {
     s.ran = false;
     s.want_download = false;
     s.want_corrected = false;
+    s.is_text = false;
     return BGR_OK;
 }
 }  // namespace
@@ -682,6 +745,156 @@ int bgr_slot_upload_packed(bgr_ctx* ctx, int slot, const uint64_t* words, const 
     if ((rc = upload_common(ctx, s, off, n))) return rc;
     s.packed = true;
     s.n_exc = n_exc;
+    return BGR_OK;
+}
+
+// ---- text batches: records parsed and output formatted on the device (bgr_text.cuh)
+
+
+int bgr_slot_upload_text(bgr_ctx* ctx, int slot, const char* text, uint64_t bytes, int fastq, uint32_t* n_reads,
+                         int* regular) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots) return fail(ctx, BGR_ERR_ARG, "bad slot");
+    if ((!text && bytes) || !n_reads || !regular) return fail(ctx, BGR_ERR_ARG, "null argument");
+    if (!ctx->has_index) return fail(ctx, BGR_ERR_NO_INDEX, "no index built or imported (the FASTA length filter needs k)");
+    if (bytes >= 0xFFFFFF00ull) return fail(ctx, BGR_ERR_LIMIT, "more than 4 GB of text in one batch: split it");
+    Slot& s = ctx->slots[slot];
+    CK(cudaSetDevice(ctx->device));
+    *n_reads = 0;
+    *regular = 1;
+    int rc;
+    if (!s.d_tmeta) {
+        CK(cudaMalloc((void**)&s.d_tmeta, sizeof(TextMeta)));
+        CK(cudaHostAlloc((void**)&s.h_tmeta, sizeof(TextMeta), cudaHostAllocPortable));
+        CK(cudaHostAlloc((void**)&s.h_ototal, 8 * sizeof(unsigned long long), cudaHostAllocPortable));
+    }
+    const size_t n16 = (size_t)((bytes + 15) / 16);
+    if ((rc = grow(ctx, s.d_text, s.cap_text, (size_t)bytes + 64))) return rc;
+    if (n16 + 1 > s.cap_tcnt || !s.d_tcnt) {
+        size_t c0 = 0, c1 = 0;
+        if ((rc = grow(ctx, s.d_tcnt, c0, n16 + 1))) return rc;
+        if ((rc = grow(ctx, s.d_tbase, c1, n16 + 1))) return rc;
+        s.cap_tcnt = std::min(c0, c1);
+    }
+    CK(cudaMemsetAsync(s.d_tmeta, 0, sizeof(TextMeta), s.stream));
+    if (bytes) CK(cudaMemcpyAsync(s.d_text, text, bytes, cudaMemcpyHostToDevice, s.stream));
+    s.text_bytes = bytes;
+    u32 n_lines = 0;
+    if (bytes) {
+        k_text_count<<<(unsigned)((n16 + TX_THREADS - 1) / TX_THREADS), TX_THREADS, 0, s.stream>>>(s.d_text, bytes, s.d_tcnt);
+        if ((rc = scan_exclusive(ctx, s, s.d_tcnt, s.d_tbase, n16))) return rc;
+        u32 last_base = 0, last_cnt = 0;
+        CK(cudaMemcpyAsync(&last_base, s.d_tbase + (n16 - 1), sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(&last_cnt, s.d_tcnt + (n16 - 1), sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        n_lines = last_base + last_cnt;
+        ctx->launches += 1;
+    }
+    const u32 lpr = fastq ? 4u : 2u;
+    const u32 n_rec = n_lines / lpr;
+    s.n_rec = n_rec;
+    if (n_lines % lpr != 0 || (bytes && n_lines == 0)) {  // a partial record: not the regular shape
+        *regular = 0;
+        return BGR_OK;
+    }
+    if ((rc = grow(ctx, s.d_nl, s.cap_nl, (size_t)n_lines + 1))) return rc;
+    if ((size_t)n_rec + 1 > s.cap_rec || !s.d_hoff) {
+        size_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if ((rc = grow(ctx, s.d_hoff, c[0], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_hlen, c[1], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_soff, c[2], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_slen, c[3], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_keep, c[4], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_ridx, c[5], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_klen, c[6], (size_t)n_rec + 1))) return rc;
+        if ((rc = grow(ctx, s.d_roff, c[7], (size_t)n_rec + 1))) return rc;
+        s.cap_rec = *std::min_element(c, c + 8);
+    }
+    if (n_rec) {
+        k_text_lines<<<(unsigned)((n16 + TX_THREADS - 1) / TX_THREADS), TX_THREADS, 0, s.stream>>>(s.d_text, bytes, s.d_tbase, s.d_nl);
+        k_text_records<<<(n_rec + TX_THREADS - 1) / TX_THREADS, TX_THREADS, 0, s.stream>>>(
+            s.d_text, bytes, s.d_nl, n_lines, lpr, ctx->ix.k, s.d_hoff, s.d_hlen, s.d_soff, s.d_slen, s.d_keep, s.d_klen, s.d_tmeta);
+        if ((rc = scan_exclusive(ctx, s, s.d_keep, s.d_ridx, n_rec))) return rc;
+        if ((rc = scan_exclusive(ctx, s, s.d_klen, s.d_roff, n_rec))) return rc;
+        // how many reads, how many characters: needed to size the batch's buffers
+        u32 last[2] = {0, 0};
+        unsigned long long lastc[2] = {0, 0};
+        CK(cudaMemcpyAsync(&last[0], s.d_ridx + (n_rec - 1), sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(&last[1], s.d_keep + (n_rec - 1), sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(&lastc[0], s.d_roff + (n_rec - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(&lastc[1], s.d_klen + (n_rec - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_tmeta, s.d_tmeta, sizeof(TextMeta), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        ctx->launches += 2;
+        if (s.h_tmeta->irregular) {
+            *regular = 0;
+            return BGR_OK;
+        }
+        const u32 n = last[0] + last[1];
+        const u64 chars = lastc[0] + lastc[1];
+        if ((rc = grow(ctx, s.d_seq, s.cap_seq, (size_t)chars + 16))) return rc;
+        if ((rc = grow(ctx, s.d_rec_of, s.cap_rec_of, (size_t)n + 1))) return rc;
+        if ((rc = upload_common(ctx, s, nullptr, n, false, chars))) return rc;
+        k_text_gather<<<(unsigned)(((size_t)n_rec * 32 + TX_THREADS - 1) / TX_THREADS), TX_THREADS, 0, s.stream>>>(
+            s.d_text, s.d_soff, s.d_slen, s.d_keep, s.d_ridx, s.d_roff, n_rec, s.d_seq, s.d_off, s.d_rec_of, s.d_tmeta);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        *n_reads = n;
+    } else {
+        if ((rc = upload_common(ctx, s, nullptr, 0, false, 0))) return rc;
+        CK(cudaMemsetAsync(s.d_off, 0, sizeof(u64), s.stream));
+    }
+    s.packed = false;
+    s.n_exc = 0;
+    s.is_text = true;
+    return BGR_OK;
+}
+
+int bgr_slot_format_text(bgr_ctx* ctx, int slot, int split_no_overlap, char* const out[3], const uint64_t cap[3],
+                         uint64_t used[3]) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots || !out || !cap || !used) return fail(ctx, BGR_ERR_ARG, "bad argument");
+    Slot& s = ctx->slots[slot];
+    if (!s.is_text || !s.ran) return fail(ctx, BGR_ERR_ARG, "slot holds no text batch that has been run");
+    // the mapping itself (scratch / pool growth included), then the text of the three files
+    int rc = bgr_slot_wait(ctx, slot, nullptr);
+    if (rc) return rc;
+    used[0] = used[1] = used[2] = 0;
+    if (s.n == 0) return BGR_OK;
+    const u32 n = s.n;
+    if ((rc = grow(ctx, s.d_osz, s.cap_osz, (size_t)3 * n + 3))) return rc;
+    {
+        size_t c = s.d_oat ? s.cap_osz : 0;
+        if (!s.d_oat || (size_t)3 * n + 3 > c) {
+            if (s.d_oat) CK(cudaFree(s.d_oat));
+            s.d_oat = nullptr;
+            CK(cudaMalloc((void**)&s.d_oat, s.cap_osz * sizeof(unsigned long long)));
+        }
+    }
+    BatchArgs a = make_args(s);
+    const u32 correction = (s.params.flags & BGR_P_CORRECT) ? 1u : 0u;
+    const unsigned blocks = (n + TX_THREADS - 1) / TX_THREADS;
+    k_text_sizes<<<blocks, TX_THREADS, 0, s.stream>>>(a, s.d_rec_of, s.d_hlen, split_no_overlap ? 1u : 0u, correction, s.d_osz);
+    for (int f = 0; f < 3; ++f)
+        if ((rc = scan_exclusive(ctx, s, s.d_osz + (size_t)f * n, s.d_oat + (size_t)f * n, n))) return rc;
+    for (int f = 0; f < 3; ++f) {
+        CK(cudaMemcpyAsync(&s.h_ototal[2 * f], s.d_oat + (size_t)f * n + (n - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(&s.h_ototal[2 * f + 1], s.d_osz + (size_t)f * n + (n - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    bool fits = true;
+    for (int f = 0; f < 3; ++f) {
+        used[f] = s.h_ototal[2 * f] + s.h_ototal[2 * f + 1];
+        if (used[f] > cap[f] || (used[f] && !out[f])) fits = false;
+    }
+    if (!fits) return fail(ctx, BGR_ERR_LIMIT, "output buffer too small (used[] holds the bytes needed)");
+    for (int f = 0; f < 3; ++f)
+        if ((rc = grow(ctx, s.d_out[f], s.cap_out[f], (size_t)used[f] + 16))) return rc;
+    k_text_format<<<blocks, TX_THREADS, 0, s.stream>>>(a, s.d_text, s.d_rec_of, s.d_hoff, s.d_hlen, split_no_overlap ? 1u : 0u,
+                                                        correction, s.d_oat, s.d_out[0], s.d_out[1], s.d_out[2]);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    for (int f = 0; f < 3; ++f)
+        if (used[f]) CK(cudaMemcpyAsync(out[f], s.d_out[f], used[f], cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
     return BGR_OK;
 }
 

@@ -194,6 +194,32 @@ int bgr_slot_wait(bgr_ctx* ctx, int slot, uint64_t* pool_used);
 #define BGR_CORRECTED_BASE(char_off, i) (((uint64_t)(char_off) >> 5) + (uint64_t)(i))
 #define BGR_CORRECTED_WORDS(chars, n) (((uint64_t)(chars) >> 5) + (uint64_t)(n) + 2)
 int bgr_slot_download_corrected(bgr_ctx* ctx, int slot, uint64_t* words, uint64_t cap_words);
+/* Text batches: record parsing and output formatting on the device, for callers that hold the input as text and
+ * want the output as text (the command line). They replace, for input of the regular shape, Aligner::getReads
+ * (aligner.cpp:46-117) and the output half of alignPartGreedy / alignPartExhaustive with printPath
+ * (alignerGreedy.cpp:393-428, aligner.cpp:600-609).
+ *
+ * bgr_slot_upload_text: text[0 .. bytes) is a run of whole records starting at a record start -- FASTA (fastq = 0:
+ * header line starting with '>', one sequence line) or FASTQ (fastq != 0: four lines), every line terminated by a
+ * newline. The reads getReads would return (sequence longer than 2 -- FASTA: and than k -- and made of A C G T N;
+ * the others are dropped and not counted) become the slot's batch, in order, exactly as if passed to
+ * bgr_slot_upload; *n_reads receives their number. *regular = 0 reports text that is not of that shape (continuation
+ * lines, a missing final newline, a partial record, a header without '>'): nothing is uploaded and the caller
+ * parses this text itself (the reference's stream semantics for such input are the host parser's business).
+ * Blocks until the batch is parsed (the host has to know its size). The text buffer may be reused on return. Needs
+ * an index (k). At most 4 GB of text per batch.
+ *
+ * bgr_slot_format_text (after bgr_slot_run on a text batch; blocks): the three output streams of the batch, in
+ * input order -- out[0] header\npath\n of every mapped read (header\ncorrected\n when the run had BGR_P_CORRECT),
+ * out[1] header\nread\n of the others, out[2] (split_no_overlap != 0 only: the command line's -o) those of them
+ * without any overlap. cap[f] = capacity of out[f]; used[f] receives the bytes written. If a buffer is too small
+ * BGR_ERR_LIMIT is returned with used[] = the sizes needed, and the call may be repeated. Counters are added to the
+ * context's totals as by bgr_slot_wait. */
+int bgr_slot_upload_text(bgr_ctx* ctx, int slot, const char* text, uint64_t bytes, int fastq, uint32_t* n_reads,
+                         int* regular);
+int bgr_slot_format_text(bgr_ctx* ctx, int slot, int split_no_overlap, char* const out[3], const uint64_t cap[3],
+                         uint64_t used[3]);
+
 /* device time of the last bgr_slot_run on this slot, per kernel (ms; CUDA events on the slot's
  * stream): [0] pack+seed-scan kernel, [1] extension kernel, [2] whole run */
 int bgr_slot_kernel_ms(bgr_ctx* ctx, int slot, float ms[3]);
