@@ -726,7 +726,7 @@ def run_b200_arm(args):
         line["cpu_baseline"] = cpu
     if world == 1 and not args.no_cli:
         al.close()  # the command line creates its own context
-        line["cli"] = cli_leg(graph, min(n_reads, args.cli_reads))
+        line["cli"] = cli_leg(graph, args.cli_reads)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

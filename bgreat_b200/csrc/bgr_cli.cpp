@@ -404,14 +404,33 @@ int main(int argc, char** argv) {
         fprintf(stderr, "bgreat: %s\n", n_dev < 1 && !*bgr_last_error(nullptr) ? "no CUDA device" : bgr_last_error(nullptr));
         return 1;
     }
-    int n_gpus = n_dev;
+    // Devices used: all of them for large inputs, fewer for small ones (a CUDA context takes about a second to
+    // create, and 4 GB of reads keep one device busy for about as long); BGR_GPUS=N says otherwise.
+    size_t input_bytes = 0;
+    for (const std::string& f : split_list(o.reads)) {
+        struct stat st;
+        if (stat(f.c_str(), &st) == 0 && S_ISREG(st.st_mode)) input_bytes += (size_t)st.st_size;
+    }
+    int n_gpus = (int)std::min<size_t>((size_t)n_dev, 1 + input_bytes / ((size_t)4 << 30));
     if (const char* e = getenv("BGR_GPUS")) n_gpus = std::max(1, std::min(16, atoi(e)));
     std::vector<bgr_ctx*> ctxs((size_t)n_gpus, nullptr);
-    for (int g = 0; g < n_gpus; ++g)
-        if (bgr_ctx_create(g % n_dev, n_slots, &ctxs[g]) != BGR_OK) {
-            fprintf(stderr, "bgreat: %s\n", bgr_last_error(nullptr));
-            return 1;
-        }
+    {
+        // contexts are created side by side: the driver initialises the devices concurrently
+        std::vector<std::thread> mk;
+        std::vector<int> rcs((size_t)n_gpus, BGR_OK);
+        std::vector<std::string> errs((size_t)n_gpus);
+        for (int g = 0; g < n_gpus; ++g)
+            mk.emplace_back([&, g] {
+                rcs[g] = bgr_ctx_create(g % n_dev, n_slots, &ctxs[g]);
+                if (rcs[g] != BGR_OK) errs[g] = bgr_last_error(nullptr);
+            });
+        for (auto& t : mk) t.join();
+        for (int g = 0; g < n_gpus; ++g)
+            if (rcs[g] != BGR_OK) {
+                fprintf(stderr, "bgreat: %s\n", errs[g].c_str());
+                return 1;
+            }
+    }
     bgr_ctx* ctx = ctxs[0];
 
     lap("context created");
@@ -438,11 +457,17 @@ int main(int argc, char** argv) {
             fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
         rc = BGR_OK;
     }
-    for (int g = 1; g < n_gpus; ++g)
-        if (bgr_index_replicate(ctxs[g], ctx) != BGR_OK) {
-            fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctxs[g]));
-            return 1;
-        }
+    {
+        std::vector<std::thread> rep;
+        std::vector<int> rcs((size_t)n_gpus, BGR_OK);
+        for (int g = 1; g < n_gpus; ++g) rep.emplace_back([&, g] { rcs[g] = bgr_index_replicate(ctxs[g], ctx); });
+        for (auto& t : rep) t.join();
+        for (int g = 1; g < n_gpus; ++g)
+            if (rcs[g] != BGR_OK) {
+                fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctxs[g]));
+                return 1;
+            }
+    }
     auto t1 = std::chrono::system_clock::now();
     std::cout << "Indexing in seconds : " << std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count()
               << std::endl;
