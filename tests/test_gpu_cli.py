@@ -230,9 +230,7 @@ def test_cli_golden_runs_on_several_contexts(name, gpus, tmp_path):
     for fn, content in case["files"].items():
         with open(tmp_path / fn, "w", newline="") as f:
             f.write(content)
-    env = {"BGR_RANGE_BYTES": "60"}
-    if gpus != "all":
-        env["BGR_GPUS"] = gpus
+    env = {"BGR_RANGE_BYTES": "60", "BGR_GPUS": gpus if gpus != "all" else str(_gpu_count())}
     rc, lines, err = run_cli(case["args"], str(tmp_path), env)
     assert rc == 0, err
     assert lines == case["stdout"]
