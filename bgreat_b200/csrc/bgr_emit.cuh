@@ -264,6 +264,8 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
         __syncwarp();
         // ---- 2. all chunks of all jobs, dealt to the 32 lanes
         for (u32 j = lane; j < total; j += 32) {
+            // its job: the last one whose first chunk is at or before j (a table chunk -> job, filled by the owners,
+            // was measured and was no faster than these seven steps)
             u32 qi = 0;
 #pragma unroll
             for (u32 sft = 64; sft; sft >>= 1)

@@ -219,7 +219,7 @@ BGR_HD u32 job_chunk_miss(const u64* pool, const u64* D, const u64* ND, bool has
     }
     if (flip) {
         y = rc64(y) << ((64 - 2 * m) & 63);
-        nm = rev2(nm) << ((64 - 2 * m) & 63);
+        if (hasN) nm = rev2(nm) << ((64 - 2 * m) & 63);
     }
     u64 d = xu ^ y;
     d = (d | (d >> 1) | nm) & 0x5555555555555555ull;
@@ -972,15 +972,20 @@ struct ExhaustiveState {
     SeedIter it;
     DfsLayout lay;
     u32 flags, phase, n;
-    // current seed
-    u64 seed_c;
+    // current seed: the key slot of its (k-1)-mer and the form of the query (entered through the canonical code
+    // or its reverse complement); every node below it follows the slots' links (USlot::next) instead of hashing
+    // the overlap code again
+    u32 seed_slot;
+    bool seed_canon;
     i32 seed_pos;
     u32 w, eb;  // ints of the final path written so far; mismatches spent on the left side
     // current search (one side)
     u32 budget, best_total, best_n;
     i32 term, depth;
-    // top frame, kept in registers; the frames below it live in the scratch row
-    u64 f_code;
+    // top frame, kept in registers; the frames below it live in the scratch row (4 ints each: slot | canon bit,
+    // pos, acc, next candidate; DfsLayout still reserves the five of the loop-shaped form)
+    u32 f_slot;
+    bool f_canon;
     i32 f_pos;
     u32 f_acc, f_next;
 
@@ -997,12 +1002,14 @@ struct ExhaustiveState {
         n = 0;
         w = eb = 0;
         phase = XP_SEED;
-        seed_c = 0;
+        seed_slot = NO_SLOT;
+        seed_canon = false;
         seed_pos = 0;
         budget = best_total = best_n = 0;
         term = -1;
         depth = -1;
-        f_code = 0;
+        f_slot = NO_SLOT;
+        f_canon = false;
         f_pos = 0;
         f_acc = f_next = 0;
         const u32 km1 = ix.k - 1;
@@ -1026,7 +1033,8 @@ struct ExhaustiveState {
         best_n = 0;
         term = -1;
         depth = 0;
-        f_code = seed_c;
+        f_slot = seed_slot;
+        f_canon = seed_canon;
         f_pos = seed_pos;
         f_acc = 0;
         f_next = 0;
@@ -1043,7 +1051,13 @@ struct ExhaustiveState {
             return;
         }
         seed_pos = p;
-        seed_c = seed_code(ix, s.v, p);
+        {
+            const u64 code = seed_code(ix, s.v, p);
+            const u64 rc = rcb(code, ix.k - 1);
+            seed_canon = code <= rc;
+            const i64 sl = index_find(ix, seed_canon ? code : rc);
+            seed_slot = sl < 0 ? NO_SLOT : (u32)sl;
+        }
         w = 0;
         eb = 0;
         if (p == 0) {
@@ -1058,7 +1072,9 @@ struct ExhaustiveState {
         --depth;
         if (depth >= 0) {
             const u32 b = lay.fr0 + 5 * (u32)depth;
-            f_code = (u64)(u32)sc.get(b) | ((u64)(u32)sc.get(b + 1) << 32);
+            const u32 sc0 = (u32)sc.get(b);
+            f_slot = (sc0 & 0x7FFFFFFFu) == 0x7FFFFFFFu ? NO_SLOT : (sc0 & 0x7FFFFFFFu);
+            f_canon = (sc0 >> 31) != 0;
             f_pos = sc.get(b + 2);
             f_acc = (u32)sc.get(b + 3);
             f_next = (u32)sc.get(b + 4);
@@ -1109,7 +1125,7 @@ struct ExhaustiveState {
             }
             pop_frame();
         } else {
-            const Cands c = index_query(ix, f_code, !right);
+            const Cands c = index_query_at(ix, f_slot, f_canon, !right);
             bool descended = false;
             for (u32 i = f_next; i < (u32)c.n; ++i) {
                 if (f_acc >= best_total) break;  // nothing below can be strictly better
@@ -1138,13 +1154,12 @@ struct ExhaustiveState {
                         }
                         // park this frame (resume with candidate i+1), make the child the top frame
                         const u32 b = lay.fr0 + 5 * (u32)depth;
-                        sc.set(b, (i32)(u32)f_code);
-                        sc.set(b + 1, (i32)(u32)(f_code >> 32));
+                        sc.set(b, (i32)((f_slot & 0x7FFFFFFFu) | (f_canon ? 0x80000000u : 0u)));
                         sc.set(b + 2, f_pos);
                         sc.set(b + 3, (i32)f_acc);
                         sc.set(b + 4, (i32)(i + 1));
                         sc.set(lay.cur0 + (u32)depth, u.sid);
-                        f_code = right ? last_code(ix, u) : first_code(ix, u);
+                        next_query(c.s[i], c.canon, f_slot, f_canon);
                         f_pos = right ? f_pos + (i32)L : f_pos - (i32)L;
                         f_acc += miss;
                         f_next = 0;
