@@ -218,6 +218,32 @@ class Aligner:
                                       pool.ctypes.data, cap, C.byref(used)))
         return MappingResult(res[:n, 0], res[:n, 1], pool[:used.value])
 
+    def map_text(self, text, fastq=False, mode=A.MODE_GREEDY, split_no_overlap=False, flags=0):
+        """A run of whole FASTA / FASTQ records as text -> (regular, n_reads, [paths, notAligned, noOverlap] as
+        bytes): records parsed and the output formatted on the device (bgr_slot_upload_text / bgr_slot_format_text).
+        regular False: the text is not of the regular shape and nothing was mapped."""
+        text = text.encode() if isinstance(text, str) else bytes(text)
+        buf = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, dtype=np.uint8)
+        n, regular = C.c_uint32(0), C.c_int(1)
+        self._ck(self.L.bgr_slot_upload_text(self.ctx, 0, buf.ctypes.data, len(text), int(fastq), C.byref(n), C.byref(regular)))
+        if not regular.value:
+            return False, 0, [b"", b"", b""]
+        p = self.params(mode, flags)
+        self._ck(self.L.bgr_slot_run(self.ctx, 0, C.byref(p)))
+        caps = [64, 64, 64]
+        for _ in range(2):
+            outs = [np.zeros(c, dtype=np.uint8) for c in caps]
+            ptrs = (C.c_void_p * 3)(*[o.ctypes.data for o in outs])
+            cap = (C.c_uint64 * 3)(*caps)
+            used = (C.c_uint64 * 3)()
+            rc = self.L.bgr_slot_format_text(self.ctx, 0, int(split_no_overlap), ptrs, cap, used)
+            if rc == 6:  # BGR_ERR_LIMIT: used[] holds the sizes needed
+                caps = [int(u) + 16 for u in used]
+                continue
+            self._ck(rc)
+            return True, n.value, [outs[f][:int(used[f])].tobytes() for f in range(3)]
+        raise A.BgrError(6, "output buffers")
+
     def counters(self):
         out = (C.c_uint64 * A.BGR_C_COUNT)()
         self._ck(self.L.bgr_counters(self.ctx, out))

@@ -497,8 +497,8 @@ int main(int argc, char** argv) {
         else total_text += range_bytes;  // pipes: size unknown
     }
     const size_t batch_text = std::min(range_bytes, total_text + 4096);
-    // regular FASTA goes through the device's parser and formatter (BGR_TEXT=0: the host stages only)
-    const bool text_path = !o.fastq && !(getenv("BGR_TEXT") && !strcmp(getenv("BGR_TEXT"), "0"));
+    // regular FASTA / FASTQ text goes through the device's parser and formatter (BGR_TEXT=0: the host stages only)
+    const bool text_path = !(getenv("BGR_TEXT") && !strcmp(getenv("BGR_TEXT"), "0"));
     std::thread allocator([&] {
         for (auto& b : batches) {
             if (text_path) b.prealloc_text(batch_text, o.have_o);
@@ -540,7 +540,18 @@ int main(int argc, char** argv) {
                 b->pb.clear();
                 b->text_mode = false;
                 size_t ra = 0, rb = 0;
-                if (text_path && pr.fasta_next_range(ra, rb)) {
+                bool final = false, have = false;
+                std::vector<size_t> cuts;
+                if (!text_path) {
+                    pr.next(b->pb);
+                } else if (!o.fastq) {
+                    have = pr.fasta_next_range(ra, rb);
+                } else if (pr.fastq_tail_pending()) {
+                    pr.fastq_tail(b->pb);  // the end of the stream: the sequential parser, as the reference sees it
+                } else {
+                    have = pr.fastq_next_range(ra, rb, final, &cuts);
+                }
+                if (have) {
                     if (text_ok.load()) {  // hand the text over as it is: copied into the pinned buffer by all workers
                         b->text_mode = true;
                         b->src = mf.data;
@@ -554,11 +565,11 @@ int main(int argc, char** argv) {
                             const size_t lo = nb * w / T, hi = nb * (w + 1) / T;
                             memcpy(b->text.p + lo, mf.data + ra + lo, hi - lo);
                         });
+                    } else if (o.fastq) {
+                        pr.fastq_parse_range(ra, rb, b->pb, &cuts);
                     } else {
                         pr.fasta_parse_range(ra, rb, b->pb);
                     }
-                } else if (!text_path) {
-                    pr.next(b->pb);
                 }
                 b->seq = seq++;
                 parse_s += since(t);
@@ -640,7 +651,7 @@ int main(int argc, char** argv) {
                 if (b->text_mode) {
                     uint32_t n_reads = 0;
                     int regular = 1;
-                    int r = bgr_slot_upload_text(ctx, b->slot, b->text.p, b->text.n, 0, &n_reads, &regular);
+                    int r = bgr_slot_upload_text(ctx, b->slot, b->text.p, b->text.n, o.fastq ? 1 : 0, &n_reads, &regular);
                     if (r == BGR_OK && regular) r = bgr_slot_run(ctx, b->slot, &params);
                     if (r != BGR_OK) {
                         fprintf(stderr, "bgreat: %s\n", bgr_last_error(ctx));
@@ -655,7 +666,8 @@ int main(int argc, char** argv) {
                     text_ok.store(false);
                     b->text_mode = false;
                     b->pb.clear();
-                    parse_fasta_text_sequential(b->src, b->src_a, b->src_b, (uint32_t)o.k, b->pb);
+                    if (o.fastq) parse_fastq_text_sequential(b->src, b->src_a, b->src_b, b->pb);
+                    else parse_fasta_text_sequential(b->src, b->src_a, b->src_b, (uint32_t)o.k, b->pb);
                 }
                 size_t n = b->pb.size();
                 b->res.reserve(n + 1);

@@ -857,21 +857,25 @@ void parse_fasta_text_sequential(const char* d, size_t a, size_t b, uint32_t k, 
     gather(sh, 1, pool, out);
 }
 
-void ParallelReader::next_fastq(ParsedBatch& out) {
-    const size_t a = pos_;
+// The next window of a FASTQ input: [a, b) = whole newline-terminated records (a multiple of getReads' chunk of
+// 10000, so that what follows starts where a getReads call would), cut for T workers; `final`: this window reaches
+// the end of the input, whose last <= 2 chunks are left to the sequential parser (fastq_tail).
+bool ParallelReader::fastq_next_range(size_t& a, size_t& b, bool& final, std::vector<size_t>* cuts) {
+    if (finished_ || tail_pending_) return false;
+    a = pos_;
     const size_t CH = 10000;  // reads per getReads call (alignerGreedy.cpp:376)
     size_t win = range_;
     for (;;) {
-        const bool final = a + win >= n_ || a + win < a;
-        const size_t b = final ? n_ : a + win;
-        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, (b - a) / min_slice_ + 1));
+        final = a + win >= n_ || a + win < a;
+        const size_t e = final ? n_ : a + win;
+        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, (e - a) / min_slice_ + 1));
         // newline counts per slice
         WorkerPool& pool = impl_->pool;
         const auto t0 = std::chrono::steady_clock::now();
         LineIndex li;
-        li.build(d_, a, b, T, pool);
-        const size_t q = li.total() / 4;  // whole newline-terminated records in [a, b)
-        size_t P;                     // records parsed here by the workers
+        li.build(d_, a, e, T, pool);
+        const size_t q = li.total() / 4;  // whole newline-terminated records in [a, e)
+        size_t P;                     // records parsed by the workers (or the device)
         if (final) P = q ? ((q - 1) / CH) * CH : 0;  // the last <= 2*CH records go to the sequential parser
         else P = (q / CH) * CH;
         if (!final && P == 0) {  // not even one getReads chunk in the window: look further
@@ -883,42 +887,74 @@ void ParallelReader::next_fastq(ParsedBatch& out) {
             if (r == 0) return a;
             return li.after(d_, 4 * r);  // 1-based newline number
         };
-        std::vector<size_t> cut(T + 1);
-        pool.run(T, [&](unsigned t) { cut[t] = record_start(P / T * t); });
-        cut[T] = record_start(P);
-        const auto t1 = std::chrono::steady_clock::now();
-        std::vector<Shard>& sh = impl_->shards(T);
-        pool.run(T, [&](unsigned t) {
-            if (cut[t] < cut[t + 1]) parse_fastq_range(d_, cut[t], cut[t + 1], sh[t]);
-        });
-        const auto t2 = std::chrono::steady_clock::now();
-        gather(sh, T, pool, out);
-        const auto t3 = std::chrono::steady_clock::now();
-        phase_s[0] += std::chrono::duration<double>(t1 - t0).count();
-        phase_s[1] += std::chrono::duration<double>(t2 - t1).count();
-        phase_s[2] += std::chrono::duration<double>(t3 - t2).count();
-        pos_ = cut[T];
-        if (final) {
-            // the end of the stream, exactly as the reference sees it
-            ReadParser rp(d_ + pos_, n_ - pos_, k_, true);
-            ReadBatch tail;
-            while (!rp.done()) rp.next_chunk((uint32_t)CH, tail);
-            const size_t nt = tail.size();
-            out.arena.assign(tail.headers.p, tail.headers.p + tail.headers.n);
-            out.seqs.reserve(out.seqs.n + tail.seqs.n + 64);
-            out.soff.reserve(out.soff.n + nt + 1);
-            for (size_t i = 0; i < nt; ++i) {
-                const size_t sn = tail.soff.p[i + 1] - tail.soff.p[i];
-                memcpy(out.seqs.p + out.seqs.n, tail.seqs.p + tail.soff.p[i], sn);
-                out.seqs.n += sn;
-                out.soff.p[out.soff.n++] = out.seqs.n;
-                out.hdr.push(HdrView{out.arena.data() + tail.hoff.p[i], (uint32_t)(tail.hoff.p[i + 1] - tail.hoff.p[i])});
-            }
-            pos_ = n_;
-            finished_ = true;
+        if (cuts) {
+            cuts->assign(T + 1, 0);
+            pool.run(T, [&](unsigned t) { (*cuts)[t] = record_start(P / T * t); });
+            (*cuts)[T] = record_start(P);
+            b = (*cuts)[T];
+        } else {
+            b = record_start(P);
         }
-        return;
+        phase_s[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        pos_ = b;
+        if (final) tail_pending_ = true;
+        return true;
     }
+}
+
+// the end of the stream, exactly as the reference sees it (phantom duplicate of the last read, truncated record)
+void ParallelReader::fastq_tail(ParsedBatch& out) {
+    if (!tail_pending_) return;
+    const size_t CH = 10000;
+    ReadParser rp(d_ + pos_, n_ - pos_, k_, true);
+    ReadBatch tail;
+    while (!rp.done()) rp.next_chunk((uint32_t)CH, tail);
+    const size_t nt = tail.size();
+    out.arena.assign(tail.headers.p, tail.headers.p + tail.headers.n);
+    out.seqs.reserve(out.seqs.n + tail.seqs.n + 64);
+    out.soff.reserve(out.soff.n + nt + 1);
+    for (size_t i = 0; i < nt; ++i) {
+        const size_t sn = tail.soff.p[i + 1] - tail.soff.p[i];
+        memcpy(out.seqs.p + out.seqs.n, tail.seqs.p + tail.soff.p[i], sn);
+        out.seqs.n += sn;
+        out.soff.p[out.soff.n++] = out.seqs.n;
+        out.hdr.push(HdrView{out.arena.data() + tail.hoff.p[i], (uint32_t)(tail.hoff.p[i + 1] - tail.hoff.p[i])});
+    }
+    pos_ = n_;
+    tail_pending_ = false;
+    finished_ = true;
+}
+
+void ParallelReader::fastq_parse_range(size_t a, size_t b, ParsedBatch& out, const std::vector<size_t>* cuts) {
+    WorkerPool& pool = impl_->pool;
+    std::vector<size_t> one{a, b};
+    const std::vector<size_t>& cut = cuts ? *cuts : one;
+    const unsigned T = (unsigned)cut.size() - 1;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::vector<Shard>& sh = impl_->shards(T);
+    pool.run(T, [&](unsigned t) {
+        if (cut[t] < cut[t + 1]) parse_fastq_range(d_, cut[t], cut[t + 1], sh[t]);
+    });
+    const auto t2 = std::chrono::steady_clock::now();
+    gather(sh, T, pool, out);
+    const auto t3 = std::chrono::steady_clock::now();
+    phase_s[1] += std::chrono::duration<double>(t2 - t1).count();
+    phase_s[2] += std::chrono::duration<double>(t3 - t2).count();
+}
+
+void ParallelReader::next_fastq(ParsedBatch& out) {
+    size_t a, b;
+    bool final = false;
+    std::vector<size_t> cuts;
+    if (fastq_next_range(a, b, final, &cuts)) fastq_parse_range(a, b, out, &cuts);
+    if (final) fastq_tail(out);
+}
+
+void parse_fastq_text_sequential(const char* d, size_t a, size_t b, ParsedBatch& out) {
+    std::vector<Shard> sh(1);
+    if (a < b) parse_fastq_range(d, a, b, sh[0]);
+    WorkerPool pool(0);
+    gather(sh, 1, pool, out);
 }
 
 // ------------------------------------------------------------------------------ parallel unitig loader

@@ -216,6 +216,13 @@ class ParallelReader {
     // (bgr_slot_upload_text): the next range [a, b) of whole records (false: the input is used up), and its parse
     bool fasta_next_range(size_t& a, size_t& b);
     void fasta_parse_range(size_t a, size_t b, ParsedBatch& out);
+    // FASTQ likewise: [a, b) = whole newline-terminated records; `final`: the input's last records (at most two
+    // getReads chunks) are still to come and are parsed by fastq_tail, sequentially, with the reference's
+    // end-of-stream behaviour. cuts: the range cut for the workers of fastq_parse_range (optional).
+    bool fastq_next_range(size_t& a, size_t& b, bool& final, std::vector<size_t>* cuts = nullptr);
+    void fastq_parse_range(size_t a, size_t b, ParsedBatch& out, const std::vector<size_t>* cuts = nullptr);
+    bool fastq_tail_pending() const { return tail_pending_; }
+    void fastq_tail(ParsedBatch& out);
     // wall time spent so far in the phases of next(): cutting (FASTQ: counting lines), parsing, copying (diagnostics)
     double phase_s[3] = {0, 0, 0};
 
@@ -228,13 +235,15 @@ class ParallelReader {
     const char* d_;
     size_t n_, pos_ = 0, range_, min_slice_;
     uint32_t k_;
-    bool fastq_, finished_ = false;
+    bool fastq_, finished_ = false, tail_pending_ = false;
     unsigned threads_;
     Impl* impl_;
 };
 
 // the FASTA records of d[a, b) (a a record start, b a record start or the end of the input) on the calling thread
 void parse_fasta_text_sequential(const char* d, size_t a, size_t b, uint32_t k, ParsedBatch& out);
+// the same for whole 4-line FASTQ records
+void parse_fastq_text_sequential(const char* d, size_t a, size_t b, ParsedBatch& out);
 
 // load_unitig_file on `threads` workers: records are two lines whatever they contain, so newlines are
 // counted in parallel and every worker takes whole records; the last record goes through the sequential
