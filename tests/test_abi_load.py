@@ -89,3 +89,60 @@ def test_host_packer_through_the_abi_needs_no_gpu():
             assert int(words[w]) == v, w
     # argument checks
     assert L.bgr_pack_reads(buf.ctypes.data, None, 1, 1, words.ctypes.data, bad.ctypes.data, None) == 2  # BGR_ERR_ARG
+
+
+def _prototypes():
+    """-> {name: (return type, [parameter types])} parsed from include/bgreat_b200.h"""
+    text = open(os.path.join(ROOT, "include", "bgreat_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z_0-9 \*]*?)\b(bgr_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        plist = []
+        if params and params != "void":
+            for p in params.split(","):
+                p = p.strip()
+                is_ptr = "*" in p or "[" in p
+                base = re.sub(r"\b(const|struct)\b", "", p)
+                base = re.sub(r"\[.*\]", "", base).replace("*", " ").split()
+                plist.append((base[0], is_ptr))
+        out[name] = (ret, plist)
+    return out
+
+
+def test_ctypes_signatures_match_the_header():
+    """bgreat_b200/_abi.py declares every signature by hand: number of parameters, pointer-ness and integer width
+    of each, and the return type are checked against the prototypes of include/bgreat_b200.h; so are the two structs."""
+    import ctypes as C
+    from bgreat_b200 import _abi as A
+    L = A.lib()
+    width = {"int": C.c_int, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "int32_t": C.c_int32}
+    protos = _prototypes()
+    assert sorted(protos) == sorted(A.SYMBOLS)
+    for name, (ret, params) in protos.items():
+        fn = getattr(L, name)
+        if params:
+            assert fn.argtypes is not None and len(fn.argtypes) == len(params), name
+            for i, ((base, is_ptr), ct) in enumerate(zip(params, fn.argtypes)):
+                ct_is_ptr = ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "contents") or issubclass(ct, C._Pointer)
+                assert ct_is_ptr == is_ptr, (name, i, base)
+                if not is_ptr:
+                    assert C.sizeof(ct) == C.sizeof(width[base]), (name, i, base)
+        if ret == "void":
+            assert fn.restype is None, name
+        elif "char" in ret:
+            assert fn.restype is C.c_char_p, name
+        elif ret == "uint64_t":
+            assert fn.restype is C.c_uint64, name
+        else:
+            assert ret == "int" and fn.restype in (C.c_int, None.__class__) or fn.restype is C.c_int, name
+    text = open(os.path.join(ROOT, "include", "bgreat_b200.h")).read()
+    for sname, ctype in (("bgr_params", A.Params),):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (sname, sname), text, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = re.findall(r"(uint32_t|uint64_t|int32_t)\s+(\w+)\s*;", body)
+        assert [f for _, f in fields] == [f for f, _ in ctype._fields_]
+        assert C.sizeof(ctype) == sum(C.sizeof(width[t]) for t, _ in fields)
+    body = re.search(r"typedef struct bgr_result \{(.*?)\} bgr_result;", text, flags=re.S).group(1)
+    assert re.findall(r"uint32_t\s+(\w+)\s*;", re.sub(r"/\*.*?\*/", "", body, flags=re.S)) == ["flags_len", "path_off"]
