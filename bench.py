@@ -672,11 +672,25 @@ def run_b200_arm(args):
     model_scan = model["windows"] * 32.0 + 40.0
     model_ext = 32.0 * model["queries"] + model["compares"] * (16 + 32.0) + 17
 
+    try:
+        rnd = json.load(open(os.path.join(ROOT, "profiles", "hbm_random.json")))
+    except Exception:
+        rnd = None
+
     def roof(name, kernel_key, ms_, need, model_b, bound_note):
         ach = need * n_reads / (ms_ / 1e3) / 1e9
         tr = measured_traffic(kernel_key)
+        tr_gbs = None if tr is None else tr / (ms_ / 1e3) / 1e9
+        random_access = None
+        if tr_gbs is not None and rnd is not None and large:
+            # on an index far larger than L2 the kernels' DRAM traffic is random 64-byte fetches: their rate against
+            # the rate a plain random-read kernel reaches on this GPU (profiles/hbm_random.json)
+            random_access = {"fetches_per_s": tr_gbs * 1e9 / 64.0, "dram_gbs": tr_gbs,
+                             "ceiling_dram_gbs": rnd["dram_gbs_when_every_access_fetches_64B"],
+                             "frac_of_ceiling": tr_gbs / rnd["dram_gbs_when_every_access_fetches_64B"],
+                             "ceiling_source": rnd["source"]}
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": tr, "traffic_achieved_gbs": None if tr is None else tr / (ms_ / 1e3) / 1e9,
+                "traffic": tr, "traffic_achieved_gbs": tr_gbs, "random_access": random_access,
                 "necessary_bytes_per_read": need, "necessary_bytes_per_launch": need * n_reads, "kernel_ms": ms_,
                 "model_bytes_per_read": model_b, "model_frac": model_b * n_reads / (ms_ / 1e3) / 1e9 / peak,
                 "binding": bound_note, "peak_source": peak_src}

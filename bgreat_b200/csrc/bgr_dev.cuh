@@ -85,7 +85,6 @@ struct BatchArgs {
     u32 tile_cb;     // bytes of one character buffer of the tile kernel
     u32 errors, effort, mode;
     u32 ext_lazy;  // greedy extension: lanes that must wait before hand-in / refill / seed selection run
-    u32 scan_hints;  // seed scan on a large index: filter loads marked evict-last in L2, packed words and hit masks stored streaming
     u64* corr;  // correction mode (-c): corrected reads, 2 bits per base, read r at word corrected_word_base(off[r], r)
 };
 

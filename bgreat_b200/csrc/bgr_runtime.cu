@@ -274,8 +274,6 @@ BatchArgs make_args(Slot& s) {
     a.mode = s.params.mode;
     a.ext_lazy = 24;  // measured: 8 -> 24 takes 10 % off the greedy kernel (fewer, fuller service rounds)
     if (const char* e = getenv("BGR_EXT_LAZY")) a.ext_lazy = (u32)std::max(1, std::min(32, atoi(e)));
-    a.scan_hints = 0;
-    if (const char* e = getenv("BGR_SCAN_HINTS")) a.scan_hints = (u32)atoi(e);
     a.corr = s.d_corr;
     return a;
 }

@@ -441,15 +441,11 @@ BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, const u32* pat, u32 km1_rt,
 // Two variants were measured at 3 Gbp and lost: requesting a chunk's blocks ahead of the test (a first pass that only
 // computes the minimizers, prefetches and lists the block numbers: 6.8 ms, twice the L2 sectors), and a bit map over
 // a sparser block array so that only occupied blocks are fetched (8.8 ms: two dependent loads per run of windows).
+// L2 cache hints (filter loads evict-last, the packed words and hit masks stored streaming) changed nothing at any
+// graph size (6.30 against 6.33 ms at 3 Gbp).
 // blocks: the filter as 64-bit blocks; pat: bloom_pattern64 table.
-BGR_HD u32 scan_chunk_mm(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0, u64 w1, u32 count, bool keep_in_l2 = false) {
+BGR_HD u32 scan_chunk_mm(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0, u64 w1, u32 count) {
     const u32 sh = 64 - 2 * MM_KM1, top = 2 * (MM_KM1 - 1);
-#if defined(__CUDA_ARCH__)
-    u64 keep_policy = 0;
-    if (keep_in_l2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
-#else
-    (void)keep_in_l2;
-#endif
     const u64 mask = ~0ull >> sh;
     u64 num = w0 >> sh;
     u64 rc = rcb(num, MM_KM1);
@@ -488,10 +484,7 @@ BGR_HD u32 scan_chunk_mm(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0
         if (b != cur) {
             cur = b;
 #if defined(__CUDA_ARCH__)
-            if (keep_in_l2)
-                asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(blk) : "l"(blocks + b), "l"(keep_policy));
-            else
-                blk = __ldg((const unsigned long long*)blocks + b);
+            blk = __ldg((const unsigned long long*)blocks + b);
 #else
             blk = blocks[b];
 #endif
@@ -629,29 +622,22 @@ __device__ __forceinline__ u32 tile_chunk(const DevIndex& ix, const BatchArgs& a
     // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads)
     u64* gF = a.F + wb;
     const u32 nw = (rlen + 31) >> 5;
-    const bool stream = !BLOOM_SMEM && a.scan_hints != 0;  // written once, read once by the extension kernel: keep L2 for the filter
-    auto put = [&](u64* p, u64 v) {
-        if (stream) __stcs((unsigned long long*)p, (unsigned long long)v);
-        else *p = v;
-    };
-    put(&gF[1 + l], w0);
-    if (l == 0) put(&gF[0], 0);
+    gF[1 + l] = w0;
+    if (l == 0) gF[0] = 0;
     if (l + 1 == rchunks) {
-        if (l + 1 < nw) put(&gF[2 + l], w1);
-        put(&gF[nw + 1], 0);
-        put(&gF[nw + 2], 0);
+        if (l + 1 < nw) gF[2 + l] = w1;
+        gF[nw + 1] = 0;
+        gF[nw + 2] = 0;
     }
     const u32 count = min(32u, rnwin - 32 * l);
     // the shared-memory tier is the single-hash tier; large indexes of 31-mers have the minimizer filter, other
     // k the two-hash word filter (bloom_layout)
     u32 hits;
-    if (!BLOOM_SMEM && KM1S == MM_KM1)
-        hits = scan_chunk_mm((const u64*)bloom, ix.n_bloom / 2, (const u64*)pat, w0, w1, count, a.scan_hints != 0);
+    if (!BLOOM_SMEM && KM1S == MM_KM1) hits = scan_chunk_mm((const u64*)bloom, ix.n_bloom / 2, (const u64*)pat, w0, w1, count);
     else hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, pat, km1, w0, w1, count);
     const u32 passed = (u32)__popc(hits);
     hits = verify_chunk<1>(ix, w0, w1, hits);
-    if (stream) __stcs(&a.H1[wb + l], hits);
-    else a.H1[wb + l] = hits;
+    a.H1[wb + l] = hits;
     const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
     if (fl) atomicOr(&s_flags[rd], fl);
     return passed;

@@ -74,7 +74,6 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
     a.tile_r = 0;
     a.tile_cb = 0;
     a.ext_lazy = 8;
-    a.scan_hints = 0;
     a.errors = errors;
     a.effort = effort;
     a.mode = mode;

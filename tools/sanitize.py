@@ -25,4 +25,13 @@ assert a == b
 c = al.align_batch(reads[:20000], 1).as_tuples()
 d = al.align_batch_packed(reads[:20000], 1, threads=4).as_tuples()
 assert c == d
-print("ok", len(reads), sum(1 for x in a if x[2]), sum(1 for x in c if x[2]))
+# the large-index filter tier (minimizer blocks) and a text batch (records parsed / output formatted on the device)
+os.environ["BGR_BLOOM"] = "global"
+al2 = bgreat_b200.Aligner(31, 2, 2)
+al2.index_unitigs(unitigs)
+e = al2.align_batch(reads[:30000], 0).as_tuples()
+assert e == a[:30000]
+text = "".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(reads[:30000]))
+regular, n_text, streams = al2.map_text(text, False, 0, True)
+assert regular and n_text > 0 and sum(len(x) for x in streams) > 0
+print("ok", len(reads), sum(1 for x in a if x[2]), sum(1 for x in c if x[2]), n_text)
