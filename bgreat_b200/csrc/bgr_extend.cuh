@@ -297,6 +297,52 @@ struct SeedIter {
     }
 };
 
+// The same walk for reads of at most 128 windows whose hit mask sits in two registers (the usual read: 150 bases,
+// 121 windows): no loop, no load. lo = windows 0..63, hi = 64..127; cur / lim / nwin / down as in SeedIter.
+// In the greedy kernel seed selection is run for a few lanes at a time, and SeedIter's loop -- one trip per empty
+// mask word, a load each -- ran with 5 of 32 lanes on average (profiles/r02_lines_k_extend_greedy_5Mbp.txt).
+BGR_HD i32 seed_next128(u64 lo, u64 hi, i32 nwin, i32 lim, bool down, i32& cur) {
+    if (cur >= lim) return -1;
+    i32 p;
+    if (!down) {
+        // first set bit at or after cur
+        const u32 s = (u32)cur;
+        const u64 a = s >= 64 ? (hi >> (s & 63)) : ((lo >> s) | (s ? hi << (64 - s) : 0ull));
+        const u64 b = s >= 64 ? 0ull : (hi >> s);
+        if ((a | b) == 0) {
+            cur = lim;
+            return -1;
+        }
+#if defined(__CUDA_ARCH__)
+        const i32 z = a ? __ffsll((long long)a) - 1 : 64 + __ffsll((long long)b) - 1;
+#else
+        const i32 z = a ? __builtin_ctzll(a) : 64 + __builtin_ctzll(b);
+#endif
+        p = cur + z;
+    } else {
+        // highest set bit at or below j = nwin-1-cur, as a distance from j
+        const u32 s = 127u - (u32)(nwin - 1 - cur);  // left shift that brings bit j to bit 127
+        const u64 a = s >= 64 ? (lo << (s & 63)) : ((hi << s) | (s ? lo >> (64 - s) : 0ull));
+        const u64 b = s >= 64 ? 0ull : (lo << s);
+        if ((a | b) == 0) {
+            cur = lim;
+            return -1;
+        }
+#if defined(__CUDA_ARCH__)
+        const i32 z = a ? __clzll((long long)a) : 64 + __clzll((long long)b);
+#else
+        const i32 z = a ? __builtin_clzll(a) : 64 + __builtin_clzll(b);
+#endif
+        p = cur + z;
+    }
+    if (p >= lim) {
+        cur = lim;
+        return -1;
+    }
+    cur = p + 1;
+    return p;
+}
+
 // ------------------------------------------------------------------------------ greedy extension
 
 // checkBeginGreedy == mapOnLeftEndGreedy (alignerGreedy.cpp:268-319,167-218), tail recursion
@@ -496,6 +542,8 @@ struct GreedyState {
     Scratch sc;
     SeedIter it;
     u32 flags, n, nl, tried, phase;
+    u64 hm_lo, hm_hi;  // the pass's hit mask, when it fits (hm_ok): seed_next128 instead of the iterator's loop
+    bool hm_ok;
     // walk state: the key slot and query form of the current level, and of the seed
     u32 slot, seed_slot;
     bool canon, seed_canon;
@@ -517,6 +565,16 @@ struct GreedyState {
         phase = GP_SEED;
         // effort 0: getNOverlap returns right after the first window, hit or not (aligner.cpp:366)
         it.init(a.H1 + s.wb, (s.info & INFO_HIT1) ? s.nwin : 0, false, a.effort ? s.nwin : 1);
+        // reads without N use the same mask for both passes (pass 1 walks it from the top)
+        hm_ok = !s.v.hasN && s.nwin <= 128;
+        hm_lo = hm_hi = 0;
+        if (hm_ok && (s.info & INFO_HIT1)) {
+            const u32* h = a.H1 + s.wb;
+            const i32 nw32 = (s.nwin + 31) >> 5;
+            const u64 w0 = nw32 > 0 ? h[0] : 0u, w1 = nw32 > 1 ? h[1] : 0u, w2 = nw32 > 2 ? h[2] : 0u, w3 = nw32 > 3 ? h[3] : 0u;
+            hm_lo = w0 | (w1 << 32);
+            hm_hi = w2 | (w3 << 32);
+        }
         slot = seed_slot = NO_SLOT;
         canon = seed_canon = false;
         pos = seed_pos = 0;
@@ -544,7 +602,8 @@ struct GreedyState {
         ReadView& v = s.v;
         const u32 max_seeds = a.effort ? a.effort : 1;
         for (int rep = 0; rep < 2 && phase == GP_SEED; ++rep) {
-            i32 p = tried < max_seeds ? it.next() : -1;
+            i32 p = -1;
+            if (tried < max_seeds) p = hm_ok ? seed_next128(hm_lo, hm_hi, it.nwin, it.lim, it.down, it.cur) : it.next();
             if (p >= 0) {
                 ++tried;
                 const u64 code = seed_code(ix, v, p);
@@ -593,11 +652,19 @@ struct GreedyState {
         return slot == NO_SLOT ? nullptr : entry_side(ix, slot, canon, phase == GP_LEFT);
     }
 
-    // ---- stage 2: comparison geometry of the level's candidates
+    // ---- stage 2: comparison geometry of the level's candidates. One formula for the three kinds of level (lanes
+    // of a warp are at different kinds; as three branches this stage ran with 10 of 32 lanes):
+    //   left walk   rem = pos                 unitig covers the rest: unitig[L-pos, L) vs read[0, pos)
+    //                                         else:                   unitig[0, L)     vs read[pos-L, pos)
+    //   right first rem = len - (pos + k-1)   comparisons start after the anchor overlap: unitig[k-1, ..) vs read[pos+k-1, ..)
+    //   right more  rem = len - pos           the remaining read starts AT the overlap; the whole unitig is compared,
+    //                                         cut at the read end (quirk 8): unitig[0, ..) vs read[pos, ..)
     BGR_HD void level_jobs(const DevIndex& ix, const USlot sl[4], int nc, GreedyLevel& lv) const {
         const ReadView& v = s.v;
         const i32 km1 = (i32)ix.k - 1;
         const u32 fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+        const bool left = phase == GP_LEFT, first = phase == GP_RIGHT_FIRST, more = phase == GP_RIGHT_MORE;
+        const i32 rem = left ? pos : (first ? v.len - pos - km1 : v.len - pos);
         lv.n = nc;
         lv.ends = 0;
 #pragma unroll
@@ -607,30 +674,11 @@ struct GreedyState {
             if (i < nc) {
                 const Oriented u = orient_slot(sl[i], fwd_bit);
                 const i32 L = (i32)(u.len - km1);
-                bool ends_here;
-                i64 upos;
-                i32 rpos, nn;
-                if (phase == GP_LEFT) {
-                    // unitig covers the rest: unitig[L-pos, L) vs read[0,pos); else unitig[0,L) vs read[pos-L,pos)
-                    ends_here = L >= pos;
-                    upos = ends_here ? L - pos : 0;
-                    rpos = ends_here ? 0 : pos - L;
-                    nn = ends_here ? pos : L;
-                } else if (phase == GP_RIGHT_FIRST) {
-                    // comparisons start after the anchor overlap
-                    const i32 rstart = pos + km1, rl = v.len - rstart;
-                    ends_here = L >= rl;
-                    upos = km1;
-                    rpos = rstart;
-                    nn = ends_here ? rl : L;
-                } else {
-                    // the remaining read starts AT the overlap; whole unitig compared, cut at the read end
-                    const i32 rl = v.len - pos;
-                    ends_here = L >= rl;
-                    upos = 0;
-                    rpos = pos;
-                    nn = ends_here ? rl : (i32)(u.len < rl ? u.len : rl);
-                }
+                const bool ends_here = L >= rem;
+                const i64 upos = left ? (ends_here ? (i64)(L - pos) : 0) : (first ? (i64)km1 : 0);
+                const i32 rpos = left ? (ends_here ? 0 : pos - L) : (first ? pos + km1 : pos);
+                const i32 whole = more ? (i32)(u.len < rem ? u.len : rem) : L;
+                const i32 nn = ends_here ? rem : whole;
                 lv.job[i] = make_job(v, u, upos, rpos, nn);
                 lv.L[i] = L;
                 lv.ends |= (ends_here ? 1u : 0u) << i;
@@ -641,39 +689,34 @@ struct GreedyState {
     // ---- stage 3: settle the level. miss[i] = mismatches of candidate i (any value above the budget counts as
     // budget+1, the cap of missmatchNumber)
     BGR_HD void level_settle(const BatchArgs& a, const USlot sl[4], const GreedyLevel& lv, const u32 miss[4]) {
-        u32 best = budget + 1;
+        // the reference's choice, without branches: first strictly smallest; a zero is taken at once (quirk 9)
+        u32 best = budget + 1, b_idf = 0, b_next = 0;
+        i32 bL = 0;
         int bi = -1;
         bool accepted = false;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (i < lv.n && !accepted) {
-                const u32 m = miss[i] < budget + 1 ? miss[i] : budget + 1;
-                if (m < best) {  // first strictly smallest; a zero is taken at once (quirk 9)
-                    best = m;
-                    bi = i;
-                    accepted = m == 0;
-                }
-            }
+            const u32 m = miss[i] < budget + 1 ? miss[i] : budget + 1;
+            const bool take = i < lv.n && !accepted && m < best;
+            best = take ? m : best;
+            bi = take ? i : bi;
+            b_idf = take ? sl[i].id_flags : b_idf;
+            b_next = take ? sl[i].next : b_next;
+            bL = take ? lv.L[i] : bL;
+            accepted = accepted || (take && m == 0);
         }
         if (bi < 0) {
             phase = GP_SEED;  // this seed failed
             return;
         }
-        const u32 fwd_bit = canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
-        USlot bs = sl[0];
-        i32 bL = lv.L[0];
-#pragma unroll
-        for (int i = 1; i < 4; ++i)
-            if (bi == i) {
-                bs = sl[i];
-                bL = lv.L[i];
-            }
-        const Oriented u = orient_slot(bs, fwd_bit);
+        const u32 id = b_idf & SLOT_ID_MASK;
+        const bool urc = (b_idf & (canon ? SLOT_FWD_CANON : SLOT_FWD_RC)) == 0;
         const bool ended = (lv.ends >> bi) & 1u;
-        sc.set(n++, u.sid);
+        const bool left = phase == GP_LEFT;
+        sc.set(n++, urc ? -(i32)id : (i32)id);
         // an exact candidate leaves the budget untouched, an inexact one pays for its mismatches
         if (ended) {
-            if (phase == GP_LEFT) {
+            if (left) {
                 sc.set(n++, bL - pos);
                 eb = acc + best;
                 go_right(a);
@@ -683,12 +726,13 @@ struct GreedyState {
         } else {
             acc += best;
             budget -= best;
+            USlot bs;
+            bs.start_len = 0;
+            bs.id_flags = b_idf;
+            bs.next = b_next;
             next_query(bs, canon, slot, canon);
-            if (phase == GP_LEFT) pos -= bL;
-            else {
-                pos += bL;
-                phase = GP_RIGHT_MORE;
-            }
+            pos += left ? -bL : bL;
+            phase = left ? (u32)GP_LEFT : (u32)GP_RIGHT_MORE;
         }
     }
 

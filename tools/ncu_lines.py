@@ -48,7 +48,7 @@ def line_table(kernel):
 
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
-    top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 40
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -74,6 +74,36 @@ def main():
         tot[2] += ss
     src = {}
     print("total: %d warp inst, %d thread inst, %d samples" % tuple(tot))
+    if "--by-function" in sys.argv:
+        # the same sums per enclosing function (the nearest preceding definition in the source file)
+        fagg = defaultdict(lambda: [0, 0, 0])
+        cache = {}
+
+        def func_of(line):
+            if not line:
+                return "?"
+            fn = os.path.join(ROOT, "bgreat_b200", "csrc", line[0])
+            if fn not in cache:
+                cache[fn] = open(fn).read().splitlines() if os.path.exists(fn) else []
+            L = cache[fn]
+            for i in range(min(line[1], len(L)) - 1, -1, -1):
+                m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:BGR_HD|__device__ __forceinline__|__global__)\b.*?\b(\w+)\s*\(", L[i])
+                if m:
+                    return "%s:%s" % (line[0], m.group(1))
+                m = re.match(r"\s*// ---- (.*)", L[i])
+                if m and line[0] == "bgr_emit.cuh":
+                    return "%s:[%s]" % (line[0], m.group(1)[:40])
+            return line[0]
+        for line, a in agg.items():
+            f = fagg[func_of(line)]
+            f[0] += a[0]
+            f[1] += a[1]
+            f[2] += a[2]
+        print("%-64s %9s %6s %8s %6s %5s" % ("function", "warp-inst", "%", "samples", "%", "thr"))
+        for f, a in sorted(fagg.items(), key=lambda kv: -kv[1][0])[:top]:
+            print("%-64s %8.1fM %5.1f%% %8d %5.1f%% %5.1f" % (f, a[0] / 1e6, 100.0 * a[0] / max(tot[0], 1), a[2],
+                                                              100.0 * a[2] / max(tot[2], 1), a[1] / max(a[0], 1)))
+        return
     print("%-26s %8s %6s %8s %6s %5s  %s" % ("line", "warp-inst", "%", "samples", "%", "thr", "source"))
     for line, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         text = ""
