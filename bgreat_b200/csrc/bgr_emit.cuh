@@ -153,6 +153,66 @@ struct ExtWarpShared {
     u32 miss[128];
 };
 
+// Steps 1b and 2 of a turn, for both extension kernels: lane's jobs lv.job[0..nc) (q: the lane has any) go to shared
+// memory with a prefix sum of their chunk counts, the chunks of all jobs are dealt to the 32 lanes, and every lane
+// gets back the mismatch counts of its own jobs (exact: not capped).
+__device__ __forceinline__ void warp_compare(ExtWarpShared& W, const DevIndex& ix, const BatchArgs& a, const u32 lane, const bool q,
+                                             const int nc, const GreedyLevel& lv, const u64 wofs, const bool hasN, const bool pass,
+                                             u32 miss[4]) {
+    u32 cnt[4], mine = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        cnt[c] = (q && c < nc) ? (u32)(lv.job[c].n + 31) >> 5 : 0u;
+        mine += cnt[c];
+    }
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += x;
+    }
+    const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    {
+        u32 at = incl - mine;
+        const u32 jf = (hasN ? 2u : 0u) | (pass ? 4u : 0u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const u32 qi = 4 * lane + c;
+            W.start[qi] = at;
+            W.miss[qi] = 0;
+            if (cnt[c]) {
+                ExtJob j;
+                j.ua = lv.job[c].ua;
+                j.wofs = wofs;
+                j.sa = lv.job[c].sa;
+                j.n = lv.job[c].n;
+                j.flags = (lv.job[c].flip ? 1u : 0u) | jf;
+                j.pad = 0;
+                W.job[qi] = j;
+            }
+            at += cnt[c];
+        }
+    }
+    __syncwarp();
+    for (u32 j = lane; j < total; j += 32) {
+        // its job: the last one whose first chunk is at or before j (a table chunk -> job, filled by the owners,
+        // was measured and was no faster than these seven steps)
+        u32 qi = 0;
+#pragma unroll
+        for (u32 sft = 64; sft; sft >>= 1)
+            if (W.start[qi + sft] <= j) qi += sft;
+        const ExtJob job = W.job[qi];
+        const i32 done = (i32)(j - W.start[qi]) * 32;
+        const u32 m = job_chunk_miss(ix.pool, a.F + job.wofs, a.NM + job.wofs, (job.flags & 2u) != 0, (job.flags & 4u) != 0,
+                                     job.ua, job.sa, job.n, (job.flags & 1u) != 0, done);
+        if (m) atomicAdd(&W.miss[qi], m);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) miss[c] = W.miss[4 * lane + c];
+    __syncwarp();  // the next turn overwrites the tables
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix, BatchArgs a) {
     __shared__ __align__(16) ExtWarpShared wsh_all[EXT_THREADS / 32];
@@ -227,73 +287,22 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_greedy(DevIndex ix
             }
             g.level_jobs(ix, sl, nc, lv);
         }
-        u32 cnt[4], mine = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            cnt[c] = (q && c < nc) ? (u32)(lv.job[c].n + 31) >> 5 : 0u;
-            mine += cnt[c];
-        }
-        u32 incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (u32)d) incl += x;
-        }
-        const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        {
-            u32 at = incl - mine;
-            const u32 jf = (g.s.v.hasN ? 2u : 0u) | (g.s.v.pass ? 4u : 0u);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const u32 qi = 4 * lane + c;
-                W.start[qi] = at;
-                W.miss[qi] = 0;
-                if (cnt[c]) {
-                    ExtJob j;
-                    j.ua = lv.job[c].ua;
-                    j.wofs = g.s.wb + 1;
-                    j.sa = lv.job[c].sa;
-                    j.n = lv.job[c].n;
-                    j.flags = (lv.job[c].flip ? 1u : 0u) | jf;
-                    j.pad = 0;
-                    W.job[qi] = j;
-                }
-                at += cnt[c];
-            }
-        }
-        __syncwarp();
-        // ---- 2. all chunks of all jobs, dealt to the 32 lanes
-        for (u32 j = lane; j < total; j += 32) {
-            // its job: the last one whose first chunk is at or before j (a table chunk -> job, filled by the owners,
-            // was measured and was no faster than these seven steps)
-            u32 qi = 0;
-#pragma unroll
-            for (u32 sft = 64; sft; sft >>= 1)
-                if (W.start[qi + sft] <= j) qi += sft;
-            const ExtJob job = W.job[qi];
-            const i32 done = (i32)(j - W.start[qi]) * 32;
-            const u32 m = job_chunk_miss(ix.pool, a.F + job.wofs, a.NM + job.wofs, (job.flags & 2u) != 0, (job.flags & 4u) != 0,
-                                         job.ua, job.sa, job.n, (job.flags & 1u) != 0, done);
-            if (m) atomicAdd(&W.miss[qi], m);
-        }
-        __syncwarp();
+        u32 miss[4];
+        warp_compare(W, ix, a, lane, q, nc, lv, g.s.wb + 1, g.s.v.hasN, g.s.v.pass, miss);
         // ---- 3. settle
-        if (q) {
-            u32 miss[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) miss[c] = W.miss[4 * lane + c];
-            g.level_settle(a, sl, lv, miss);
-        }
-        __syncwarp();
+        if (q) g.level_settle(a, sl, lv, miss);
     }
     if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
     count_classes(a, n_al, n_na, n_no);
 }
 
-// alignReadExhaustive / alignReadExhaustivePath as persistent warps (same life cycle as k_extend_greedy):
-// every lane runs one node of its read's search per turn.
+// alignReadExhaustive / alignReadExhaustivePath as persistent warps (same life cycle as k_extend_greedy): every lane
+// runs one node of its read's search per turn, in the stages of ExhaustiveState, and the candidates of all the
+// lanes' nodes are compared by the whole warp (warp_compare).
 template <int MINB>
 __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_exhaustive_nodes(DevIndex ix, BatchArgs a) {
+    __shared__ __align__(16) ExtWarpShared wsh_all[EXT_THREADS / 32];
+    ExtWarpShared& W = wsh_all[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31;
     const u32 list_n = a.scnt->list_n;
     ExhaustiveState g;
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_exhaustive_nodes(D
     bool any_overflow = false;
     const u32 lazy = a.ext_lazy ? a.ext_lazy : 1;
     for (;;) {
-        const bool searching = have && (g.phase == XP_LEFT || g.phase == XP_RIGHT);
+        const bool searching = have && g.searching();
         const u32 waiting = __ballot_sync(0xFFFFFFFFu, !searching);
         if ((u32)__popc(waiting) >= lazy || waiting == 0xFFFFFFFFu) {
             if (have && g.done()) {  // hand in
@@ -347,7 +356,23 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_exhaustive_nodes(D
             }
             if (have && g.phase == XP_SEED) g.pick_seed(ix, a);
         }
-        if (have && (g.phase == XP_LEFT || g.phase == XP_RIGHT)) g.step_node(ix, a);
+        // ---- one node: entry side -> comparison jobs -> warp-wide comparing -> settle
+        const bool q = have && g.searching() && g.node_begin(ix, a);
+        USlot sl[4];
+        int nc = 0;
+        GreedyLevel lv;
+        lv.n = 0;
+        lv.ends = 0;
+        if (q) {
+            if (const USlot* side = g.node_side(ix)) {
+                load_side(side, sl);
+                nc = count_slots(sl);
+            }
+            g.node_jobs(ix, sl, nc, lv);
+        }
+        u32 miss[4];
+        warp_compare(W, ix, a, lane, q, nc, lv, g.s.wb + 1, g.s.v.hasN, g.s.v.pass, miss);
+        if (q) g.node_settle(ix, a, sl, lv, miss);
     }
     if (any_overflow) atomicExch(&a.cnt->scratch_overflow, 1u);
     count_classes(a, n_al, n_na, 0);

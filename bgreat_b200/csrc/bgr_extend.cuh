@@ -1157,12 +1157,20 @@ struct ExhaustiveState {
         }
     }
 
-    // one node of the search (the body of exhaustive_side's while loop)
-    BGR_HD void step_node(const DevIndex& ix, const BatchArgs& a) {
-        const ReadView& v = s.v;
-        const i64 km1 = ix.k - 1;
+    // One node of the search (the body of exhaustive_side's while loop), in the three stages of the greedy level so
+    // that the kernel can compare the candidates of all its lanes' nodes together:
+    //   node_begin : nodes that need no query (the read is used up: record the walk; or nothing below can beat the
+    //                incumbent); false = the node is finished
+    //   node_jobs  : one comparison job per candidate from f_next on (geometry only)
+    //   node_settle: the loop over the candidates with their exact mismatch counts: a candidate that covers the
+    //                rest of the read may become the incumbent, the first other one within reach is descended into
+    // The comparisons of the candidates behind the one descended into are wasted (and made again when the search
+    // comes back to this node): the price of comparing them side by side.
+    BGR_HD bool searching() const { return phase == XP_LEFT || phase == XP_RIGHT; }
+    BGR_HD bool node_begin(const DevIndex& ix, const BatchArgs& a) {
         const bool right = phase == XP_RIGHT;
-        const i32 rl = right ? v.len - (f_pos + (i32)km1) : f_pos;
+        const i32 rl = right ? s.v.len - (f_pos + (i32)ix.k - 1) : f_pos;
+        bool query = true;
         if (rl == 0) {
             if (f_acc < best_total) {
                 best_total = f_acc;
@@ -1170,55 +1178,108 @@ struct ExhaustiveState {
                 term = right ? 0 : -1;
                 for (u32 j = 0; j < best_n; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
             }
-            pop_frame();
-        } else {
-            const Cands c = index_query_at(ix, f_slot, f_canon, !right);
-            bool descended = false;
-            for (u32 i = f_next; i < (u32)c.n; ++i) {
-                if (f_acc >= best_total) break;  // nothing below can be strictly better
-                const Oriented u = orient(ix, c, (int)i);
-                const i64 L = u.len - km1;
-                const u32 cap = best_total - 1 - f_acc;
-                if (L >= rl) {
-                    const u32 miss = right ? mismatches(ix, v, u, km1, f_pos + (i32)km1, rl, cap)
-                                           : mismatches(ix, v, u, L - rl, 0, rl, cap);
-                    if (miss <= cap) {
-                        best_total = f_acc + miss;
-                        best_n = (u32)depth + 1;
-                        term = right ? rl + (i32)km1 : (i32)(L - rl);
-                        for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
-                        sc.set(lay.best0 + (u32)depth, u.sid);
-                    }
-                } else {
-                    const u32 miss = right ? mismatches(ix, v, u, km1, f_pos + (i32)km1, (i32)L, cap)
-                                           : mismatches(ix, v, u, 0, rl - (i32)L, (i32)L, cap);
-                    if (miss <= cap) {
-                        if ((u32)depth + 1 >= lay.D) {  // search stack too small: give up, the host grows the scratch
-                            sc.overflow = true;
-                            depth = -1;
-                            side_finished(a);
-                            return;
-                        }
-                        // park this frame (resume with candidate i+1), make the child the top frame
-                        const u32 b = lay.fr0 + 5 * (u32)depth;
-                        sc.set(b, (i32)((f_slot & 0x7FFFFFFFu) | (f_canon ? 0x80000000u : 0u)));
-                        sc.set(b + 2, f_pos);
-                        sc.set(b + 3, (i32)f_acc);
-                        sc.set(b + 4, (i32)(i + 1));
-                        sc.set(lay.cur0 + (u32)depth, u.sid);
-                        next_query(c.s[i], c.canon, f_slot, f_canon);
-                        f_pos = right ? f_pos + (i32)L : f_pos - (i32)L;
-                        f_acc += miss;
-                        f_next = 0;
-                        ++depth;
-                        descended = true;
-                        break;
-                    }
-                }
-            }
-            if (!descended) pop_frame();
+            query = false;
+        } else if (f_acc >= best_total) {
+            query = false;  // nothing below can be strictly better
         }
+        if (!query) {
+            pop_frame();
+            if (depth < 0) side_finished(a);
+        }
+        return query;
+    }
+    BGR_HD const USlot* node_side(const DevIndex& ix) const {
+        return f_slot == NO_SLOT ? nullptr : entry_side(ix, f_slot, f_canon, phase != XP_RIGHT);
+    }
+    BGR_HD void node_jobs(const DevIndex& ix, const USlot sl[4], int nc, GreedyLevel& lv) const {
+        const ReadView& v = s.v;
+        const i32 km1 = (i32)ix.k - 1;
+        const bool right = phase == XP_RIGHT;
+        const u32 fwd_bit = f_canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+        const i32 rl = right ? v.len - (f_pos + km1) : f_pos;
+        lv.n = nc;
+        lv.ends = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            lv.job[i].n = 0;
+            lv.L[i] = 0;
+            if (i < nc && (u32)i >= f_next) {
+                const Oriented u = orient_slot(sl[i], fwd_bit);
+                const i32 L = (i32)(u.len - km1);
+                const bool ends_here = L >= rl;
+                // right: unitig[k-1, ..) vs read[pos+k-1, ..); left: unitig[L-rl, L) vs read[0, rl) when it covers the
+                // rest, else unitig[0, L) vs read[rl-L, rl)
+                const i64 upos = right ? (i64)km1 : (ends_here ? (i64)(L - rl) : 0);
+                const i32 rpos = right ? f_pos + km1 : (ends_here ? 0 : rl - L);
+                lv.job[i] = make_job(v, u, upos, rpos, ends_here ? rl : L);
+                lv.L[i] = L;
+                lv.ends |= (ends_here ? 1u : 0u) << i;
+            }
+        }
+    }
+    BGR_HD void node_settle(const DevIndex& ix, const BatchArgs& a, const USlot sl[4], const GreedyLevel& lv, const u32 miss[4]) {
+        const bool right = phase == XP_RIGHT;
+        const u32 fwd_bit = f_canon ? SLOT_FWD_CANON : SLOT_FWD_RC;
+        const i32 km1 = (i32)ix.k - 1;
+        const i32 rl = right ? s.v.len - (f_pos + km1) : f_pos;
+        bool descended = false;
+        for (u32 i = f_next; i < (u32)lv.n; ++i) {
+            if (f_acc >= best_total) break;  // nothing below can be strictly better
+            const u32 cap = best_total - 1 - f_acc;
+            const Oriented u = orient_slot(sl[i], fwd_bit);
+            const i32 L = lv.L[i];
+            if ((lv.ends >> i) & 1u) {
+                if (miss[i] <= cap) {
+                    best_total = f_acc + miss[i];
+                    best_n = (u32)depth + 1;
+                    term = right ? rl + km1 : L - rl;
+                    for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+                    sc.set(lay.best0 + (u32)depth, u.sid);
+                }
+            } else if (miss[i] <= cap) {
+                if ((u32)depth + 1 >= lay.D) {  // search stack too small: give up, the host grows the scratch
+                    sc.overflow = true;
+                    depth = -1;
+                    side_finished(a);
+                    return;
+                }
+                // park this frame (resume with candidate i+1), make the child the top frame
+                const u32 b = lay.fr0 + 5 * (u32)depth;
+                sc.set(b, (i32)((f_slot & 0x7FFFFFFFu) | (f_canon ? 0x80000000u : 0u)));
+                sc.set(b + 2, f_pos);
+                sc.set(b + 3, (i32)f_acc);
+                sc.set(b + 4, (i32)(i + 1));
+                sc.set(lay.cur0 + (u32)depth, u.sid);
+                next_query(sl[i], f_canon, f_slot, f_canon);
+                f_pos = right ? f_pos + L : f_pos - L;
+                f_acc += miss[i];
+                f_next = 0;
+                ++depth;
+                descended = true;
+                break;
+            }
+        }
+        if (!descended) pop_frame();
         if (depth < 0) side_finished(a);
+    }
+
+    // one node, start to finish, by one thread (emulator; the kernel runs the stages itself)
+    BGR_HD void step_node(const DevIndex& ix, const BatchArgs& a) {
+        if (!node_begin(ix, a)) return;
+        USlot sl[4];
+        int nc = 0;
+        if (const USlot* side = node_side(ix)) {
+            load_side(side, sl);
+            nc = count_slots(sl);
+        }
+        GreedyLevel lv;
+        node_jobs(ix, sl, nc, lv);
+        u32 miss[4] = {0, 0, 0, 0};
+        for (int i = 0; i < nc; ++i)
+            for (i32 d = 0; d < lv.job[i].n; d += 32)
+                miss[i] += job_chunk_miss(ix.pool, s.v.D, s.v.ND, s.v.hasN, s.v.pass, lv.job[i].ua, lv.job[i].sa, lv.job[i].n,
+                                          lv.job[i].flip, d);
+        node_settle(ix, a, sl, lv, miss);
     }
 
     BGR_HD void step(const DevIndex& ix, const BatchArgs& a) {

@@ -52,7 +52,34 @@ void run(const uint4* buf, uint64_t bytes_total, uint64_t* sink, int warps_per_s
            warps_per_sm, acc / ms / 1e6, acc * BYTES / ms / 1e6, acc * 64 / ms / 1e6);
 }
 
+// Second form: `hbm_random sweep` -- footprints from 8 MB to 12 GB under each L2 fetch granularity the driver
+// accepts (cudaLimitMaxL2FetchGranularity 32 / 64 / 128): where random reads stop being L2 hits, and whether the
+// granularity changes the rate HBM serves them at.
+static void sweep() {
+    uint4* buf;
+    uint64_t* sink;
+    if (cudaMalloc(&buf, 12ull << 30) != cudaSuccess) return;
+    cudaMalloc(&sink, 8);
+    cudaMemset(buf, 1, 12ull << 30);
+    for (size_t gran : {64, 32, 128}) {
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("L2 fetch granularity asked %zu (%s), in force %zu\n", gran, cudaGetErrorName(e), got);
+        for (uint64_t mb : {8, 16, 24, 32, 48, 64, 96, 128, 256, 1024, 12288}) {
+            printf("  footprint %5llu MB: ", (unsigned long long)mb);
+            run<32, 4>(buf, mb << 20, sink, 32);
+        }
+        printf("  footprint 12288 MB, 64 B: ");
+        run<64, 4>(buf, 12288ull << 20, sink, 32);
+    }
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == 's') {
+        sweep();
+        return 0;
+    }
     const uint64_t gb = argc > 1 ? atoll(argv[1]) : 12;
     const uint64_t bytes_total = gb << 30;
     uint4* buf;
