@@ -100,7 +100,7 @@ struct BlobHeader {
     u32 pad;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
-static const u32 BLOB_VERSION = 5;
+static const u32 BLOB_VERSION = 6;  // 6: minimizer filter's bit pattern from mm_pat_hash
 
 // 2-bit code of a base character, A0 C1 G2 T3 (utils.cpp:117-129). Returns 4 for anything else.
 BGR_HD u32 base_code(unsigned char c) {
@@ -232,7 +232,7 @@ BGR_HD u32 bloom_word_of(u32 h1, u32 n_bloom) {
 //                     minimizer, so the scan fetches a block once per run of ~8 windows instead of once per window
 //                     (the L2 sector rate was what bound the scan on large indexes: 1.6 G sectors per 10 M reads,
 //                     profiles/r01_ncu_k_scan_tiles_v9_1Gbp.txt). Inside the block a key sets 3 of 64 bits, chosen
-//                     by bloom_h2 of the whole (k-1)-mer.
+//                     by mm_pat_hash of its first and last 16-mer.
 enum { BLOOM_SMEM_1HASH = 0, BLOOM_WORDS_2HASH = 1, BLOOM_MINIMIZER = 2 };
 static const u32 MM_M = 16;       // minimizer length: a 16-mer is one 32-bit word
 static const u32 MM_KM1 = 30;     // the (k-1) the minimizer mode is built for
@@ -242,6 +242,10 @@ static const u32 MM_W = MM_KM1 - MM_M + 1;  // 16-mers per (k-1)-mer
 // few distinct values for a word and its reversed complement, and a filter addressed by it had a third of its
 // blocks empty and 31 % false positives.
 BGR_HD u32 mm_hash(u32 s, u32 r) { return (s * r) * 0x9E3779B1u + s * 0x85EBCA77u + r * 0x85EBCA77u; }
+// which three bits a (k-1)-mer sets in its block: a hash of its FIRST 16-mer s and of the reverse complement r of its
+// LAST 16-mer. The reverse complement of the (k-1)-mer swaps the two, so this too is the same on both strands, and
+// the scan gets both words as slices of the chunk's packed words (no rolling 60-bit codes: mm_test_windows).
+BGR_HD u32 mm_pat_hash(u32 s, u32 r) { return (s * r) * 0xC2B2AE3Du + s * 0x27D4EB2Fu + r * 0x27D4EB2Fu; }
 // block of a (k-1)-mer whose smallest 16-mer hash is hmin (the multiplication spreads the small values a
 // minimum takes over the whole range)
 BGR_HD u32 mm_block(u32 hmin, u32 n_blocks) {
@@ -288,7 +292,8 @@ BGR_HD void bloom_slot(u64 key, u32 km1, bool two_hashes, u32 n_bloom, u32& word
 // block index and bit pattern of a canonical 30-mer: minimizer mode (n_blocks = n_bloom / 2)
 BGR_HD void bloom_slot_mm(u64 key, u32 n_blocks, u32& block, u64& pattern) {
     block = mm_block(mm_min_hash(key), n_blocks);
-    pattern = bloom_pattern64(bloom_pidx(bloom_h2(key, rcb(key, MM_KM1))));
+    const u32 first = (u32)(key >> (2 * (MM_KM1 - MM_M))), last = (u32)key;
+    pattern = bloom_pattern64(bloom_pidx(mm_pat_hash(first, (u32)rcb((u64)last, MM_M))));
 }
 // filter layout for n_keys keys of k-mers: mode and number of 32-bit words (power of two not required)
 inline u64 bloom_layout(u64 n_keys, u32 k, u32& mode) {

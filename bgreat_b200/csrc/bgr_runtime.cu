@@ -937,15 +937,24 @@ int bgr_slot_run(bgr_ctx* ctx, int slot, const bgr_params* p) {
         if (s.tile_r >= 2) {
             // tile scan: one persistent CTA per SM; the Bloom filter rides in shared memory when it is small
             const bool bloom_smem = ctx->ix.bloom_mode == BLOOM_SMEM_1HASH;
-            const size_t smem = ctx->scan_ws ? tile_ws_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB)
+            bool mm_async = ctx->scan_ws && ctx->ix.bloom_mode == BLOOM_MINIMIZER && ctx->ix.k == 31;  // k_scan_tiles_ws' STAGED
+            if (const char* e = getenv("BGR_SCAN_MM")) mm_async = mm_async && strcmp(e, "inline") != 0;  // experiment hook
+            const size_t smem = ctx->scan_ws ? tile_ws_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB, mm_async)
                                              : tile_smem_bytes(bloom_smem ? ctx->ix.n_bloom : 0, TILE_CB);
             const u32 ntiles = (s.n + s.tile_r - 1) / s.tile_r;
             const u32 blocks = std::min<u32>(ntiles, (u32)ctx->sm_count);
 #define BGR_LAUNCH_TILES(BS, PK, KS)                                                                                 \
     do {                                                                                                             \
         if (ctx->scan_ws) {                                                                                          \
-            CK(cudaFuncSetAttribute(k_scan_tiles_ws<BS, PK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_scan_tiles_ws<BS, PK, KS><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                           \
+            if (!BS && KS == 30 && mm_async) {                                                                       \
+                CK(cudaFuncSetAttribute(k_scan_tiles_ws<BS, PK, KS, !BS && KS == 30>,                                \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+                k_scan_tiles_ws<BS, PK, KS, !BS && KS == 30><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);      \
+            } else {                                                                                                 \
+                CK(cudaFuncSetAttribute(k_scan_tiles_ws<BS, PK, KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                                 \
+                k_scan_tiles_ws<BS, PK, KS, false><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                \
+            }                                                                                                        \
         } else {                                                                                                     \
             CK(cudaFuncSetAttribute(k_scan_tiles<BS, PK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             k_scan_tiles<BS, PK, KS><<<blocks, ST_THREADS, smem, s.stream>>>(ctx->ix, a);                              \

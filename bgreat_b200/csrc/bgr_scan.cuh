@@ -489,7 +489,7 @@ BGR_HD u32 scan_chunk_mm(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0
             blk = blocks[b];
 #endif
         }
-        const u64 m = pat[bloom_pidx(bloom_h2(num, rc))];
+        const u64 m = pat[bloom_pidx(mm_pat_hash((u32)(num >> (2 * (MM_KM1 - MM_M))), (u32)(rc >> (2 * (MM_KM1 - MM_M)))))];
         hits |= ((blk & m) == m ? 1u : 0u) << j;
         const u64 nb = (inc >> (62 - 2 * j)) & 3;
         num = ((num << 2) | nb) & mask;
@@ -540,6 +540,222 @@ BGR_HD u32 verify_chunk(const DevIndex& ix, u64 w0, u64 w1, u32 hits) {
 // ------------------------------------------------------------------------------ tile scan kernel
 
 static const int ST_THREADS = 1024;
+static const u32 WS_WORKERS = ST_THREADS - 32;  // worker threads of the warp-specialised tile kernel
+
+// ------------------------------------------------------------------------------ minimizer tier, loads off the critical path
+//
+// scan_chunk_mm asks for a filter block at the window where a run starts and tests that window with it at once: in a
+// warp some lane starts a run at nearly every one of the 32 unrolled windows, so the warp waits out a memory round
+// trip per WINDOW, and then one more per survivor in verify_chunk. On an index far larger than L2 that chain, not
+// the rate at which HBM serves random reads, was what the scan took its time from (profiles/r02_scan_experiments.txt:
+// 6.2 ms per 10 M reads at 3 Gbp; 4.1 ms without the key-table checks, 2.9 ms without any index load, while a
+// micro-benchmark of the same mix of accesses runs at 2.5 times the kernel's rate). The tile kernel's workers
+// therefore take a chunk in three steps, none of which waits for memory inside a loop:
+//   mm_stage_blocks  the minimizers of all 32 windows (16-mer hashes straight from slices of the chunk's two
+//                    words and of their reverse complements: no rolling codes yet); at every run start a
+//                    cp.async carries the run's block into a shared-memory slot of the thread -- no register waits
+//                    for it. One bit per run start is all that is kept.
+//   mm_test_windows  after ONE wait for the thread's copies: the rolling codes, the bit pattern of every window,
+//                    tested against the block of its run (shared memory).
+//   verify_warp      the survivors of all 32 lanes are listed in shared memory and checked against the key table
+//                    side by side, one bucket load per lane: one round trip per chunk of the warp instead of one
+//                    per survivor of its unluckiest lane.
+static const u32 MM_SLOTS = 10;  // runs of a chunk with a slot (a chunk has 4.8 on average; the others are loaded in place)
+static const u32 VQ_CAP = 128;   // survivors listed per round: four per lane
+struct VerifyQueue {
+    u32 hits[32];
+    unsigned short tag[VQ_CAP];  // lane << 5 | window
+};
+
+__device__ __forceinline__ void cp_async8(void* dst_shared, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_if(u32 dst_shared, const void* src, bool p) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %2, 0;\n"
+        "@q cp.async.ca.shared.global [%0], [%1], 8;\n"
+        "}" ::"r"(dst_shared),
+        "l"(src), "r"((u32)p)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The 16-mer at offset T of the 64 bases (A:B:C:D), and its reverse complement: the 16-mer at offset 48 - T of the
+// reverse-complemented 64 bases (E:F:G:H). T is a compile-time constant: a slice is one funnel shift.
+template <u32 T>
+__device__ __forceinline__ u32 mm_s_at(u32 A, u32 B, u32 C, u32 D) {
+    return T == 0 ? A : T < 16 ? __funnelshift_l(B, A, 2 * T) : T == 16 ? B : T < 32 ? __funnelshift_l(C, B, 2 * T - 32)
+                                                                                 : T == 32 ? C : __funnelshift_l(D, C, 2 * T - 64);
+}
+template <u32 T>
+__device__ __forceinline__ u32 mm_r_at(u32 E, u32 F, u32 G, u32 H) {
+    constexpr u32 U = 48 - T;
+    return U == 48 ? H : U > 32 ? __funnelshift_l(H, G, 2 * U - 64) : U == 32 ? G : U > 16 ? __funnelshift_l(G, F, 2 * U - 32)
+                                                                                   : U == 16 ? F : __funnelshift_l(F, E, 2 * U);
+}
+template <u32 T>
+__device__ __forceinline__ u32 mm_hash_at(u32 A, u32 B, u32 C, u32 D, u32 E, u32 F, u32 G, u32 H) {
+    return mm_hash(mm_s_at<T>(A, B, C, D), mm_r_at<T>(E, F, G, H));
+}
+
+template <u32 J>
+struct MMStage {
+    // window J of the chunk (and, recursively, the windows after it): the sliding minimum as in scan_chunk_mm
+    static __device__ __forceinline__ void run(const u64* blocks, u32 n_blocks, u32 count, u32 sp_last, u32 A, u32 B, u32 C, u32 D,
+                                               u32 E, u32 F, u32 G, u32 H, u32 (&S)[MM_W], u32 (&hb)[MM_W], u32& P, u32& Q,
+                                               u32& cur, u32& runs, u32& sp) {
+        u32 wmin;
+        if (J == 0) {
+            wmin = S[0];
+        } else if (J <= MM_W) {  // 16-mer offsets 15..29
+            const u32 h = mm_hash_at<J + 14>(A, B, C, D, E, F, G, H);
+            hb[J - 1] = h;
+            P = (J == 1 || h < P) ? h : P;
+            constexpr u32 si = J < MM_W ? J : 0;
+            wmin = (J < MM_W) ? (S[si] < P ? S[si] : P) : P;
+            if (J == MM_W) {  // the block is complete: its suffix minima replace the first block's
+                S[MM_W - 1] = hb[MM_W - 1];
+#pragma unroll
+                for (int i = (int)MM_W - 2; i >= 0; --i) S[i] = hb[i] < S[i + 1] ? hb[i] : S[i + 1];
+            }
+        } else {  // offsets 30..45
+            const u32 h = mm_hash_at<J + 14>(A, B, C, D, E, F, G, H);
+            if (J <= 2 * MM_W) P = (J == MM_W + 1 || h < P) ? h : P;
+            if (J >= MM_W + 2) Q = h < Q ? h : Q;  // offsets 31..: the last window starts one past a block start
+            constexpr u32 si = J > MM_W && J < 2 * MM_W ? J - MM_W : 0;
+            wmin = (J < 2 * MM_W) ? (S[si] < P ? S[si] : P) : (J == 2 * MM_W ? P : Q);
+        }
+        // no branch: a predicated copy, and the slot pointer stops at the last slot (a chunk with more runs than slots
+        // is redone by scan_chunk_mm, see tile_chunk_mm)
+        const u32 b = mm_block(wmin, n_blocks);
+        const bool isnew = (J == 0 || b != cur) && J < count;
+        cur = b;
+        cp_async8_if(sp, blocks + b, isnew);
+        runs |= (isnew ? 1u : 0u) << J;
+        sp = min(sp + (isnew ? WS_WORKERS * 8 : 0u), sp_last);
+        if constexpr (J + 1 < 32) MMStage<J + 1>::run(blocks, n_blocks, count, sp_last, A, B, C, D, E, F, G, H, S, hb, P, Q, cur, runs, sp);
+    }
+};
+
+// slot: the thread's first slot; its slot i is slot[i * WS_WORKERS]. Returns the mask of the windows that start a run.
+__device__ __forceinline__ u32 mm_stage_blocks(const u64* blocks, u32 n_blocks, u64 w0, u64 w1, u32 count, u64* slot) {
+    const u32 A = (u32)(w0 >> 32), B = (u32)w0, C = (u32)(w1 >> 32), D = (u32)w1;
+    const u64 R0 = rc64(w0), R1 = rc64(w1);
+    const u32 E = (u32)(R1 >> 32), F = (u32)R1, G = (u32)(R0 >> 32), H = (u32)R0;
+    u32 S[MM_W], hb[MM_W];
+    S[0] = mm_hash_at<0>(A, B, C, D, E, F, G, H);
+    S[1] = mm_hash_at<1>(A, B, C, D, E, F, G, H);
+    S[2] = mm_hash_at<2>(A, B, C, D, E, F, G, H);
+    S[3] = mm_hash_at<3>(A, B, C, D, E, F, G, H);
+    S[4] = mm_hash_at<4>(A, B, C, D, E, F, G, H);
+    S[5] = mm_hash_at<5>(A, B, C, D, E, F, G, H);
+    S[6] = mm_hash_at<6>(A, B, C, D, E, F, G, H);
+    S[7] = mm_hash_at<7>(A, B, C, D, E, F, G, H);
+    S[8] = mm_hash_at<8>(A, B, C, D, E, F, G, H);
+    S[9] = mm_hash_at<9>(A, B, C, D, E, F, G, H);
+    S[10] = mm_hash_at<10>(A, B, C, D, E, F, G, H);
+    S[11] = mm_hash_at<11>(A, B, C, D, E, F, G, H);
+    S[12] = mm_hash_at<12>(A, B, C, D, E, F, G, H);
+    S[13] = mm_hash_at<13>(A, B, C, D, E, F, G, H);
+    S[14] = mm_hash_at<14>(A, B, C, D, E, F, G, H);
+    static_assert(MM_W == 15, "the offsets above");
+#pragma unroll
+    for (int i = (int)MM_W - 2; i >= 0; --i) S[i] = S[i] < S[i + 1] ? S[i] : S[i + 1];
+    u32 P = 0, Q = 0xFFFFFFFFu, cur = 0xFFFFFFFFu, runs = 0;
+    u32 sp = (u32)__cvta_generic_to_shared(slot);  // shared-memory address of the next free slot
+    const u32 sp_last = sp + (MM_SLOTS - 1) * WS_WORKERS * 8;
+    MMStage<0>::run(blocks, n_blocks, count, sp_last, A, B, C, D, E, F, G, H, S, hb, P, Q, cur, runs, sp);
+    return runs;
+}
+
+// a chunk with more runs than slots (rare): the blocks loaded where they are tested
+__device__ __noinline__ u32 scan_chunk_mm_far(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0, u64 w1, u32 count) {
+    return scan_chunk_mm(blocks, n_blocks, pat, w0, w1, count);
+}
+
+template <u32 J>
+struct MMTest {
+    // window J (and the ones after it): the block of its run, its bit pattern from its first 16-mer and the reverse
+    // complement of its last one (mm_pat_hash), the test
+    static __device__ __forceinline__ void run(const u64* pat, u32 runs, u32 A, u32 B, u32 C, u32 D, u32 E, u32 F, u32 G, u32 H,
+                                               const u64*& sp, u64& blk, u32& hits) {
+        if ((runs >> J) & 1u) {
+            blk = *sp;
+            sp += WS_WORKERS;
+        }
+        const u64 m = pat[bloom_pidx(mm_pat_hash(mm_s_at<J>(A, B, C, D), mm_r_at<J + MM_W - 1>(E, F, G, H)))];
+        hits |= ((blk & m) == m ? 1u : 0u) << J;
+        if constexpr (J + 1 < 32) MMTest<J + 1>::run(pat, runs, A, B, C, D, E, F, G, H, sp, blk, hits);
+    }
+};
+
+// the chunk's runs must all have a slot: popc(runs) <= MM_SLOTS
+__device__ __forceinline__ u32 mm_test_windows(const u64* pat, u64 w0, u64 w1, u32 count, u32 runs, const u64* slot) {
+    const u32 A = (u32)(w0 >> 32), B = (u32)w0, C = (u32)(w1 >> 32), D = (u32)w1;
+    const u64 R0 = rc64(w0), R1 = rc64(w1);
+    const u32 E = (u32)(R1 >> 32), F = (u32)R1, G = (u32)(R0 >> 32), H = (u32)R0;
+    u32 hits = 0;
+    const u64* sp = slot;
+    u64 blk = 0;
+    MMTest<0>::run(pat, runs, A, B, C, D, E, F, G, H, sp, blk, hits);
+    return count >= 32 ? hits : hits & ((1u << count) - 1);
+}
+
+__device__ __noinline__ bool index_has_far(const DevIndex& ix, u64 key) { return index_has(ix, key); }
+
+// The windows of the warp's 32 chunks that passed the filter, checked against the key table: all lanes call this
+// (hits = 0 for a lane without a chunk); the returned mask is exact.
+__device__ __forceinline__ u32 verify_warp(const DevIndex& ix, const u32 km1, VerifyQueue& Q, const u32 lane, const u64 w0,
+                                           const u64 w1, u32 hits) {
+    const u32 FULL = 0xFFFFFFFFu;
+    if (!__any_sync(FULL, hits != 0)) return hits;
+    const u32 sh = 64 - 2 * km1;
+    Q.hits[lane] = hits;
+    u32 m = hits;
+    for (;;) {
+        const u32 have = (u32)__popc(m);
+        const u32 c = have < 4 ? have : 4;
+        u32 incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 x = __shfl_up_sync(FULL, incl, d);
+            if (lane >= (u32)d) incl += x;
+        }
+        const u32 total = __shfl_sync(FULL, incl, 31);
+        u32 at = incl - c;
+#pragma unroll 1
+        for (u32 t = 0; t < c; ++t) {
+            const u32 j = (u32)__ffs(m) - 1;
+            m &= m - 1;
+            Q.tag[at++] = (unsigned short)((lane << 5) | j);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (u32 e0 = 0; e0 < total; e0 += 32) {
+            const u32 e = e0 + lane;
+            const bool valid = e < total;
+            const u32 tag = valid ? Q.tag[e] : 0u;
+            const u32 owner = tag >> 5, j = tag & 31;
+            const u64 o0 = __shfl_sync(FULL, w0, owner), o1 = __shfl_sync(FULL, w1, owner);
+            if (valid) {
+                const u64 x = (j ? ((o0 << (2 * j)) | (o1 >> (64 - 2 * j))) : o0) >> sh;
+                const u64 rc = rcb(x, km1);
+                const u64 key = x < rc ? x : rc;
+                const u64x4 v = ld_bucket(ix.keys + bucket_of(key, ix.n_buckets) * 4);
+                bool found = v.a == key || v.b == key || v.c == key || v.d == key;
+                // a full home bucket: the key may have overflowed into a later one
+                if (!found && v.d != EMPTY_KEY) found = index_has_far(ix, key);
+                if (!found) atomicAnd(&Q.hits[owner], ~(1u << j));
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(FULL, m != 0)) break;
+    }
+    return Q.hits[lane];
+}
+
 static const u32 ST_MAX_R = 256;    // reads per tile (one prologue / epilogue thread each)
 static const u32 ST_CHAR_SLACK = 128;  // bytes readable behind a character buffer (look-ahead of the last span)
 
@@ -562,6 +778,9 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        // a waiting warp must not take issue slots from the working ones: the bookkeeper warp of k_scan_tiles_ws spent
+        // 18 % of the kernel's issued instructions in this loop (profiles/r02_lines_k_scan_tiles_async_3Gbp.txt)
+        if (!done) __nanosleep(100);
     } while (!done);
 }
 // TMA bulk copy global -> shared (1-D, 16-byte granules), completion counted on an mbarrier; the read
@@ -640,6 +859,58 @@ __device__ __forceinline__ u32 tile_chunk(const DevIndex& ix, const BatchArgs& a
     a.H1[wb + l] = hits;
     const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
     if (fl) atomicOr(&s_flags[rd], fl);
+    return passed;
+}
+
+// The same chunk on the minimizer tier of the warp-specialised kernel, in the three steps of mm_stage_blocks /
+// mm_test_windows / verify_warp. Called by whole warps; `active`: the lane has a chunk (j < chunks of the tile).
+template <bool PACKED>
+__device__ __forceinline__ u32 tile_chunk_mm(const DevIndex& ix, const BatchArgs& a, const u64* pat, const unsigned char* cb,
+                                             const u64 gs, const u64* s_off, const u32* s_prefix, u32* s_flags, const u32 cnt,
+                                             const u32 r0, const u32 j, const bool active, u64* slot, VerifyQueue& Q,
+                                             const u32 lane) {
+    u64 w0 = 0, w1 = 0, wb = 0;
+    u32 hits = 0, passed = 0, bad = 0, rd = 0, l = 0;
+    if (active) {
+#pragma unroll
+        for (u32 sft = ST_MAX_R / 2; sft; sft >>= 1) {
+            const u32 c = rd + sft;
+            if (c < cnt && s_prefix[c] <= j) rd = c;
+        }
+        l = j - s_prefix[rd];
+        const u64 ro = s_off[rd];
+        const u32 rlen = (u32)(s_off[rd + 1] - ro);
+        const u32 rnwin = rlen - MM_KM1 + 1;
+        const u32 rchunks = (rnwin + 31) >> 5;
+        wb = read_word_base(ro, r0 + rd);
+        if (PACKED) packed_span((const u64*)cb, ro - gs + 32 * l, w0, w1);
+        else pack_span(cb + (u32)(ro - gs) + 32 * l, w0, w1, bad);
+        clip_span(rlen - 32 * l, w0, w1);
+        const u32 count = min(32u, rnwin - 32 * l);
+        const u64* blocks = (const u64*)ix.bloom;
+        const u32 n_blocks = ix.n_bloom / 2;
+        const u32 runs = mm_stage_blocks(blocks, n_blocks, w0, w1, count, slot);
+        // packed words for the extension kernel (layout of read_word_base: pad, words, 2 pads), while the blocks travel
+        u64* gF = a.F + wb;
+        const u32 nw = (rlen + 31) >> 5;
+        gF[1 + l] = w0;
+        if (l == 0) gF[0] = 0;
+        if (l + 1 == rchunks) {
+            if (l + 1 < nw) gF[2 + l] = w1;
+            gF[nw + 1] = 0;
+            gF[nw + 2] = 0;
+        }
+        cp_async_wait_all();
+        if ((u32)__popc(runs) <= MM_SLOTS) hits = mm_test_windows(pat, w0, w1, count, runs, slot);
+        else hits = scan_chunk_mm_far(blocks, n_blocks, pat, w0, w1, count);
+        passed = (u32)__popc(hits);
+    }
+    hits = verify_warp(ix, MM_KM1, Q, lane, w0, w1, hits);
+    if (active) {
+        a.H1[wb + l] = hits;
+        const u32 fl = (hits ? TS_FLAG_HIT : 0u) | (bad ? TS_FLAG_BAD : 0u);
+        if (fl) atomicOr(&s_flags[rd], fl);
+    }
     return passed;
 }
 
@@ -879,13 +1150,14 @@ struct TileMeta {
     u64 t_lo;
     u32 cnt, r0, T, fits, wait_tma, tma_parity;
 };
-static const u32 WS_WORKERS = ST_THREADS - 32;
 
-__host__ __device__ inline size_t tile_ws_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb) {
+// mm_async: the minimizer tier's block slots and verify queues (mm_stage_blocks / verify_warp)
+__host__ __device__ inline size_t tile_ws_smem_bytes(u32 bloom_words_in_smem, u32 tile_cb, bool mm_async) {
     size_t b = ((size_t)bloom_words_in_smem * 4 + 127) & ~(size_t)127;
     b += BLOOM_PATTERNS * 8;
     b += 2 * ((size_t)tile_cb + ST_CHAR_SLACK);
     b += 2 * ((sizeof(TileMeta) + 15) & ~(size_t)15) + 6 * 8;
+    if (mm_async) b += (size_t)MM_SLOTS * WS_WORKERS * 8 + (WS_WORKERS / 32) * sizeof(VerifyQueue);
     return b + 128;
 }
 
@@ -893,13 +1165,16 @@ __device__ __forceinline__ void mbar_arrive(u64* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool BLOOM_SMEM, bool PACKED, u32 KM1S>
+// STAGED: the minimizer tier in the three steps of mm_stage_blocks / mm_test_windows / verify_warp (see there)
+template <bool BLOOM_SMEM, bool PACKED, u32 KM1S, bool STAGED>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, BatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32 *s_bloom, *s_pat;
     unsigned char* s_chars[2];
     TileMeta* M;
-    u64 *bar_tma, *bar_full, *bar_done;
+    u64 *bar_tma, *bar_full, *bar_done, *s_slots;
+    VerifyQueue* s_vq;
+    constexpr bool MM_ASYNC = STAGED && !BLOOM_SMEM && KM1S == MM_KM1;  // the minimizer tier (bloom_layout)
     {
         unsigned char* q = smem_raw;
         s_bloom = (u32*)q;
@@ -915,6 +1190,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, Ba
         bar_tma = (u64*)q;
         bar_full = bar_tma + 2;
         bar_done = bar_tma + 4;
+        q += 6 * 8;
+        s_slots = (u64*)q;
+        q += MM_ASYNC ? (size_t)MM_SLOTS * WS_WORKERS * 8 : 0;
+        s_vq = (VerifyQueue*)q;
     }
     auto meta = [&](u32 b) -> TileMeta& { return *(TileMeta*)((unsigned char*)M + b * ((sizeof(TileMeta) + 15) & ~(size_t)15)); };
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1100,9 +1379,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, Ba
                 const u32 T = m.T, cnt = m.cnt, r0 = m.r0;
                 const unsigned char* cb = s_chars[b];
                 const u64 gs = tile_start(m.t_lo);
-                for (u32 j = wtid; j < T; j += WS_WORKERS)
-                    c_verify += tile_chunk<BLOOM_SMEM, PACKED, KM1S>(ix, a, bloom, s_pat, km1, cb, gs, m.off, m.prefix, m.flags,
-                                                                      cnt, r0, j);
+                if (MM_ASYNC) {
+                    for (u32 jb = 0; jb < T; jb += WS_WORKERS)  // whole warps: verify_warp is a warp's joint step
+                        c_verify += tile_chunk_mm<PACKED>(ix, a, (const u64*)s_pat, cb, gs, m.off, m.prefix, m.flags, cnt, r0,
+                                                          jb + wtid, jb + wtid < T, s_slots + wtid, s_vq[warp - 1], lane);
+                } else {
+                    for (u32 j = wtid; j < T; j += WS_WORKERS)
+                        c_verify += tile_chunk<BLOOM_SMEM, PACKED, KM1S>(ix, a, bloom, s_pat, km1, cb, gs, m.off, m.prefix,
+                                                                          m.flags, cnt, r0, j);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_done[b]);

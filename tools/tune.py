@@ -11,11 +11,17 @@ from tools import synth
 import bgreat_b200
 from bgreat_b200 import _abi as A
 
+if os.environ.get("BGR_TUNE_LIB"):  # an experiment build of the library (tools only; the product loads its own)
+    A.LIB_PATH = os.environ["BGR_TUNE_LIB"]
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 genome = int(sys.argv[2]) if len(sys.argv) > 2 else 5_000_000
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 g = synth.Graph(genome, 31, seed=1)
 al = bgreat_b200.Aligner(31, 2, 2, n_slots=1)
+if os.environ.get("BGR_TUNE_L2GRAN"):  # experiment: cudaLimitMaxL2FetchGranularity (limit 5) of the primary context
+    rt = C.CDLL("libcudart.so.12")
+    print("cudaDeviceSetLimit ->", rt.cudaDeviceSetLimit(5, C.c_size_t(int(os.environ["BGR_TUNE_L2GRAN"]))), file=sys.stderr)
 us, uo = g.unitig_arrays()
 al.index_unitigs_packed(us, uo)
 seqs, off = g.make_reads(n, 150, 0.01)
