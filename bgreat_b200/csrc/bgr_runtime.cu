@@ -172,9 +172,10 @@ int set_index_from_device_blob(bgr_ctx* ctx) {
         return fail(ctx, BGR_ERR_FORMAT, "index blob: filter mode does not match k");
     ctx->ix.k = h.k;
     ctx->has_index = true;
-    // (A persisting L2 access window over the filter -- cudaStreamAttributeAccessPolicyWindow, with the device's
-    // persisting carve-out at its maximum -- was measured and dropped: the 64 MB filter of a 3 Gbp index gained
-    // 1 % while the carve-out took L2 away from everything else: 5 Mbp scan 2.68 -> 2.97 ms, extension +10 %.)
+    // (A persisting L2 access window over the filter -- cudaStreamAttributeAccessPolicyWindow -- was measured twice
+    // and dropped. With the carve-out at its maximum the 64 MB filter of a 3 Gbp index gained 1 % while the carve-out
+    // took L2 away from everything else: 5 Mbp scan 2.68 -> 2.97 ms, extension +10 %. With the staged scan, a window
+    // for the scan kernel only and a carve-out of 64 / 72 MB: scan 4.79 -> 5.28 / 7.45 ms, extension 3.94 -> 4.29 / 4.67.)
     return BGR_OK;
 }
 

@@ -436,13 +436,14 @@ BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, const u32* pat, u32 km1_rt,
 // scheme over blocks of 15 offsets -- suffix minima of the block a window starts in, a running prefix minimum of
 // the block it ends in: three min operations per window. Everything is unrolled, the arrays live in registers.
 // Measured, 10 M reads: 3.7 ms at 100 Mbp and 4.4 ms at 1 Gbp against 5.7 / 5.9 ms for the word filter (one L2 sector
-// per window); at 3 Gbp (40 M keys, 64 MB of blocks, more than L2 keeps) 6.2 against 6.0 ms: there the loads of a
-// chunk -- four or five blocks, one or two key buckets -- are HBM round trips (profiles/r02_ncu_k_scan_tiles_d_3Gbp.txt).
-// Two variants were measured at 3 Gbp and lost: requesting a chunk's blocks ahead of the test (a first pass that only
-// computes the minimizers, prefetches and lists the block numbers: 6.8 ms, twice the L2 sectors), and a bit map over
-// a sparser block array so that only occupied blocks are fetched (8.8 ms: two dependent loads per run of windows).
-// L2 cache hints (filter loads evict-last, the packed words and hit masks stored streaming) changed nothing at any
-// graph size (6.30 against 6.33 ms at 3 Gbp).
+// per window); at 3 Gbp (40 M keys, 64 MB of blocks) 6.2 against 6.0 ms: there a warp waits out a memory round trip at
+// nearly every window (profiles/r02_ncu_k_scan_tiles_d_3Gbp.txt), which is what the staged form below (mm_stage_blocks /
+// mm_test_windows / verify_warp, used by k_scan_tiles_ws) removes. This function is the form with the loads in place:
+// k_scan_tiles (BGR_SCAN=classic), chunks with more runs than slots, and the host emulator.
+// Measured at 3 Gbp and lost: a first pass that only computes the minimizers, prefetches into L2 and lists the block
+// numbers (6.8 ms, twice the L2 sectors); a bit map over a sparser block array so that only occupied blocks are fetched
+// (8.8 ms: two dependent loads per run of windows); L2 cache hints (filter loads evict-last, the packed words and hit
+// masks stored streaming: nothing at any graph size, with either form of the scan).
 // blocks: the filter as 64-bit blocks; pat: bloom_pattern64 table.
 BGR_HD u32 scan_chunk_mm(const u64* blocks, u32 n_blocks, const u64* pat, u64 w0, u64 w1, u32 count) {
     const u32 sh = 64 - 2 * MM_KM1, top = 2 * (MM_KM1 - 1);

@@ -127,7 +127,10 @@ __global__ void k_mix(const uint64_t* small_, uint64_t n_small, const uint4* big
                 v.y ^= x.x ^ y.w;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) wr[at + q] = v;
+            for (int q = 0; q < 4; ++q) {
+                if (WR & 4) __stcs(wr + at + q, v);
+                else wr[at + q] = v;
+            }
         }
     }
     if (acc == 0x1234567) *sink = acc;
@@ -193,6 +196,7 @@ static void mixes() {
         run_mix_wr<4, 1, 0, 0, 1>(buf, mb, sink);
         run_mix_wr<4, 1, 0, 0, 3>(buf, mb, sink);
         run_mix_wr<4, 0, 0, 0, 3>(buf, mb, sink);
+        run_mix_wr<4, 1, 0, 0, 7>(buf, mb, sink);  // 7: the written stream as st.global.cs
     }
 }
 
