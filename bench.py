@@ -683,14 +683,15 @@ def run_b200_arm(args):
         tr_gbs = None if tr is None else tr / (ms_ / 1e3) / 1e9
         random_access = None
         if tr_gbs is not None and rnd is not None and large:
-            # on an index far larger than L2 the kernels' DRAM traffic is random 64-byte fetches: their rate against
-            # the rate a plain random-read kernel reaches on this GPU (profiles/hbm_random.json)
-            random_access = {"fetches_per_s": tr_gbs * 1e9 / 64.0, "dram_gbs": tr_gbs,
-                             "ceiling_dram_gbs": rnd["dram_gbs_when_every_access_fetches_64B"],
-                             "frac_of_ceiling": tr_gbs / rnd["dram_gbs_when_every_access_fetches_64B"],
+            # on an index far larger than L2 the kernels' DRAM traffic is random reads, each of which brings its
+            # 128-byte line from HBM: the rate against what a plain random-read kernel makes this GPU's HBM deliver
+            # (profiles/hbm_random.json: 36 G random reads/s, whatever their size up to the line)
+            ceil = rnd["dram_gbs_when_every_access_fetches_its_128B_line"]
+            random_access = {"dram_gbs": tr_gbs, "ceiling_dram_gbs": ceil, "frac_of_ceiling": tr_gbs / ceil,
                              "ceiling_source": rnd["source"]}
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": tr, "traffic_achieved_gbs": tr_gbs, "random_access": random_access,
+                "traffic": tr, "traffic_achieved_gbs": tr_gbs,
+                "traffic_frac_of_peak": None if tr_gbs is None else tr_gbs / peak, "random_access": random_access,
                 "necessary_bytes_per_read": need, "necessary_bytes_per_launch": need * n_reads, "kernel_ms": ms_,
                 "model_bytes_per_read": model_b, "model_frac": model_b * n_reads / (ms_ / 1e3) / 1e9 / peak,
                 "binding": bound_note, "peak_source": peak_src}
@@ -698,8 +699,9 @@ def run_b200_arm(args):
     tier = "L2/HBM (minimizer-addressed filter)" if large else "shared memory (filter copied into every CTA)"
     k_scan = roof("k_scan_tiles_ws (pack + seed scan / index probe)", "k_scan_tiles", scan_ms, scan_bytes, model_scan,
                   "filter tier: %s. With the filter in shared memory the kernel is bound by the integer ALU pipe (80 %% busy, "
-                  "profiles/r01_ncu_k_scan_tiles_v11_5Mbp.txt); with it in L2/HBM by the latency of the block and key-bucket "
-                  "loads (long scoreboard, profiles/r02_ncu_k_scan_tiles_*_3Gbp.txt)" % tier)
+                  "profiles/r01_ncu_k_scan_tiles_v11_5Mbp.txt; 70 %% at 100 Mbp with the filter in L2); on an index far larger "
+                  "than L2 by the rate at which HBM serves random reads: about 14 DRAM transactions per read "
+                  "(profiles/r02_scan_experiments.txt, profiles/r02b_ncu_k_scan_tiles_3Gbp.txt)" % tier)
     k_ext = roof("k_extend_greedy (overlap extension)" if not EXHAUSTIVE else "k_extend_exhaustive_nodes (overlap extension)",
                  "k_extend_greedy" if not EXHAUSTIVE else "k_extend_exhaustive", ext_ms, ext_bytes, model_ext,
                  "dependent round trips (entry side, then unitig words) at 20 warps per SM and 15 of 32 threads per "
@@ -713,7 +715,8 @@ def run_b200_arm(args):
     roofline = dict(dominant)
     roofline["note"] = ("frac = necessary bytes of THIS design / kernel time / measured HBM peak; model_frac = the same with "
                         "SURVEY 8(d)'s bytes (one 32-byte index sector per window the reference examines), which the "
-                        "filter makes unnecessary to move; traffic = DRAM bytes ncu measured for this kernel and graph size")
+                        "filter makes unnecessary to move; traffic = DRAM bytes ncu measured for this kernel and graph size, "
+                        "traffic_frac_of_peak = that traffic / kernel time / measured HBM peak")
     roofline["kernels"] = {"scan": k_scan, "extend": k_ext}
     roofline["reference_model_per_read"] = model
     roofline["reference_model_source"] = model_src
