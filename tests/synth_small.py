@@ -31,10 +31,12 @@ def mutate(rng, s, rate, with_n=0.0):
     return "".join(out)
 
 
-def make_graph(rng, k, genome_len=300, mean_unitig=12, n_variants=6, low_complexity=False):
-    """-> (unitigs in file order, haplotypes). Unitigs overlap their neighbours by k-1 bases."""
+def make_graph(rng, k, genome_len=300, mean_unitig=12, n_variants=6, low_complexity=False, genome=None):
+    """-> (unitigs in file order, haplotypes). Unitigs overlap their neighbours by k-1 bases.
+    genome: the first haplotype, given instead of drawn."""
     alphabet = "ACGT" if not low_complexity else "AACGT"
-    g1 = random_seq(rng, genome_len, alphabet)
+    g1 = random_seq(rng, genome_len, alphabet) if genome is None else genome
+    genome_len = len(g1)
     # second haplotype: a few substitutions
     g2 = list(g1)
     for _ in range(n_variants):

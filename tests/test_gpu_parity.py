@@ -88,6 +88,35 @@ def test_large_index_filter_tier(bg, monkeypatch):
         al.close()
 
 
+def test_staged_scan_chunks_with_more_runs_than_slots(bg, monkeypatch):
+    """Minimizer tier, staged scan (bgr_scan.cuh: mm_stage_blocks keeps ten block slots per chunk): reads cut from a
+    sequence built so that the minimizer changes at every third window; four chunks in ten have more runs than slots
+    and are redone with the loads in place. Character and packed upload, greedy and exhaustive."""
+    import mm_spiky
+    monkeypatch.setenv("BGR_BLOOM", "global")
+    rng = random.Random(77)
+    genome = mm_spiky.spiky_sequence(rng, 2500, beam=48)
+    mins = mm_spiky.minimizers(genome)
+    over = sum(1 for j in range(0, len(mins) - 32, 5) if mm_spiky.runs_in(mins, j, j + 32) > 10)
+    assert over > 50, "the generator no longer produces chunks with more than ten runs"
+    unitigs, haps = S.make_graph(rng, 31, mean_unitig=25, n_variants=12, genome=genome)
+    reads = S.make_reads(rng, haps, 6000, 150, sub_rate=0.01, n_rate=0.0003)
+    reads += S.make_reads(rng, haps, 500, 97, sub_rate=0.0, n_rate=0.0)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(31, 2, 2, unitigs, reads, mode)
+        al = bg.Aligner(31, 2, 2)
+        al.index_unitigs(unitigs)
+        assert al.index_stats()["keys"] > 0
+        got = al.align_batch(reads, mode).as_tuples()
+        bad = [i for i in range(len(reads)) if got[i] != want[i]]
+        assert not bad, (len(bad), bad[:5], [(got[i], want[i]) for i in bad[:3]])
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        assert al.align_batch_packed(reads, mode, threads=2).as_tuples() == want
+        al.close()
+
+
 def test_many_tiles_and_mixed_lengths(bg):
     """a batch spanning several tiles per CTA, with read lengths that leave tiles ragged"""
     rng = random.Random(21)

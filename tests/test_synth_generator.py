@@ -62,3 +62,17 @@ def test_reads_do_not_depend_on_how_they_are_generated():
     for i in range(50):
         s = e[i * 150:(i + 1) * 150].tobytes().decode()
         assert any(s in h or rc(s) in h for h in haps)
+
+
+def test_spiky_sequence_has_chunks_with_more_runs_than_slots():
+    """tests/mm_spiky.py (input of the staged scan's overflow test): its plain-Python minimizers find, in the
+    sequence it builds, spans of 32 windows with more than ten minimizer runs; a random sequence has next to none"""
+    import random
+    import mm_spiky
+    rng = random.Random(77)
+    g = mm_spiky.spiky_sequence(rng, 600, beam=48)
+    m = mm_spiky.minimizers(g)
+    assert sum(1 for j in range(0, len(m) - 32, 5) if mm_spiky.runs_in(m, j, j + 32) > 10) > 5
+    r = "".join(rng.choice("ACGT") for _ in range(600))
+    m = mm_spiky.minimizers(r)
+    assert max(mm_spiky.runs_in(m, j, j + 32) for j in range(0, len(m) - 32, 5)) <= 12
