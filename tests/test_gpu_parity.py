@@ -117,6 +117,26 @@ def test_staged_scan_chunks_with_more_runs_than_slots(bg, monkeypatch):
         al.close()
 
 
+def test_staged_scan_many_borders_per_chunk(bg, monkeypatch):
+    """Minimizer tier: unitigs a few bases long, so that a chunk of 32 windows holds eight or more border keys and the
+    warp's joint verification (verify_warp: four survivors per lane and round) takes several rounds"""
+    monkeypatch.setenv("BGR_BLOOM", "global")
+    rng = random.Random(78)
+    unitigs, haps = S.make_graph(rng, 31, genome_len=6000, mean_unitig=3, n_variants=30)
+    reads = S.make_reads(rng, haps, 5000, 150, sub_rate=0.005, n_rate=0.0002)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(31, 2, 2, unitigs, reads, mode)
+        al = bg.Aligner(31, 2, 2)
+        al.index_unitigs(unitigs)
+        got = al.align_batch(reads, mode).as_tuples()
+        bad = [i for i in range(len(reads)) if got[i] != want[i]]
+        assert not bad, (len(bad), bad[:5], [(got[i], want[i]) for i in bad[:3]])
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        al.close()
+
+
 def test_many_tiles_and_mixed_lengths(bg):
     """a batch spanning several tiles per CTA, with read lengths that leave tiles ragged"""
     rng = random.Random(21)
