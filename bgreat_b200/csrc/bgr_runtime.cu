@@ -122,7 +122,7 @@ struct bgr_ctx {
     u32 scratch_greedy = 32, scratch_exhaustive = 128;  // ints per read, grown on overflow
     // resident CTAs per SM the kernels are compiled for (register budget); tuned on B200, see
     // profiles/. BGR_SCAN_MINB / BGR_EXT_MINB override for experiments.
-    u32 scan_blocks_per_sm = 4, ext_blocks_per_sm = 6;  // greedy kernel: 6 CTAs (24 warps, 80 registers) measured 2 % ahead of 5
+    u32 scan_blocks_per_sm = 4, ext_blocks_per_sm = 6, exh_blocks_per_sm = 6;  // both extension kernels (exhaustive: 6.65 / 6.25 / 6.11 / 6.99 ms with 4 / 5 / 6 / 8 at configs[3]); greedy kernel: 6 CTAs (24 warps, 80 registers) measured 2 % ahead of 5
     bool scan_ws = true;  // tile scan in its warp-specialised form (BGR_SCAN=classic: the barrier-per-phase form)
     std::string err;
 };
@@ -219,9 +219,14 @@ int launch_extension(bgr_ctx* ctx, Slot& s, const BatchArgs& a) {
         case BGR_MODE_EXHAUSTIVE_PATH: {
             // persistent warps, one node of the depth-first search per lane and turn
             u32 blocks = (s.n + EXT_THREADS - 1) / EXT_THREADS;
-            const u32 maxb = (u32)ctx->sm_count * 5;
+            const u32 maxb = (u32)ctx->sm_count * ctx->exh_blocks_per_sm;
             if (blocks > maxb) blocks = maxb;
-            k_extend_exhaustive_nodes<5><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a);
+            switch (ctx->exh_blocks_per_sm) {
+                case 4: k_extend_exhaustive_nodes<4><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+                case 5: k_extend_exhaustive_nodes<5><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+                case 8: k_extend_exhaustive_nodes<8><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+                default: k_extend_exhaustive_nodes<6><<<blocks, EXT_THREADS, 0, s.stream>>>(ctx->ix, a); break;
+            }
             break;
         }
         case BGR_MODE_GREEDY_PATH: {
@@ -368,6 +373,10 @@ int bgr_ctx_create(int device, int n_slots, bgr_ctx** out) {
     if (const char* e = getenv("BGR_EXT_MINB")) {
         int v = atoi(e);
         if (v == 4 || v == 5 || v == 6 || v == 8) ctx->ext_blocks_per_sm = (u32)v;
+    }
+    if (const char* e = getenv("BGR_EXH_MINB")) {
+        int v = atoi(e);
+        if (v == 4 || v == 5 || v == 6 || v == 8) ctx->exh_blocks_per_sm = (u32)v;
     }
     for (int i = 0; i < n_slots; ++i) {
         Slot& s = ctx->slots[i];
