@@ -540,7 +540,7 @@ BGR_HD u32 verify_chunk(const DevIndex& ix, u64 w0, u64 w1, u32 hits) {
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------ tile scan kernel
 
-static const int ST_THREADS = 512;
+static const int ST_THREADS = 1024;
 static const u32 WS_WORKERS = ST_THREADS - 32;  // worker threads of the warp-specialised tile kernel
 
 // ------------------------------------------------------------------------------ minimizer tier, loads off the critical path
