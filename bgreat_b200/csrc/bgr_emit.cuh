@@ -305,9 +305,12 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB) k_extend_exhaustive_nodes(D
     ExtWarpShared& W = wsh_all[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31;
     const u32 list_n = a.scnt->list_n;
+    __shared__ i32 xf_all[XF_INTS * EXT_THREADS];  // the lanes' list heads and parked frames (ExhaustiveState::fast)
+    static_assert(XF_STRIDE == (u32)EXT_THREADS, "a lane's entries are one CTA width apart");
     ExhaustiveState g;
     g.phase = XP_DONE;
     g.sc.overflow = false;
+    g.fast = xf_all + threadIdx.x;
     bool have = false;
     u32 r = 0, t = 0;
     u32 chunk_base = 0, chunk_left = 0;

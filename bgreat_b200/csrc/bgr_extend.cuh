@@ -1016,6 +1016,9 @@ BGR_HD u32 exhaustive_read(const DevIndex& ix, const BatchArgs& a, u32 r, Scratc
 // procedure; tests/emu runs both and compares.
 enum { XP_SEED = 0, XP_LEFT = 1, XP_RIGHT = 2, XP_DONE = 3 };
 
+// shared-memory part of ExhaustiveState's lists (see there): ints per lane, and the distance between a lane's entries
+static const u32 XF_LIST = 8, XF_FRAMES = 4, XF_INTS = 2 * XF_LIST + 4 * XF_FRAMES, XF_STRIDE = 128;
+
 struct ExhaustiveState {
     ReadSetup s;
     Scratch sc;
@@ -1038,6 +1041,32 @@ struct ExhaustiveState {
     bool f_canon;
     i32 f_pos;
     u32 f_acc, f_next;
+    // The first XF_LIST entries of the current / best id lists and the first XF_FRAMES parked frames live in shared
+    // memory when the kernel provides it (fast: this lane's column, entry e at fast[e * XF_STRIDE]); deeper entries,
+    // and everything in the host emulator (fast == nullptr), in the scratch row. In global memory these few ints
+    // were a quarter of the kernel's instructions and a fifth of its stalls: copies of a handful of ids, with two
+    // or three lanes of the warp active and an L2 round trip per int (profiles/r02b_lines_k_extend_exhaustive_*.txt).
+    i32* fast;
+    BGR_HD i32 cur_get(u32 j) const { return (fast && j < XF_LIST) ? fast[j * XF_STRIDE] : sc.get(lay.cur0 + j); }
+    BGR_HD void cur_set(u32 j, i32 x) {
+        if (fast && j < XF_LIST) fast[j * XF_STRIDE] = x;
+        else sc.set(lay.cur0 + j, x);
+    }
+    BGR_HD i32 best_get(u32 j) const {
+        return (fast && j < XF_LIST) ? fast[(XF_LIST + j) * XF_STRIDE] : sc.get(lay.best0 + j);
+    }
+    BGR_HD void best_set(u32 j, i32 x) {
+        if (fast && j < XF_LIST) fast[(XF_LIST + j) * XF_STRIDE] = x;
+        else sc.set(lay.best0 + j, x);
+    }
+    // frame d, field f (0: slot | canon bit, 1: pos, 2: acc, 3: next candidate)
+    BGR_HD i32 frame_get(u32 d, u32 f) const {
+        return (fast && d < XF_FRAMES) ? fast[(2 * XF_LIST + 4 * d + f) * XF_STRIDE] : sc.get(lay.fr0 + 5 * d + (f ? f + 1 : 0));
+    }
+    BGR_HD void frame_set(u32 d, u32 f, i32 x) {
+        if (fast && d < XF_FRAMES) fast[(2 * XF_LIST + 4 * d + f) * XF_STRIDE] = x;
+        else sc.set(lay.fr0 + 5 * d + (f ? f + 1 : 0), x);
+    }
 
     BGR_HD bool done() const { return phase == XP_DONE; }
 
@@ -1121,13 +1150,13 @@ struct ExhaustiveState {
     BGR_HD void pop_frame() {
         --depth;
         if (depth >= 0) {
-            const u32 b = lay.fr0 + 5 * (u32)depth;
-            const u32 sc0 = (u32)sc.get(b);
+            const u32 d = (u32)depth;
+            const u32 sc0 = (u32)frame_get(d, 0);
             f_slot = (sc0 & 0x7FFFFFFFu) == 0x7FFFFFFFu ? NO_SLOT : (sc0 & 0x7FFFFFFFu);
             f_canon = (sc0 >> 31) != 0;
-            f_pos = sc.get(b + 2);
-            f_acc = (u32)sc.get(b + 3);
-            f_next = (u32)sc.get(b + 4);
+            f_pos = frame_get(d, 1);
+            f_acc = (u32)frame_get(d, 2);
+            f_next = (u32)frame_get(d, 3);
         }
     }
 
@@ -1148,11 +1177,11 @@ struct ExhaustiveState {
         if (phase == XP_LEFT) {
             // left part in output order: [offset] then the ids from the far end to the anchor
             if (term >= 0) sc.set(w++, term);
-            for (u32 j = 0; j < best_n; ++j) sc.set(w++, sc.get(lay.best0 + best_n - 1 - j));
+            for (u32 j = 0; j < best_n; ++j) sc.set(w++, best_get(best_n - 1 - j));
             eb = best_total;
             begin_side(true, a.errors - eb);
         } else {
-            for (u32 j = 0; j < best_n; ++j) sc.set(w++, sc.get(lay.best0 + j));
+            for (u32 j = 0; j < best_n; ++j) sc.set(w++, best_get(j));
             sc.set(w++, term);
             n = w;
             flags |= BGR_F_MAPPED | BGR_F_CNT_ALIGNED;
@@ -1179,7 +1208,7 @@ struct ExhaustiveState {
                 best_total = f_acc;
                 best_n = (u32)depth;
                 term = right ? 0 : -1;
-                for (u32 j = 0; j < best_n; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
+                for (u32 j = 0; j < best_n; ++j) best_set(j, cur_get(j));
             }
             query = false;
         } else if (f_acc >= best_total) {
@@ -1236,8 +1265,8 @@ struct ExhaustiveState {
                     best_total = f_acc + miss[i];
                     best_n = (u32)depth + 1;
                     term = right ? rl + km1 : L - rl;
-                    for (u32 j = 0; j < (u32)depth; ++j) sc.set(lay.best0 + j, sc.get(lay.cur0 + j));
-                    sc.set(lay.best0 + (u32)depth, u.sid);
+                    for (u32 j = 0; j < (u32)depth; ++j) best_set(j, cur_get(j));
+                    best_set((u32)depth, u.sid);
                 }
             } else if (miss[i] <= cap) {
                 if ((u32)depth + 1 >= lay.D) {  // search stack too small: give up, the host grows the scratch
@@ -1247,12 +1276,12 @@ struct ExhaustiveState {
                     return;
                 }
                 // park this frame (resume with candidate i+1), make the child the top frame
-                const u32 b = lay.fr0 + 5 * (u32)depth;
-                sc.set(b, (i32)((f_slot & 0x7FFFFFFFu) | (f_canon ? 0x80000000u : 0u)));
-                sc.set(b + 2, f_pos);
-                sc.set(b + 3, (i32)f_acc);
-                sc.set(b + 4, (i32)(i + 1));
-                sc.set(lay.cur0 + (u32)depth, u.sid);
+                const u32 d = (u32)depth;
+                frame_set(d, 0, (i32)((f_slot & 0x7FFFFFFFu) | (f_canon ? 0x80000000u : 0u)));
+                frame_set(d, 1, f_pos);
+                frame_set(d, 2, (i32)f_acc);
+                frame_set(d, 3, (i32)(i + 1));
+                cur_set(d, u.sid);
                 next_query(sl[i], f_canon, f_slot, f_canon);
                 f_pos = right ? f_pos + L : f_pos - L;
                 f_acc += miss[i];

@@ -280,6 +280,10 @@ extern "C" int emu_map2(const char* useqs, const uint64_t* uoff, uint32_t nu, ui
         } else if (mode == BGR_MODE_EXHAUSTIVE || mode == BGR_MODE_EXHAUSTIVE_PATH) {
             // the persistent kernel's per-lane life cycle: start, one search node per step until done
             ExhaustiveState x;
+            // the kernel's shared-memory list heads (ExhaustiveState::fast): a host buffer for every other read, none
+            // for the rest, so that both placements of the lists are single-stepped
+            std::vector<i32> fastbuf((size_t)XF_INTS * XF_STRIDE, 0);
+            x.fast = (r & 1u) ? fastbuf.data() : nullptr;
             x.start(ix, a, r, sc.base);
             while (!x.done()) x.step(ix, a);
             flags = x.flags;
