@@ -28,7 +28,7 @@ import json, sys
 try:
     d = json.load(open(sys.argv[1]))
     print({k: d.get(k) for k in ("value", "ms_per_step")}, d.get("kernel_ms_per_pass"), (d.get("e2e") or {}).get("value"),
-          {k: round(v["frac"], 3) for k, v in (d.get("roofline") or {}).get("kernels", {}).items()},
+          {k: (None if v["frac"] is None else round(v["frac"], 3)) for k, v in (d.get("roofline") or {}).get("kernels", {}).items()},
           (d.get("cpu_baseline") or {}).get("value"), (d.get("cli") or {}).get("reads_per_s_mapping"))
 except Exception as e:
     print("unreadable:", e)
