@@ -117,6 +117,30 @@ def test_staged_scan_chunks_with_more_runs_than_slots(bg, monkeypatch):
         al.close()
 
 
+def test_staged_scan_mixed_lengths(bg, monkeypatch):
+    """Minimizer tier with read lengths around every boundary of the staged scan: one window (k-1 bases), a chunk of
+    fewer than 32 windows, exactly 32 / 33 windows (61 / 62 bases), the last chunk of one window, long reads"""
+    monkeypatch.setenv("BGR_BLOOM", "global")
+    rng = random.Random(79)
+    unitigs, haps = S.make_graph(rng, 31, genome_len=20000, mean_unitig=60, n_variants=130)
+    reads = []
+    for ln in (30, 31, 33, 60, 61, 62, 63, 93, 94, 100, 125, 126, 150, 151, 250, 400):
+        reads += S.make_reads(rng, haps, 400, ln, sub_rate=0.01, n_rate=0.0003)
+    rng.shuffle(reads)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(31, 2, 2, unitigs, reads, mode)
+        al = bg.Aligner(31, 2, 2)
+        al.index_unitigs(unitigs)
+        got = al.align_batch(reads, mode).as_tuples()
+        bad = [i for i in range(len(reads)) if got[i] != want[i]]
+        assert not bad, (len(bad), bad[:5], [(len(reads[i]), got[i], want[i]) for i in bad[:3]])
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        assert al.align_batch_packed(reads, mode, threads=2).as_tuples() == want
+        al.close()
+
+
 def test_staged_scan_many_borders_per_chunk(bg, monkeypatch):
     """Minimizer tier: unitigs a few bases long, so that a chunk of 32 windows holds eight or more border keys and the
     warp's joint verification (verify_warp: four survivors per lane and round) takes several rounds"""
