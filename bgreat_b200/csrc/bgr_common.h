@@ -100,7 +100,7 @@ struct BlobHeader {
     u32 pad;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
-static const u32 BLOB_VERSION = 6;  // 6: minimizer filter's bit pattern from mm_pat_hash
+static const u32 BLOB_VERSION = 7;  // 6: minimizer filter's bit pattern from mm_pat_hash; 7: so the single-hash filter of 31-mers
 
 // 2-bit code of a base character, A0 C1 G2 T3 (utils.cpp:117-129). Returns 4 for anything else.
 BGR_HD u32 base_code(unsigned char c) {
@@ -283,9 +283,16 @@ BGR_HD u32 mm_min_hash(u64 key) {
 }
 
 // word index and bit pattern of a canonical key (the index builders; km1 = k-1): word modes
+// Single-hash tier of 31-mers: the hash is mm_pat_hash of the (k-1)-mer's first 16-mer and of the reverse complement
+// of its last one instead of bloom_h1 of the two 60-bit codes -- the same on both strands, and the tile scan gets the
+// two words as slices of a chunk's packed words without rolling the codes (scan_chunk_slices).
+BGR_HD u32 bloom_h1_of(u64 x, u64 r, u32 km1, bool two_hashes) {
+    if (!two_hashes && km1 == MM_KM1) return mm_pat_hash((u32)(x >> (2 * (MM_KM1 - MM_M))), (u32)(r >> (2 * (MM_KM1 - MM_M))));
+    return bloom_h1(x, r);
+}
 BGR_HD void bloom_slot(u64 key, u32 km1, bool two_hashes, u32 n_bloom, u32& word, u32& pattern) {
     const u64 r = rcb(key, km1);
-    const u32 h1 = bloom_h1(key, r);
+    const u32 h1 = bloom_h1_of(key, r, km1, two_hashes);
     word = bloom_word_of(h1, n_bloom);
     pattern = bloom_pattern(bloom_pidx(two_hashes ? bloom_h2(key, r) : h1));
 }

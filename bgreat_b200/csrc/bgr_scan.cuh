@@ -417,7 +417,7 @@ BGR_HD u32 scan_chunk(const u32* bloom, u32 n_bloom, const u32* pat, u32 km1_rt,
 #pragma unroll
     for (u32 j = 0; j < 32; ++j) {
         // symmetric in (num, rc): no canonical minimum needed
-        const u32 h1 = bloom_h1(num, rc);
+        const u32 h1 = bloom_h1_of(num, rc, km1, TWO);
         const u32 m = pat[bloom_pidx(TWO ? bloom_h2(num, rc) : h1)];
         const u32 w = bloom[bloom_word_of(h1, n_bloom)];
         hits |= ((w & m) == m ? 1u : 0u) << j;
@@ -706,6 +706,30 @@ __device__ __forceinline__ u32 mm_test_windows(const u64* pat, u64 w0, u64 w1, u
 
 __device__ __noinline__ bool index_has_far(const DevIndex& ix, u64 key) { return index_has(ix, key); }
 
+// scan_chunk<false, 30> without the rolling codes: the single-hash filter of 31-mers is addressed by mm_pat_hash of a
+// window's first 16-mer and of the reverse complement of its last one (bloom_h1_of), both slices of the chunk's two
+// packed words and of their reverse complements. 14 instructions per window against 24 (the shared-memory tier is
+// bound by the integer pipes).
+template <u32 J>
+struct SliceTest {
+    static __device__ __forceinline__ void run(const u32* bloom, u32 n_bloom, const u32* pat, u32 A, u32 B, u32 C, u32 D, u32 E,
+                                               u32 F, u32 G, u32 H, u32& hits) {
+        const u32 h1 = mm_pat_hash(mm_s_at<J>(A, B, C, D), mm_r_at<J + MM_W - 1>(E, F, G, H));
+        const u32 m = pat[bloom_pidx(h1)];
+        const u32 w = bloom[bloom_word_of(h1, n_bloom)];
+        hits |= ((w & m) == m ? 1u : 0u) << J;
+        if constexpr (J + 1 < 32) SliceTest<J + 1>::run(bloom, n_bloom, pat, A, B, C, D, E, F, G, H, hits);
+    }
+};
+__device__ __forceinline__ u32 scan_chunk_slices(const u32* bloom, u32 n_bloom, const u32* pat, u64 w0, u64 w1, u32 count) {
+    const u32 A = (u32)(w0 >> 32), B = (u32)w0, C = (u32)(w1 >> 32), D = (u32)w1;
+    const u64 R0 = rc64(w0), R1 = rc64(w1);
+    const u32 E = (u32)(R1 >> 32), F = (u32)R1, G = (u32)(R0 >> 32), H = (u32)R0;
+    u32 hits = 0;
+    SliceTest<0>::run(bloom, n_bloom, pat, A, B, C, D, E, F, G, H, hits);
+    return count >= 32 ? hits : hits & ((1u << count) - 1);
+}
+
 // The windows of the warp's 32 chunks that passed the filter, checked against the key table: all lanes call this
 // (hits = 0 for a lane without a chunk); the returned mask is exact.
 __device__ __forceinline__ u32 verify_warp(const DevIndex& ix, const u32 km1, VerifyQueue& Q, const u32 lane, const u64 w0,
@@ -816,7 +840,8 @@ __host__ __device__ inline size_t tile_smem_bytes(u32 bloom_words_in_smem, u32 t
 // tile's offsets / chunk prefix sums / flag words in shared memory and its characters (or 2-bit words) at cb,
 // whose first base is base gs of the batch. Packs, stores the words for the extension kernel, scans, verifies,
 // stores the hit mask and flags the read. Returns the number of windows that passed the filter.
-template <bool BLOOM_SMEM, bool PACKED, u32 KM1S>
+// SLICES: the single-hash filter of 31-mers tested from slices (scan_chunk_slices) instead of rolling codes
+template <bool BLOOM_SMEM, bool PACKED, u32 KM1S, bool SLICES = false>
 __device__ __forceinline__ u32 tile_chunk(const DevIndex& ix, const BatchArgs& a, const u32* bloom, const u32* pat,
                                           const u32 km1, const unsigned char* cb, const u64 gs, const u64* s_off,
                                           const u32* s_prefix, u32* s_flags, const u32 cnt, const u32 r0, const u32 j) {
@@ -854,6 +879,7 @@ __device__ __forceinline__ u32 tile_chunk(const DevIndex& ix, const BatchArgs& a
     // k the two-hash word filter (bloom_layout)
     u32 hits;
     if (!BLOOM_SMEM && KM1S == MM_KM1) hits = scan_chunk_mm((const u64*)bloom, ix.n_bloom / 2, (const u64*)pat, w0, w1, count);
+    else if (SLICES && BLOOM_SMEM && KM1S == MM_KM1) hits = scan_chunk_slices(bloom, ix.n_bloom, pat, w0, w1, count);
     else hits = scan_chunk<!BLOOM_SMEM, KM1S>(bloom, ix.n_bloom, pat, km1, w0, w1, count);
     const u32 passed = (u32)__popc(hits);
     hits = verify_chunk<1>(ix, w0, w1, hits);
@@ -1388,7 +1414,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_scan_tiles_ws(DevIndex ix, Ba
                                                           jb + wtid, jb + wtid < T, s_slots + wtid, s_vq[warp - 1], lane);
                 } else {
                     for (u32 j = wtid; j < T; j += WS_WORKERS)
-                        c_verify += tile_chunk<BLOOM_SMEM, PACKED, KM1S>(ix, a, bloom, s_pat, km1, cb, gs, m.off, m.prefix,
+                        c_verify += tile_chunk<BLOOM_SMEM, PACKED, KM1S, true>(ix, a, bloom, s_pat, km1, cb, gs, m.off, m.prefix,
                                                                           m.flags, cnt, r0, j);
                 }
             }
