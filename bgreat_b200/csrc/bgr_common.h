@@ -100,7 +100,7 @@ struct BlobHeader {
     u32 pad;
 };
 static const u64 BLOB_MAGIC = 0x3030324252474221ull;  // "!BGRB200"
-static const u32 BLOB_VERSION = 7;  // 6: minimizer filter's bit pattern from mm_pat_hash; 7: so the single-hash filter of 31-mers
+static const u32 BLOB_VERSION = 8;  // 6: minimizer filter's bit pattern from mm_pat_hash; 7: so the single-hash filter of 31-mers; 8: four bits per key in a minimizer block
 
 // 2-bit code of a base character, A0 C1 G2 T3 (utils.cpp:117-129). Returns 4 for anything else.
 BGR_HD u32 base_code(unsigned char c) {
@@ -231,7 +231,7 @@ BGR_HD u32 bloom_word_of(u32 h1, u32 n_bloom) {
 //                     16-mer and its reverse complement). Consecutive windows of a read mostly share their
 //                     minimizer, so the scan fetches a block once per run of ~8 windows instead of once per window
 //                     (the L2 sector rate was what bound the scan on large indexes: 1.6 G sectors per 10 M reads,
-//                     profiles/r01_ncu_k_scan_tiles_v9_1Gbp.txt). Inside the block a key sets 3 of 64 bits, chosen
+//                     profiles/r01_ncu_k_scan_tiles_v9_1Gbp.txt). Inside the block a key sets 4 of 64 bits, chosen
 //                     by mm_pat_hash of its first and last 16-mer.
 enum { BLOOM_SMEM_1HASH = 0, BLOOM_WORDS_2HASH = 1, BLOOM_MINIMIZER = 2 };
 static const u32 MM_M = 16;       // minimizer length: a 16-mer is one 32-bit word
@@ -255,7 +255,7 @@ BGR_HD u32 mm_block(u32 hmin, u32 n_blocks) {
     return (u32)(((u64)(u32)(hmin * 0x85EBCA77u) * (u64)n_blocks) >> 32);
 #endif
 }
-// pattern i: three distinct bits of a 64-bit block
+// pattern i: four distinct bits of a 64-bit block
 BGR_HD u64 bloom_pattern64(u32 i) {
     u32 r = (i + 1) * 0x9E3779B1u;
     r ^= r >> 16;
@@ -267,7 +267,20 @@ BGR_HD u64 bloom_pattern64(u32 i) {
     u32 b2 = ((r >> 16) & 1023) % 62;
     if (b2 >= lo) ++b2;
     if (b2 >= hi) ++b2;
-    return (1ull << b0) | (1ull << b1) | (1ull << b2);
+    u64 p = (1ull << b0) | (1ull << b1) | (1ull << b2);
+    // a fourth bit, distinct from the three: the ((r >> 26) % 61)-th clear bit of p. Four bits instead of three take
+    // the windows of a 3 Gbp index that pass the filter from 3.34 to 2.96 per read (each one a random read of HBM).
+    u32 skip = (r >> 26) % 61;
+    for (u32 b = 0; b < 64; ++b) {
+        if (!((p >> b) & 1)) {
+            if (skip == 0) {
+                p |= 1ull << b;
+                break;
+            }
+            --skip;
+        }
+    }
+    return p;
 }
 // smallest 16-mer hash of a 30-mer code
 BGR_HD u32 mm_min_hash(u64 key) {
