@@ -36,6 +36,12 @@ def main():
            "ncu summaries (`ncu --set full --clock-control none`, one launch of 10 M reads after warm-up launches; "
            "`tools/gpu_profile.sh`, condensed by `tools/ncu_summary.py`) and bench lines (`bench.py`). "
            "Regenerate this file with `python tools/profiles_readme.py`.", "",
+           "File name prefixes: `r01_` round 1; `r02_` round 2 up to the first full measurement set (and the round's "
+           "experiment records: `r02_scan_experiments.txt`, `r02_hbm_random*`); `r02b_` the set after the staged seed "
+           "scan (plus the 2-GPU line, the sanitizer runs and the exhaustive kernel before / after its shared-memory "
+           "lists); `r02c_` the round's last full set (every config, ncu of every kernel, launch list); `r02d_` / `r02e_` "
+           "single lines taken after the last two filter changes (configs[1] with the slice-addressed shared-memory "
+           "filter; the default 3 Gbp line with four filter bits per key).", "",
            "## Kernels", "",
            "| file | kernel | ms | DRAM GB/s (rd+wr) | DRAM bytes/read | L2 hit % | ld sectors/request | issue active % | threads/inst | regs | top stall |",
            "|---|---|---|---|---|---|---|---|---|---|---|"]
