@@ -88,6 +88,28 @@ def test_large_index_filter_tier(bg, monkeypatch):
         al.close()
 
 
+@pytest.mark.parametrize("env", [{"BGR_SCAN": "classic"}, {"BGR_SCAN": "classic", "BGR_BLOOM": "global"},
+                                 {"BGR_SCAN_MM": "inline", "BGR_BLOOM": "global"}],
+                         ids=["classic-smem", "classic-minimizer", "ws-minimizer-inline"])
+def test_other_scan_schedules_agree(bg, monkeypatch, env):
+    """The comparison forms of the tile scan -- CTA-wide barriers between the phases (BGR_SCAN=classic, the schedule
+    compute-sanitizer's racecheck models completely) on both filter tiers, and the warp-specialised kernel with the
+    minimizer blocks loaded where they are tested (BGR_SCAN_MM=inline) -- give the oracle's results too"""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    unitigs, reads = _k31_case(11, 3000)
+    for mode in (O.GREEDY, O.EXHAUSTIVE):
+        want, wc = oracle_results(31, 2, 2, unitigs, reads, mode)
+        al = bg.Aligner(31, 2, 2)
+        al.index_unitigs(unitigs)
+        assert al.align_batch(reads, mode).as_tuples() == want
+        gc = al.counters()
+        for name in COUNTERS:
+            assert gc[name] == wc[name]
+        assert al.align_batch_packed(reads, mode, threads=2).as_tuples() == want
+        al.close()
+
+
 def test_staged_scan_chunks_with_more_runs_than_slots(bg, monkeypatch):
     """Minimizer tier, staged scan (bgr_scan.cuh: mm_stage_blocks keeps ten block slots per chunk): reads cut from a
     sequence built so that the minimizer changes at every third window; four chunks in ten have more runs than slots
